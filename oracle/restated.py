@@ -1,0 +1,494 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (the oracle) of MoDA's articulated volume renderer.
+
+This file is the checker for the CUDA path in ``moda_b200/``; it is never imported by the product
+(only by ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl
+reference`` legs).  It needs only torch (CPU) and works in fp32 or fp64 (dtype follows the inputs).
+Gradients come from torch autograd on this restatement.
+
+Parity status: PINNED BY EXECUTING THE REFERENCE.  The reference has no tests or golden vectors of
+its own for this path; ``oracle/make_golden.py`` runs the real reference code
+(imported from /root/reference in the build container) on the seeded inputs of
+``moda_b200/synth.py`` and commits its outputs and gradients under ``tests/golden/``;
+``tests/test_oracle.py`` checks this restatement against those files (and against the live
+reference when /root/reference is present).
+
+Each function cites the reference lines it restates (paths relative to /root/reference).  The
+functional style (state dicts instead of nn.Modules) is this repo's own; op order within a formula
+follows the reference so that fp32 results agree to rounding.  Chunk sizes are the reference's
+(4096 / 8192 rays) so that timing this file is a fair stand-in for timing the reference on a CPU.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------------
+# positional encoding -- nnutils/nerf.py:35-75
+
+
+def pe_window(n_freqs, alpha, dtype=torch.float32, device=None):
+    """nerf.py:63-66: w_k = 0.5 * (1 + cos(pi * clamp(alpha - k, 0, 1) + pi))."""
+    k = torch.arange(n_freqs, dtype=dtype, device=device)
+    return 0.5 * (1 + torch.cos(math.pi * torch.clamp(alpha - k, 0.0, 1.0) + math.pi))
+
+
+def embed(x, n_freqs, alpha=None):
+    """nerf.py:47-75.  Layout: [x | w0 sin(x) | w0 cos(x) | w1 sin(2x) | w1 cos(2x) | ...]."""
+    if n_freqs <= 0:
+        return x
+    if alpha is None:
+        alpha = n_freqs
+    c = x.shape[-1]
+    flat = x.reshape(-1, c)
+    win = pe_window(n_freqs, float(alpha), dtype=x.dtype, device=x.device)
+    parts = [flat]
+    for k in range(n_freqs):
+        f = float(2 ** k)
+        parts.append(win[k] * torch.sin(f * flat))
+        parts.append(win[k] * torch.cos(f * flat))
+    return torch.cat(parts, -1).reshape(x.shape[:-1] + (c * (1 + 2 * n_freqs),))
+
+
+# ------------------------------------------------------------------------------------------------
+# the D x W MLP -- nnutils/nerf.py:147-198
+
+
+class NerfSpec:
+    """Shape description of one ``NeRF`` instance (nerf.py:84-105)."""
+
+    def __init__(self, D=8, W=256, in_channels_xyz=63, in_channels_dir=27, out_channels=3,
+                 skips=(4,), raw_feat=False):
+        self.D, self.W = D, W
+        self.in_channels_xyz, self.in_channels_dir = in_channels_xyz, in_channels_dir
+        self.out_channels, self.skips, self.raw_feat = out_channels, tuple(skips), raw_feat
+
+
+COARSE_SPEC = NerfSpec(8, 256, 63, 27 + 64, 3, (4,), False)
+SKIN_SPEC = NerfSpec(5, 64, 63 + 128, 0, 25, (4,), True)
+
+
+def nerf_forward(sd, spec, x, sigma_only=False):
+    """nerf.py:163-198.  ``sd`` uses the reference's state-dict names."""
+    cx = spec.in_channels_xyz
+    inp = x[..., :cx]
+    h = inp
+    for i in range(spec.D):
+        if i in spec.skips:
+            h = torch.cat([inp, h], -1)
+        h = torch.relu(F.linear(h, sd["xyz_encoding_%d.0.weight" % (i + 1)],
+                                sd["xyz_encoding_%d.0.bias" % (i + 1)]))
+    sigma = F.linear(h, sd["sigma.weight"], sd["sigma.bias"])
+    if sigma_only:
+        return sigma
+    fin = F.linear(h, sd["xyz_encoding_final.weight"], sd["xyz_encoding_final.bias"])
+    d_in = torch.cat([fin, x[..., cx:cx + spec.in_channels_dir]], -1)
+    dfe = torch.relu(F.linear(d_in, sd["dir_encoding.0.weight"], sd["dir_encoding.0.bias"]))
+    rgb = F.linear(dfe, sd["rgb.0.weight"], sd["rgb.0.bias"])
+    if spec.raw_feat:
+        return rgb
+    return torch.cat([torch.sigmoid(rgb), sigma], -1)
+
+
+def evaluate_mlp(sd, spec, pts, n_freqs=None, alpha=None, dir_embedded=None, code=None,
+                 chunk=32 * 1024, sigma_only=False):
+    """geom_utils.py:19-57: ray-chunked [PE | dir | code] assembly then the MLP.
+
+    pts (R,S,k); dir_embedded (R,S,c) or None; code (R,c) / (R,1,c) / (1,c) or None.
+    """
+    R, S, _ = pts.shape
+    if code is not None and code.dim() == 2 and code.shape[0] != R:
+        code = code.repeat(R, 1)
+    outs = []
+    for i in range(0, R, chunk):
+        e = pts[i:i + chunk]
+        if n_freqs is not None:
+            e = embed(e, n_freqs, alpha)
+        if dir_embedded is not None:
+            e = torch.cat([e, dir_embedded[i:i + chunk]], -1)
+        if code is not None:
+            cc = code[i:i + chunk]
+            if cc.dim() == 2:
+                cc = cc[:, None]
+            e = torch.cat([e, cc.repeat(1, S, 1)], -1)
+        outs.append(nerf_forward(sd, spec, e, sigma_only=sigma_only))
+    return torch.cat(outs, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# quaternion helpers -- third_party/pytorch3d/pytorch3d/transforms/rotation_conversions.py
+
+
+def quat_to_matrix(q):
+    """rotation_conversions.py:41-69 (two_s = 2/|q|^2: no normalisation required)."""
+    r, i, j, k = q.unbind(-1)
+    two_s = 2.0 / (q * q).sum(-1)
+    m = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return m.reshape(q.shape[:-1] + (3, 3))
+
+
+def quat_raw_mul(a, b):
+    """rotation_conversions.py:374-392 (Hamilton product, real part first)."""
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = b.unbind(-1)
+    return torch.stack((aw * bw - ax * bx - ay * by - az * bz,
+                        aw * bx + ax * bw + ay * bz - az * by,
+                        aw * by - ax * bz + ay * bw + az * bx,
+                        aw * bz + ax * by - ay * bx + az * bw), -1)
+
+
+def quat_mul_std(a, b):
+    """rotation_conversions.py:359-409: product flipped so that the real part is >= 0."""
+    ab = quat_raw_mul(a, b)
+    return torch.where(ab[..., 0:1] < 0, -ab, ab)
+
+
+# ------------------------------------------------------------------------------------------------
+# dual quaternions -- nnutils/dual_quat.py
+
+
+def q_normalize(q):
+    """dual_quat.py:4-12."""
+    return q / torch.sqrt((q * q).sum(-1))[..., None]
+
+
+def q_mul(q1, q2):
+    """dual_quat.py:14-31 (== q1 (x) q2, verified against the outer-product form)."""
+    return quat_raw_mul(q1, q2)
+
+
+def dq_mul(a, b):
+    """dual_quat.py:33-49: (r1 r2, r1 d2 + d1 r2)."""
+    ar, ad = a[..., :4], a[..., 4:]
+    br, bd = b[..., :4], b[..., 4:]
+    return torch.cat([q_mul(ar, br), q_mul(ar, bd) + q_mul(ad, br)], -1)
+
+
+def dq_normalize(dq):
+    """dual_quat.py:51-62: all 8 components divided by the norm of the real quaternion."""
+    return dq / torch.norm(dq[..., :4], dim=-1, keepdim=True)
+
+
+_CONJ_Q = (1.0, -1.0, -1.0, -1.0, 1.0, -1.0, -1.0, -1.0)
+_CONJ_C = (1.0, -1.0, -1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
+
+
+def dq_quaternion_conjugate(dq):
+    """dual_quat.py:65-74."""
+    return dq * torch.tensor(_CONJ_Q, dtype=dq.dtype, device=dq.device)
+
+
+def dq_combined_conjugate(dq):
+    """dual_quat.py:76-85."""
+    return dq * torch.tensor(_CONJ_C, dtype=dq.dtype, device=dq.device)
+
+
+def dq_inverse(dq):
+    """dual_quat.py:87-93: conj_q(dq) / |r|^2."""
+    return dq_quaternion_conjugate(dq) / (dq[..., :4] ** 2).sum(-1, keepdim=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Gaussian bones, skinning weights, DQ blending -- nnutils/geom_utils.py
+
+
+def bone_transform(bones, rts):
+    """geom_utils.py:59-111, neudbs branch 73-86.  bones (...,B,10), rts (R, B*8) -> (R,B,10)."""
+    B = bones.shape[-2]
+    b = bones.reshape(-1, B, 10)
+    rts = rts.reshape(-1, B, 8)
+    R = rts.shape[0]
+    qr, qd = rts[..., :4], rts[..., 4:]
+    rot = quat_to_matrix(qr)
+    conj = qr * torch.tensor((1.0, -1.0, -1.0, -1.0), dtype=qr.dtype, device=qr.device)
+    trn = (2 * quat_raw_mul(qd, conj))[..., 1:]
+    center = rot.matmul(b[:, :, :3, None])[..., 0] + trn
+    orient = quat_mul_std(qr, b[:, :, 3:7])
+    scale = b[:, :, 7:10].repeat(R // b.shape[0], 1, 1) if b.shape[0] != R else b[:, :, 7:10]
+    return torch.cat([center, orient, scale], -1)
+
+
+def vec_to_sim3(vec):
+    """geom_utils.py:187-199."""
+    center = vec[..., :3]
+    orient = quat_to_matrix(F.normalize(vec[..., 3:7], 2, -1))
+    scale = vec[..., 7:10].exp()
+    return center, orient, scale
+
+
+def _skinning_chunk(bones, pts, dskin, skin_aux):
+    """geom_utils.py:237-277."""
+    R, S, _ = pts.shape
+    B = bones.shape[-2]
+    center, orient, scale = vec_to_sim3(bones)
+    orient_t = orient.permute(0, 1, 3, 2)
+    diff = center.view(R, 1, B, 3) - pts.view(R, S, 1, 3)
+    # axis_rotate (geom_utils.py:231-235): rows of R^T dotted with diff
+    m = (orient_t.view(R, 1, B, 3, 3) * diff.view(R, S, B, 1, 3)).sum(4)
+    m = scale.view(R, 1, B, 3) * m.pow(2)
+    m = m * 100 * skin_aux[0].exp()
+    logit = -10 * m.sum(3)
+    if dskin is not None:
+        logit = logit + dskin
+    return logit.softmax(2)
+
+
+def skinning(bones, pts, dskin=None, skin_aux=None, chunk=4096):
+    """geom_utils.py:280-302.  bones (B,10) or (R,B,10); pts (R,S,3) -> (R,S,B)."""
+    R = pts.shape[0]
+    B = bones.shape[-2]
+    if bones.dim() == 2:
+        bones = bones[None].repeat(R, 1, 1)
+    bones = bones.reshape(-1, B, 10)
+    out = []
+    for i in range(0, R, chunk):
+        out.append(_skinning_chunk(bones[i:i + chunk], pts[i:i + chunk],
+                                   None if dskin is None else dskin[i:i + chunk], skin_aux))
+    return torch.cat(out, 0)
+
+
+def gauss_mlp_skinning(xyz, n_freqs, alpha, bones, pose_code, skin_sd, skin_spec, skin_aux):
+    """geom_utils.py:202-229: Delta logits from nerf_skin(PE(xyz) | pose_code), then ``skinning``."""
+    R = xyz.shape[0]
+    if pose_code.dim() == 2 and pose_code.shape[0] != R:
+        pose_code = pose_code[None].repeat(R, 1, 1)
+    dskin = None
+    if skin_sd is not None:
+        dskin = evaluate_mlp(skin_sd, skin_spec, embed(xyz, n_freqs, alpha), code=pose_code,
+                             chunk=8 * 1024)
+    return skinning(bones, xyz, dskin, skin_aux)
+
+
+def _dqs_blend_chunk(dq, skin, pts):
+    """geom_utils.py:457-493."""
+    b = (skin[..., None] * dq[:, None]).sum(2)
+    c = dq_normalize(b)
+    a0, d0 = c[..., 0:1], c[..., 1:4]
+    ae, de = c[..., 4:5], c[..., 5:8]
+    trans = 2 * (a0 * de - ae * d0 + torch.cross(d0, de, dim=-1))
+    rot = pts + 2 * torch.cross(d0, torch.cross(d0, pts, dim=-1) + a0 * pts, dim=-1)
+    return rot + trans
+
+
+def dqs_blend_skinning(dq, skin, pts, chunk=4096):
+    """geom_utils.py:495-517."""
+    B = dq.shape[-2]
+    S = pts.shape[-2]
+    pts = pts.reshape(-1, S, 3)
+    dq = dq.reshape(-1, B, 8)
+    out = []
+    for i in range(0, pts.shape[0], chunk):
+        out.append(_dqs_blend_chunk(dq[i:i + chunk], skin[i:i + chunk], pts[i:i + chunk]))
+    return torch.cat(out, 0)
+
+
+def neu_dbs(bones, rts_fw, skin, xyz_in, backward=True):
+    """geom_utils.py:372-456 without the optional ``nerf_dis`` residual."""
+    B = bones.shape[-2]
+    rts = rts_fw.reshape(-1, B, 8)
+    bones_dfm = bone_transform(bones.reshape(-1, B, 10), rts)
+    dq = dq_inverse(rts) if backward else rts
+    return dqs_blend_skinning(dq, skin, xyz_in), bones_dfm
+
+
+# ------------------------------------------------------------------------------------------------
+# volume rendering -- nnutils/rendering.py
+
+
+def sample_depths(near, far, n_samples, use_disp=False, perturb=0.0, perturb_rand=None):
+    """rendering.py:68-83.  ``perturb_rand`` is the U[0,1) tensor the reference draws at :82."""
+    s = torch.linspace(0, 1, n_samples, device=near.device, dtype=near.dtype)
+    if not use_disp:
+        z = near * (1 - s) + far * s
+    else:
+        z = 1 / (1 / near * (1 - s) + 1 / far * s)
+    z = z.expand(near.shape[0], n_samples)
+    if perturb > 0:
+        mid = 0.5 * (z[:, :-1] + z[:, 1:])
+        upper = torch.cat([mid, z[:, -1:]], -1)
+        lower = torch.cat([z[:, :1], mid], -1)
+        if perturb_rand is None:
+            perturb_rand = torch.rand(z.shape, device=z.device, dtype=z.dtype)
+        z = lower + (upper - lower) * (perturb * perturb_rand)
+    return z
+
+
+def density_to_alpha(sigma_raw, deltas, beta):
+    """rendering.py:199-207 (VolSDF-style Laplace CDF of the signed distance -sigma)."""
+    ibeta = 1 / (beta.abs() + 1e-9)
+    sdf = -sigma_raw
+    dens = (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() * ibeta)) * ibeta
+    return 1 - torch.exp(-deltas * dens)
+
+
+def composite(rgbs, sigma_raw, z_vals, rays_d, beta, noise=None, alpha_mask=None):
+    """rendering.py:183-235.  Returns rgb (R,3), depth (R,), sil (R,), weights (R,S), visibility."""
+    deltas = z_vals[:, 1:] - z_vals[:, :-1]
+    deltas = torch.cat([deltas, 1e10 * torch.ones_like(deltas[:, :1])], -1)
+    deltas = deltas * torch.norm(rays_d.unsqueeze(1), dim=-1)
+    if noise is not None:
+        sigma_raw = sigma_raw + noise
+    alphas = density_to_alpha(sigma_raw, deltas, beta)
+    if alpha_mask is not None:  # rendering.py:210-215 (out-of-bound / invisible samples)
+        alphas = torch.where(alpha_mask, torch.zeros_like(alphas), alphas)
+    shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-10], -1)
+    trans = torch.cumprod(shifted, -1)[:, :-1]
+    weights = alphas * trans
+    rgb = (weights.unsqueeze(-1) * rgbs).sum(-2)
+    depth = (weights * z_vals).sum(-1)
+    sil = weights[:, :-1].sum(-1)
+    return rgb, depth, sil, weights, trans.detach()
+
+
+def sample_pdf(bins, weights, n_importance, det=False, eps=1e-5, u=None):
+    """rendering.py:582-623."""
+    R, n = weights.shape
+    weights = weights + eps
+    pdf = weights / weights.sum(-1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
+    if u is None:
+        if det:
+            u = torch.linspace(0, 1, n_importance, device=bins.device, dtype=bins.dtype).expand(R, n_importance)
+        else:
+            u = torch.rand(R, n_importance, device=bins.device, dtype=bins.dtype)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp_min(inds - 1, 0)
+    above = torch.clamp_max(inds, n)
+    ig = torch.stack([below, above], -1).view(R, 2 * n_importance)
+    cdf_g = torch.gather(cdf, 1, ig).view(R, n_importance, 2)
+    bins_g = torch.gather(bins, 1, ig).view(R, n_importance, 2)
+    denom = cdf_g[..., 1] - cdf_g[..., 0]
+    denom = torch.where(denom < eps, torch.ones_like(denom), denom)
+    return bins_g[..., 0] + (u - cdf_g[..., 0]) / denom * (bins_g[..., 1] - bins_g[..., 0])
+
+
+def _deform_and_render(prob, xyz, z_vals, dir_embedded, n_freqs, alpha, fine_iter, noise=None,
+                       vis_sd=None, vis_spec=None, obj_bound=None):
+    """rendering.py:239-579 restricted to the core path."""
+    rays = prob["rays"]
+    R, S, _ = xyz.shape
+    res = {}
+    xyz_frame = xyz
+    if prob.get("bones_rst") is not None:
+        bones_rst = prob["bones_rst"]
+        rts_fw = rays["bone_rts"]
+        skin_aux = prob["skin_aux"]
+        rest_code = prob["rest_pose_code"][0:1]  # rest_pose_code(LongTensor([0])), rendering.py:293-294
+        skin_sd = prob.get("nerf_skin")
+        spec = prob.get("skin_spec", SKIN_SPEC)
+        time_emb = rays["time_embedded"][:, None]
+        bones_dfm = bone_transform(bones_rst, rts_fw)
+        skin_bw = gauss_mlp_skinning(xyz, n_freqs, alpha, bones_dfm, time_emb, skin_sd, spec, skin_aux)
+        xyz, _ = neu_dbs(bones_rst, rts_fw, skin_bw, xyz, backward=True)
+        if fine_iter:
+            skin_fw = gauss_mlp_skinning(xyz, n_freqs, alpha, bones_rst, rest_code, skin_sd, spec, skin_aux)
+            xyz_cyc, _ = neu_dbs(bones_rst, rts_fw, skin_fw, xyz, backward=False)
+            cyc = (xyz_frame - xyz_cyc).norm(2, -1)
+    alpha_mask = None
+    if vis_sd is not None:  # render_vis branch, rendering.py:373-379, 210-215
+        vis_pred = evaluate_mlp(vis_sd, vis_spec, embed(xyz, n_freqs, alpha), chunk=32768)[..., 0].sigmoid()
+        cb = torch.as_tensor(obj_bound, dtype=xyz.dtype, device=xyz.device)[None, None]
+        alpha_mask = ((xyz.abs() > cb).sum(-1) > 0) | (vis_pred < 0.5)
+    dir_rep = dir_embedded[:, None].expand(R, S, dir_embedded.shape[-1])
+    out = evaluate_mlp(prob["coarse"], prob.get("coarse_spec", COARSE_SPEC), xyz, n_freqs, alpha,
+                       dir_embedded=dir_rep, code=rays.get("env_code"), chunk=4096)
+    rgbs, sig = out[..., :3], out[..., 3]
+    rgb, depth, sil, weights, vis = composite(rgbs, sig, z_vals, rays["rays_d"], prob["coarse"]["beta"],
+                                              noise=noise, alpha_mask=alpha_mask)
+    res["img_coarse"], res["depth_rnd"], res["sil_coarse"] = rgb, depth, sil
+    if vis_sd is not None:
+        res["vis_pred"] = (vis_pred * weights).sum(-1)
+    if fine_iter:
+        res["xyz_camera_vis"] = xyz_frame
+        if prob.get("bones_rst") is not None:
+            res["xyz_canonical_vis"] = xyz
+            res["frame_cyc_dis"] = (cyc * weights.detach()).sum(-1)
+    return res, weights
+
+
+def render_rays(prob, n_samples=128, use_disp=False, perturb=0.0, perturb_rand=None, noise=None,
+                use_fine=False, xyz_freqs=10, dir_freqs=4, alpha=10, vis_sd=None, vis_spec=None,
+                obj_bound=None, pdf_u=None):
+    """rendering.py:19-122.  ``prob`` is the dict of ``moda_b200.synth.make_problem``."""
+    rays = prob["rays"]
+    if use_fine:
+        n_samples = n_samples // 2
+    d = rays["rays_d"]
+    dir_embedded = embed(d / d.norm(2, -1)[:, None], dir_freqs, alpha)
+    z = sample_depths(rays["near"], rays["far"], n_samples, use_disp, perturb, perturb_rand)
+    xyz = rays["rays_o"].unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)
+    if use_fine:
+        with torch.no_grad():
+            _, w = _deform_and_render(prob, xyz, z, dir_embedded, xyz_freqs, alpha, False, noise=None,
+                                      vis_sd=None)
+        mid = 0.5 * (z[:, :-1] + z[:, 1:])
+        z_new = sample_pdf(mid, w[:, 1:-1], n_samples, det=(perturb == 0), u=pdf_u).detach()
+        z, _ = torch.sort(torch.cat([z, z_new], -1), -1)
+        xyz = rays["rays_o"].unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)
+    res, _ = _deform_and_render(prob, xyz, z, dir_embedded, xyz_freqs, alpha, True, noise=noise,
+                                vis_sd=vis_sd, vis_spec=vis_spec, obj_bound=obj_bound)
+    return res
+
+
+def parity_loss(res):
+    """The scalar used for gradient parity."""
+    return ((res["img_coarse"] - 0.3) ** 2).mean() + ((res["sil_coarse"] - 0.5) ** 2).mean() \
+        + res["frame_cyc_dis"].mean()
+
+
+def skin_warp_roundtrip(bones_rst, bone_rts, skin_aux, xyz):
+    """BASELINE config 4: Gaussian weights + backward warp, then weights + forward warp, no Delta MLP."""
+    bones_dfm = bone_transform(bones_rst, bone_rts)
+    w_bw = skinning(bones_dfm, xyz, None, skin_aux)
+    xyz_can, _ = neu_dbs(bones_rst, bone_rts, w_bw, xyz, backward=True)
+    w_fw = skinning(bones_rst, xyz_can, None, skin_aux)
+    xyz_cyc, _ = neu_dbs(bones_rst, bone_rts, w_fw, xyz_can, backward=False)
+    return xyz_can, xyz_cyc
+
+
+def density_grid(coarse_sd, grid_size, bound, spec=COARSE_SPEC, n_freqs=10, alpha=10, chunk=32768,
+                 x_range=None):
+    """train_utils.py:1377-1404: sigma on a G^3 lattice, (x,y,z) C-order, 32768-point chunks."""
+    G = grid_size
+    dt = coarse_sd["sigma.weight"].dtype
+    ax = [torch.linspace(-float(b), float(b), G, dtype=dt) for b in bound]
+    xs = ax[0] if x_range is None else ax[0][x_range[0]:x_range[1]]
+    pts = torch.stack(torch.meshgrid(xs, ax[1], ax[2], indexing="ij"), -1).reshape(-1, 3)
+    out = []
+    for i in range(0, pts.shape[0], chunk):
+        e = embed(pts[i:i + chunk], n_freqs, alpha)
+        out.append(nerf_forward(coarse_sd, spec, e, sigma_only=True))
+    return torch.cat(out, 0).reshape(len(xs), G, G)
+
+
+def to_dtype(prob, dtype):
+    """Deep-copies a synth problem to another dtype (fp64 oracle runs) with grads enabled on leaves."""
+    def conv(v):
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if torch.is_tensor(v) and v.is_floating_point():
+            return v.detach().clone().to(dtype)
+        return v
+    return conv(prob)
+
+
+GRAD_PARAMS = ("bones_rst", "skin_aux", "rest_pose_code")
+GRAD_RAYS = ("bone_rts", "time_embedded", "env_code", "rays_o", "rays_d")
+
+
+def require_grads(prob):
+    leaves = {}
+    for k in GRAD_PARAMS:
+        prob[k].requires_grad_(True)
+        leaves[k] = prob[k]
+    for net in ("coarse", "nerf_skin"):
+        for k, v in prob[net].items():
+            v.requires_grad_(True)
+            leaves[net + "." + k] = v
+    for k in GRAD_RAYS:
+        prob["rays"][k].requires_grad_(True)
+        leaves["rays." + k] = prob["rays"][k]
+    return leaves

@@ -1,0 +1,114 @@
+"""CPU tests: the oracle (oracle/restated.py) against the golden vectors produced by the real
+reference (oracle/make_golden.py), and against the live reference when /root/reference exists."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as O
+from oracle import ref_loader
+from tests.util import golden_problem, load_npz, max_abs, rel_err
+
+
+def _render_with_grads(prob, **kw):
+    leaves = O.require_grads(prob)
+    res = O.render_rays(prob, n_samples=128, perturb=0.0, **kw)
+    loss = O.parity_loss(res)
+    loss.backward()
+    return res, loss, leaves
+
+
+def _check_render(name, dtype, tol_out, tol_grad, **kw):
+    prob, g = golden_problem(name, dtype)
+    res, loss, leaves = _render_with_grads(prob, **kw)
+    for k in ("img_coarse", "depth_rnd", "sil_coarse", "frame_cyc_dis", "xyz_camera_vis", "xyz_canonical_vis"):
+        assert max_abs(res[k], g["out." + k]) <= tol_out, k
+    assert abs(float(loss.detach()) - float(g["out.loss"])) <= tol_out
+    n_checked = 0
+    for k, v in g.items():
+        if not k.startswith("grad."):
+            continue
+        leaf = leaves[k[5:]]
+        got = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+        # gradients are compared relative to each tensor's own scale (they span 1e-7 .. 1e0)
+        assert max_abs(got, v) <= tol_grad * max(1.0, float(np.abs(v).max())) or rel_err(got, v) <= tol_grad, k
+        n_checked += 1
+    assert n_checked > 20
+
+
+def test_render_fp32_matches_reference_golden():
+    _check_render("render_n32_fp32.npz", torch.float32, 2e-6, 2e-4)
+
+
+def test_render_fp64_matches_reference_golden():
+    _check_render("render_n32_fp64.npz", torch.float64, 1e-12, 1e-9)
+
+
+def test_render_use_fine_matches_reference_golden():
+    _check_render("render_fine_n16_fp32.npz", torch.float32, 5e-6, 5e-4, use_fine=True)
+
+
+def test_geometry_golden():
+    g = load_npz("geometry_fp32.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    x = t("embed.x")
+    for a in ("10", "6.4", "2.0"):
+        assert max_abs(O.embed(x, 10, float(a)), g["embed.xyz.alpha" + a]) < 1e-6
+    assert max_abs(O.embed(x, 4, 10), g["embed.dir"]) < 1e-6
+    bones, rts, aux, xyz, dsk = t("geom.bones"), t("geom.rts"), t("geom.skin_aux"), t("geom.xyz"), t("geom.dskin")
+    bd = O.bone_transform(bones, rts)
+    assert max_abs(bd, g["geom.bones_dfm"]) < 1e-6
+    sbw = O.skinning(bd, xyz, dsk, aux)
+    assert max_abs(sbw, g["geom.skin_bw"]) < 1e-5
+    assert max_abs(O.skinning(bones, xyz, None, aux), g["geom.skin_rest"]) < 1e-5
+    assert max_abs(O.neu_dbs(bones, rts, sbw, xyz, True)[0], g["geom.xyz_can"]) < 1e-6
+    assert max_abs(O.neu_dbs(bones, rts, t("geom.skin_rest"), xyz, False)[0], g["geom.xyz_fw"]) < 1e-6
+    assert max_abs(O.dqs_blend_skinning(rts.view(-1, 25, 8), sbw, xyz), g["geom.blend"]) < 1e-6
+    a, b = t("dq.a"), t("dq.b")
+    assert max_abs(O.dq_mul(a, b), g["dq.mul"]) < 1e-6
+    assert max_abs(O.dq_normalize(a), g["dq.normalize"]) < 1e-6
+    assert max_abs(O.dq_inverse(a), g["dq.inverse"]) < 1e-5
+    assert max_abs(O.dq_quaternion_conjugate(a), g["dq.qconj"]) == 0
+    assert max_abs(O.dq_combined_conjugate(a), g["dq.cconj"]) == 0
+    assert max_abs(O.q_mul(a[..., :4].reshape(-1, 4), b[..., :4].reshape(-1, 4)), g["dq.qmul"]) < 1e-6
+    assert max_abs(O.q_normalize(a[..., :4].reshape(-1, 4)), g["dq.qnormalize"]) < 1e-6
+
+
+def test_composite_pdf_grid_golden():
+    g = load_npz("geometry_fp32.npz")
+    nets = load_npz("nets_seed0.npz")
+    sd = {k[len("coarse."):]: torch.from_numpy(v) for k, v in nets.items() if k.startswith("coarse.")}
+    t = lambda k: torch.from_numpy(g[k])
+    pts, z, d, env = t("comp.pts"), t("comp.z"), t("comp.rays_d"), t("comp.env_code")
+    de = O.embed(d / d.norm(2, -1)[:, None], 4, 10)
+    assert max_abs(de, g["comp.dir_embedded"]) < 1e-6
+    raw = O.evaluate_mlp(sd, O.COARSE_SPEC, pts, 10, 10, dir_embedded=de[:, None].expand(-1, pts.shape[1], -1),
+                         code=env, chunk=4096)
+    assert max_abs(raw, g["comp.raw"]) < 2e-6
+    rgb, depth, sil, w, vis = O.composite(raw[..., :3], raw[..., 3], z, d, sd["beta"])
+    for got, key in ((rgb, "comp.rgb"), (depth, "comp.depth"), (sil, "comp.sil"), (w, "comp.weights"), (vis, "comp.vis")):
+        assert max_abs(got, g[key]) < 2e-6, key
+    assert max_abs(O.sample_pdf(t("pdf.bins"), t("pdf.weights"), 32, det=True), g["pdf.det"]) < 1e-6
+    assert max_abs(O.sample_pdf(t("pdf.bins"), t("pdf.weights"), 32, det=False, u=t("pdf.u")), g["pdf.rand"]) < 1e-6
+    with torch.no_grad():
+        vol = O.density_grid(sd, 12, (0.3, 0.3, 0.3))
+    assert max_abs(vol, g["grid.sigma"]) < 2e-6
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="live reference tree not present")
+def test_oracle_against_live_reference_random_seed():
+    """A seed/shape the fixtures do not contain, perturb>0 with the same jitter tensor."""
+    from moda_b200 import synth
+    from oracle.make_golden import build_reference_models
+    ref = ref_loader.load()
+    prob = synth.make_problem(8, seed=11)
+    models, emb = build_reference_models(ref, prob)
+    rays = {k: v.clone() for k, v in prob["rays"].items()}
+    torch.manual_seed(3)
+    res_ref = ref.render_rays(models, emb, rays, N_samples=64, perturb=1.0, noise_std=0, opts=synth.default_opts(),
+                              img_size=512)
+    torch.manual_seed(3)
+    jitter = torch.rand(8, 64)
+    with torch.no_grad():
+        res = O.render_rays(prob, n_samples=64, perturb=1.0, perturb_rand=jitter)
+    for k in ("img_coarse", "depth_rnd", "sil_coarse", "frame_cyc_dis", "xyz_canonical_vis"):
+        assert max_abs(res[k], res_ref[k]) < 2e-6, k
