@@ -1,0 +1,376 @@
+// fp32 SIMT linear layers for the NeRF MLPs (nnutils/nerf.py:147-198) with the operand assembly of
+// evaluate_mlp (nnutils/geom_utils.py:19-57) folded into the tile loaders: the "A" operand is a virtual
+// concatenation of up to three column segments, each of which is either a dense matrix, a per-ray vector
+// broadcast over the ray's samples (code.repeat(1,nbins,1), geom_utils.py:43) or the positional encoding
+// of a point computed on the fly (Embedding.forward, nerf.py:56-73) -- nothing is materialised.
+//
+// One generic kernel computes C[i,j] = sum_r P(i,r) * Q(j,r) for three roles:
+//   forward  Y[m,n]  = act(sum_k A(m,k) W[n,k] + b[n])
+//   dgrad    dA[m,k] = sum_n dY[m,n] W[n,k0+k]        (optionally masked by relu, or accumulated)
+//   wgrad    dW[n,k0+k] += sum_m dY[m,n] A(m,k)       (split over m, fp32 atomics)
+// This is the full-precision path (used for nerf_skin, whose gradients are ill-conditioned through the
+// peaked skinning softmax, SURVEY.md section 7 "hard parts") and the exact mode of the 8x256 trunk; the
+// tensor-core path for the trunk lives in tc_gemm.cu.
+#include "common.cuh"
+
+namespace moda {
+
+constexpr int SEG_DENSE = 0, SEG_BCAST = 1, SEG_PE = 2;
+constexpr int MAX_SEG = 3;
+constexpr int MAX_FREQS = 16;
+
+struct Seg {
+  const float* p;
+  int ld;     // row stride of p (for PE: stride of the point array, >= C)
+  int k0;     // first column of this segment in the virtual matrix
+  int k1;     // one past the last column
+  int type;   // SEG_*
+  int rep;    // BCAST: rows per source row (samples per ray)
+  int C;      // PE: input channels
+};
+
+struct ASrc {
+  Seg s[MAX_SEG];
+  int nseg;
+  float win[MAX_FREQS];  // PE window weights (nerf.py:63-66)
+  int M;                 // rows
+  int K;                 // total columns
+  __device__ __forceinline__ float at(int m, int k) const {
+    if (m >= M || k >= K) return 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_SEG; ++i) {
+      if (i < nseg && k < s[i].k1) {
+        const Seg& g = s[i];
+        const int j = k - g.k0;
+        if (g.type == SEG_DENSE) return g.p[(size_t)m * g.ld + j];
+        if (g.type == SEG_BCAST) return g.p[(size_t)(m / g.rep) * g.ld + j];
+        if (j < g.C) return g.p[(size_t)m * g.ld + j];
+        const int jj = j - g.C;
+        const int band = jj / (2 * g.C);
+        const int rem = jj - band * 2 * g.C;
+        const int c = rem % g.C;
+        const float v = g.p[(size_t)m * g.ld + c] * (float)(1 << band);
+        return win[band] * ((rem >= g.C) ? cosf(v) : sinf(v));
+      }
+    }
+    return 0.f;
+  }
+};
+
+struct Dense {  // element (i, r) = p[i*ld + r]
+  const float* p;
+  int ld, I, Rr;
+  __device__ __forceinline__ float at(int i, int r) const {
+    return (i < I && r < Rr) ? p[(size_t)i * ld + r] : 0.f;
+  }
+};
+
+struct DenseT {  // element (i, r) = p[r*ld + i]
+  const float* p;
+  int ld, I, Rr;
+  __device__ __forceinline__ float at(int i, int r) const {
+    return (i < I && r < Rr) ? p[(size_t)r * ld + i] : 0.f;
+  }
+};
+
+struct ASrcT {  // element (i=k, r=m) of the virtual A
+  ASrc a;
+  __device__ __forceinline__ float at(int i, int r) const { return a.at(r, i); }
+};
+
+constexpr int ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2;
+
+struct EpiFwd {
+  float* y;
+  int ldy;
+  const float* bias;  // (N) or null
+  int act;
+  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+    if (bias) v += bias[j];
+    if (act == ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+    y[(size_t)i * ldy + j] = v;
+  }
+};
+
+struct EpiDgrad {
+  float* c;
+  int ldc;
+  const float* mask;  // post-relu activation of the producing layer, or null
+  int ldm;
+  int accumulate;
+  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+    if (mask && !(mask[(size_t)i * ldm + j] > 0.f)) v = 0.f;
+    float* o = c + (size_t)i * ldc + j;
+    *o = accumulate ? (*o + v) : v;
+  }
+};
+
+struct EpiWgrad {
+  float* w;
+  int ldw;
+  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+    if (v != 0.f) atomicAdd(w + (size_t)i * ldw + j, v);
+  }
+};
+
+constexpr int BR = 16;
+constexpr int GEMM_THREADS = 256;
+
+// P_ROW: P's memory is contiguous along r (each thread loads consecutive r of one i); otherwise along i.
+template <class PL, class QL, class EP, int BI, int BJ, bool P_ROW, bool Q_ROW>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(PL P, QL Q, EP ep, int I, int J, int Rdim,
+                                                            int r_chunk) {
+  constexpr int TI = BI / 16, TJ = BJ / 16;
+  constexpr int PE_ = BI * BR / GEMM_THREADS, QE_ = BJ * BR / GEMM_THREADS;
+  __shared__ __align__(16) float Ps[BR][BI];
+  __shared__ __align__(16) float Qs[BR][BJ];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * BI, j0 = blockIdx.y * BJ;
+  const int r_begin = blockIdx.z * r_chunk;
+  const int r_end = min(Rdim, r_begin + r_chunk);
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[TI][TJ];
+#pragma unroll
+  for (int a = 0; a < TI; ++a)
+#pragma unroll
+    for (int b = 0; b < TJ; ++b) acc[a][b] = 0.f;
+  float pv[PE_], qv[QE_];
+
+  auto fetch = [&](int r0) {
+    if (P_ROW) {
+      const int i = tid % BI, rr = (tid / BI) * PE_;
+#pragma unroll
+      for (int e = 0; e < PE_; ++e) {
+        const int r = r0 + rr + e;
+        pv[e] = (r < r_end) ? P.at(i0 + i, r) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < PE_; ++e) {
+        const int lin = tid + e * GEMM_THREADS;
+        const int i = lin % BI, r = r0 + lin / BI;
+        pv[e] = (r < r_end) ? P.at(i0 + i, r) : 0.f;
+      }
+    }
+    if (Q_ROW) {
+      const int j = tid % BJ, rr = (tid / BJ) * QE_;
+#pragma unroll
+      for (int e = 0; e < QE_; ++e) {
+        const int r = r0 + rr + e;
+        qv[e] = (r < r_end) ? Q.at(j0 + j, r) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < QE_; ++e) {
+        const int lin = tid + e * GEMM_THREADS;
+        const int j = lin % BJ, r = r0 + lin / BJ;
+        qv[e] = (r < r_end) ? Q.at(j0 + j, r) : 0.f;
+      }
+    }
+  };
+  auto stash = [&]() {
+    if (P_ROW) {
+      const int i = tid % BI, rr = (tid / BI) * PE_;
+#pragma unroll
+      for (int e = 0; e < PE_; ++e) Ps[rr + e][i] = pv[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < PE_; ++e) {
+        const int lin = tid + e * GEMM_THREADS;
+        Ps[lin / BI][lin % BI] = pv[e];
+      }
+    }
+    if (Q_ROW) {
+      const int j = tid % BJ, rr = (tid / BJ) * QE_;
+#pragma unroll
+      for (int e = 0; e < QE_; ++e) Qs[rr + e][j] = qv[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < QE_; ++e) {
+        const int lin = tid + e * GEMM_THREADS;
+        Qs[lin / BJ][lin % BJ] = qv[e];
+      }
+    }
+  };
+
+  if (r_begin < r_end) fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += BR) {
+    __syncthreads();
+    stash();
+    __syncthreads();
+    if (r0 + BR < r_end) fetch(r0 + BR);
+#pragma unroll
+    for (int kk = 0; kk < BR; ++kk) {
+      float a[TI], b[TJ];
+#pragma unroll
+      for (int x = 0; x < TI; x += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Ps[kk][ty * TI + x]);
+        a[x] = t.x; a[x + 1] = t.y; a[x + 2] = t.z; a[x + 3] = t.w;
+      }
+      if constexpr (TJ % 4 == 0) {
+#pragma unroll
+        for (int x = 0; x < TJ; x += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&Qs[kk][tx * TJ + x]);
+          b[x] = t.x; b[x + 1] = t.y; b[x + 2] = t.z; b[x + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < TJ; ++x) b[x] = Qs[kk][tx * TJ + x];
+      }
+#pragma unroll
+      for (int x = 0; x < TI; ++x)
+#pragma unroll
+        for (int y = 0; y < TJ; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < TI; ++x) {
+    const int i = i0 + ty * TI + x;
+    if (i >= I) continue;
+#pragma unroll
+    for (int y = 0; y < TJ; ++y) {
+      const int j = j0 + tx * TJ + y;
+      if (j < J) ep(i, j, acc[x][y]);
+    }
+  }
+}
+
+// out[r, n] = sum_{s<S} in[(r*S+s)*ld + n]   (per-ray sums of a per-sample gradient)
+__global__ void segsum_kernel(const float* in, int ld, float* out, int R, int S, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= N) return;
+  const float* p = in + (size_t)r * S * ld + n;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += p[(size_t)s * ld];
+  out[(size_t)r * N + n] = acc;
+}
+
+// out[n] += sum_m in[m*ld + n]
+__global__ void colsum_kernel(const float* in, int ld, float* out, int M, int N, int rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc += in[(size_t)m * ld + n];
+  if (acc != 0.f) atomicAdd(out + n, acc);
+}
+
+}  // namespace moda
+
+using namespace moda;
+
+// Flat description of the virtual A operand as it crosses the C ABI:
+//   seg_ptr[i], seg_ld[i], seg_width[i], seg_type[i], seg_aux[i] (BCAST: rows per source row; PE: channels)
+static int build_asrc(ASrc& a, int M, int nseg, const float* const* seg_ptr, const int* seg_ld,
+                      const int* seg_width, const int* seg_type, const int* seg_aux, const float* win,
+                      int n_win) {
+  MODA_REQUIRE(nseg >= 1 && nseg <= MAX_SEG, "linear: nseg=%d outside [1,%d]", nseg, MAX_SEG);
+  MODA_REQUIRE(n_win <= MAX_FREQS, "linear: more than %d PE bands", MAX_FREQS);
+  a.nseg = nseg;
+  a.M = M;
+  int k = 0;
+  for (int i = 0; i < nseg; ++i) {
+    MODA_REQUIRE(seg_ptr[i] != nullptr && seg_width[i] > 0, "linear: segment %d is empty", i);
+    a.s[i].p = seg_ptr[i];
+    a.s[i].ld = seg_ld[i];
+    a.s[i].k0 = k;
+    a.s[i].k1 = k + seg_width[i];
+    a.s[i].type = seg_type[i];
+    a.s[i].rep = (seg_type[i] == SEG_BCAST) ? seg_aux[i] : 1;
+    a.s[i].C = (seg_type[i] == SEG_PE) ? seg_aux[i] : 1;
+    if (seg_type[i] == SEG_BCAST) MODA_REQUIRE(seg_aux[i] >= 1, "linear: BCAST segment needs rep >= 1");
+    if (seg_type[i] == SEG_PE) {
+      MODA_REQUIRE(seg_aux[i] >= 1 && (seg_width[i] - seg_aux[i]) % (2 * seg_aux[i]) == 0,
+                   "linear: PE segment width %d is not C*(1+2F)", seg_width[i]);
+      MODA_REQUIRE((seg_width[i] / seg_aux[i] - 1) / 2 <= n_win, "linear: PE window has too few bands");
+    }
+    k = a.s[i].k1;
+  }
+  a.K = k;
+  for (int i = 0; i < MAX_FREQS; ++i) a.win[i] = (i < n_win && win) ? win[i] : 1.0f;
+  return 0;
+}
+
+// Y[M,N] = act(A(M,K) W[N,K]^T + bias)
+extern "C" int moda_linear_fwd(int M, int N, int nseg, const float* const* seg_ptr, const int* seg_ld,
+                               const int* seg_width, const int* seg_type, const int* seg_aux,
+                               const float* win, int n_win, const float* W, int ldw, const float* bias,
+                               int act, float* Y, int ldy, cudaStream_t stream) {
+  ASrc a;
+  if (int e = build_asrc(a, M, nseg, seg_ptr, seg_ld, seg_width, seg_type, seg_aux, win, n_win)) return e;
+  MODA_REQUIRE(W && Y && ldw >= a.K && ldy >= N, "linear_fwd: bad W/Y");
+  if (M == 0 || N == 0) return 0;
+  Dense q{W, ldw, N, a.K};
+  EpiFwd ep{Y, ldy, bias, act};
+  if (N > 32) {
+    dim3 grid(cdiv(M, 128), cdiv(N, 64), 1);
+    gemm_kernel<ASrc, Dense, EpiFwd, 128, 64, true, true><<<grid, GEMM_THREADS, 0, stream>>>(a, q, ep, M, N, a.K, a.K);
+  } else {
+    dim3 grid(cdiv(M, 128), cdiv(N, 16), 1);
+    gemm_kernel<ASrc, Dense, EpiFwd, 128, 16, true, true><<<grid, GEMM_THREADS, 0, stream>>>(a, q, ep, M, N, a.K, a.K);
+  }
+  return check_launch("linear_fwd");
+}
+
+// dA[M,Kseg] (=|+=) dY[M,N] W[N, k0:k0+Kseg], optionally masked by (mask > 0)
+extern "C" int moda_linear_dgrad(int M, int N, int Kseg, const float* dY, int ldy, const float* W, int ldw,
+                                 int k0, const float* mask, int ldm, int accumulate, float* dA, int lda,
+                                 cudaStream_t stream) {
+  MODA_REQUIRE(dY && W && dA && ldy >= N && lda >= Kseg, "linear_dgrad: bad arguments");
+  if (M == 0 || Kseg == 0) return 0;
+  Dense p{dY, ldy, M, N};
+  DenseT q{W + k0, ldw, Kseg, N};
+  EpiDgrad ep{dA, lda, mask, ldm, accumulate};
+  if (Kseg > 32) {
+    dim3 grid(cdiv(M, 128), cdiv(Kseg, 64), 1);
+    gemm_kernel<Dense, DenseT, EpiDgrad, 128, 64, true, false><<<grid, GEMM_THREADS, 0, stream>>>(p, q, ep, M, Kseg, N, N);
+  } else {
+    dim3 grid(cdiv(M, 128), cdiv(Kseg, 16), 1);
+    gemm_kernel<Dense, DenseT, EpiDgrad, 128, 16, true, false><<<grid, GEMM_THREADS, 0, stream>>>(p, q, ep, M, Kseg, N, N);
+  }
+  return check_launch("linear_dgrad");
+}
+
+// dW[N, k0:k0+K] += dY[M,N]^T A(M,K) ; dbias[N] += colsum(dY) when dbias != null
+extern "C" int moda_linear_wgrad(int M, int N, int nseg, const float* const* seg_ptr, const int* seg_ld,
+                                 const int* seg_width, const int* seg_type, const int* seg_aux,
+                                 const float* win, int n_win, const float* dY, int ldy, float* dW, int ldw,
+                                 int k0, float* dbias, cudaStream_t stream) {
+  ASrcT a;
+  if (int e = build_asrc(a.a, M, nseg, seg_ptr, seg_ld, seg_width, seg_type, seg_aux, win, n_win)) return e;
+  MODA_REQUIRE(dY && dW && ldy >= N, "linear_wgrad: bad arguments");
+  if (M == 0 || N == 0) return 0;
+  const int K = a.a.K;
+  DenseT p{dY, ldy, N, M};
+  EpiWgrad ep{dW + k0, ldw};
+  // split the reduction over rows so that the grid covers the machine a few times over
+  const int tiles = cdiv(N, 64) * cdiv(K, 64);
+  int splits = cdiv(148 * 4, tiles);
+  int r_chunk = cdiv(M, splits);
+  r_chunk = ((r_chunk + BR - 1) / BR) * BR;
+  if (r_chunk < 256) r_chunk = 256;
+  splits = cdiv(M, r_chunk);
+  dim3 grid(cdiv(N, 64), cdiv(K, 64), splits);
+  gemm_kernel<DenseT, ASrcT, EpiWgrad, 64, 64, false, false><<<grid, GEMM_THREADS, 0, stream>>>(p, a, ep, N, K, M, r_chunk);
+  if (dbias) {
+    const int rpb = 2048;
+    dim3 g2(cdiv(N, 64), cdiv(M, rpb));
+    colsum_kernel<<<g2, 64, 0, stream>>>(dY, ldy, dbias, M, N, rpb);
+  }
+  return check_launch("linear_wgrad");
+}
+
+extern "C" int moda_segsum(const float* in, int ld, float* out, int R, int S, int N, cudaStream_t stream) {
+  MODA_REQUIRE(in && out && ld >= N, "segsum: bad arguments");
+  if (R == 0 || N == 0) return 0;
+  MODA_REQUIRE(R <= 65535 * 1024, "segsum: too many rows");
+  for (int r0 = 0; r0 < R; r0 += 65535) {
+    const int rc = (R - r0 < 65535) ? R - r0 : 65535;
+    dim3 grid(cdiv(N, 64), rc);
+    segsum_kernel<<<grid, 64, 0, stream>>>(in + (size_t)r0 * S * ld, ld, out + (size_t)r0 * N, rc, S, N);
+  }
+  return check_launch("segsum");
+}
