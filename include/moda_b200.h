@@ -1,0 +1,140 @@
+/* libmoda_b200.so -- C ABI of the B200-native articulated volume renderer.
+ *
+ * The reference (ChaoyueSong/MoDA) has no FFI: its boundary for this path is a Python function-level API
+ * (nnutils/rendering.py, nnutils/nerf.py, nnutils/geom_utils.py, nnutils/dual_quat.py).  Each entry point
+ * below names the reference function(s) it replaces; the Python side that keeps the reference's names and
+ * signatures on top of this ABI is moda_b200/{rendering,nerf,geom_utils,dual_quat}.py, and the binding a
+ * MoDA maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise ("host"); pointers are
+ *     borrowed for the duration of the stream-ordered call; the library allocates nothing;
+ *   - "ld*" arguments are row strides in elements, so column slices of wider matrices can be passed;
+ *   - return value 0 = success; >0 = cudaError_t of the launch; <0 = argument check failed;
+ *     moda_last_error() returns the thread-local message; nothing synchronises the device;
+ *   - re-entrant: no global mutable state; work is issued only on the stream argument;
+ *   - optional pointers may be NULL where stated.
+ */
+#ifndef MODA_B200_H
+#define MODA_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* moda_version(void);
+const char* moda_last_error(void);
+/* 0 when the current device is sm_100 (the only target this library is built for) */
+int moda_device_check(void);
+
+/* ---- positional encoding: Embedding.forward, nnutils/nerf.py:35-75 -----------------------------------
+ * out (M, C*(1+2F)) = [x | w_k sin(2^k x) | w_k cos(2^k x)]_k ; win: HOST array of F window weights
+ * (nerf.py:63-66) or NULL for all-ones. */
+int moda_embed_fwd(const float* x, int ldx, float* out, int ldo, long long M, int C, int F, const float* win,
+                   cudaStream_t stream);
+/* gx (M,C) (= or += when accumulate) d out/d x ^T gout */
+int moda_embed_bwd(const float* x, int ldx, const float* gout, int ldo, float* gx, int ldg, long long M, int C,
+                   int F, const float* win, int accumulate, cudaStream_t stream);
+
+/* ---- ray sampling: render_rays, nnutils/rendering.py:64-89 -------------------------------------------
+ * z (R,S) = near(1-s)+far s [or disparity], stratified jitter with mid-point bins when perturb>0
+ * (jitter = the U[0,1) tensor of rendering.py:82); xyz (R,S,3) = o + d z; dn (R,3) = d/|d| (may be NULL). */
+int moda_sample_rays_fwd(const float* o, const float* d, const float* near_, const float* far_,
+                         const float* jitter, float perturb, int use_disp, float* z, float* xyz, float* dn, int R,
+                         int S, cudaStream_t stream);
+/* xyz = o + d z for given depths (second pass of the coarse->fine scheme, rendering.py:112-113) */
+int moda_points_from_depths(const float* o, const float* d, const float* z, float* xyz, int R, int S,
+                            cudaStream_t stream);
+/* go (R,3) = sum_s gxyz ; gd (R,3) = sum_s z gxyz + gnd d/|d| + normalise-adjoint(gdn); gxyz/gdn/gnd/go may be NULL */
+int moda_sample_rays_bwd(const float* d, const float* z, const float* gxyz, const float* gdn, const float* gnd,
+                         float* go, float* gd, int R, int S, cudaStream_t stream);
+/* sample_pdf, rendering.py:582-623.  merge=0: bins (R,n+1), weights (R,n) -> out (R,NI).
+ * merge=1: weights = compositing weights (R,S); bins are the mid-points of z (R,S), the pdf uses
+ * weights[:,1:-1] (n = S-2) and out (R,S+NI) is the sorted union with z (rendering.py:103-110).
+ * det: u = linspace(0,1,NI); else u (R,NI) is the uniform draw. */
+int moda_sample_pdf(const float* z, const float* bins, const float* weights, const float* u, float* out, int R,
+                    int S, int n, int NI, int det, float eps, int merge, cudaStream_t stream);
+
+/* ---- dual quaternions: nnutils/dual_quat.py ------------------------------------------------------------
+ * op: 0 dq_quaternion_conjugate (:65-74), 1 dq_combined_conjugate (:76-85), 2 dq_normalize (:51-62),
+ *     3 dq_inverse (:87-93), 4 q_normalize (:4-12, 4-wide).  n = number of (dual) quaternions. */
+int moda_dq_unary_fwd(int op, const float* in, float* out, long long n, cudaStream_t stream);
+int moda_dq_unary_bwd(int op, const float* in, const float* gout, float* gin, long long n, cudaStream_t stream);
+/* width 4: q_mul (:14-31); width 8: dq_mul (:33-49) */
+int moda_dq_mul_fwd(const float* a, const float* b, float* out, long long n, int width, cudaStream_t stream);
+int moda_dq_mul_bwd(const float* a, const float* b, const float* gout, float* ga, float* gb, long long n,
+                    int width, cudaStream_t stream);
+
+/* ---- Gaussian bones: bone_transform, nnutils/geom_utils.py:59-111 (dual-quaternion branch) -------------
+ * bones (B,10) or (R,B,10) when bones_per_ray; rts (R,B,8); out (R,B,10). */
+int moda_bone_transform_fwd(const float* bones, const float* rts, float* out, int R, int B, int bones_per_ray,
+                            cudaStream_t stream);
+/* gbones accumulated (zero it first) when shared, overwritten when per-ray; grts overwritten */
+int moda_bone_transform_bwd(const float* bones, const float* rts, const float* gout, float* gbones, float* grts,
+                            int R, int B, int bones_per_ray, cudaStream_t stream);
+
+/* ---- skinning weights + dual-quaternion blend skinning ------------------------------------------------
+ * One kernel covers skinning / skinning_chunk (geom_utils.py:237-302), dqs_blend_skinning(_chunk)
+ * (:457-517) and the warps of neu_dbs (:372-456) fused with gauss_mlp_skinning's weight computation:
+ *   weights  W = softmax_b(-kappa sum_k s_k (R_b^T (c_b - p))_k^2 + dskin_b),  kappa = 1000 exp(skin_aux[0])
+ *            (or W = skin_in when given);   blend b = sum_b W_b dq_b;   y = DQ-transform(p; b/|b_real|).
+ *   deform: bones are first moved by bone_transform(bones, rts) (backward warp);
+ *   invert: dq = dq_inverse(rts) (backward warp) instead of rts (forward warp).
+ * pts (R,S,3); rts (R,B,8) or NULL (weights only); dskin / skin_in / y / skin_out (R,S,*) optional. */
+int moda_skin_warp_fwd(const float* pts, const float* bones, const float* rts, const float* skin_aux,
+                       const float* dskin, const float* skin_in, float* y, float* skin_out, int R, int S, int B,
+                       int bones_per_ray, int deform, int invert, cudaStream_t stream);
+/* gy (R,S,3) / gskin (R,S,B): incoming gradients (either may be NULL).  gpts, gdskin, gskin_in overwritten;
+ * grts (R,B,8), gbones, gaux (2) accumulated (zero them first). */
+int moda_skin_warp_bwd(const float* pts, const float* bones, const float* rts, const float* skin_aux,
+                       const float* dskin, const float* skin_in, const float* gy, const float* gskin, float* gpts,
+                       float* gdskin, float* gskin_in, float* grts, float* gbones, float* gaux, int R, int S,
+                       int B, int bones_per_ray, int deform, int invert, cudaStream_t stream);
+
+/* ---- compositing: inference, nnutils/rendering.py:183-235 (+ frame_cyc_dis :341,:473) ------------------
+ * rgb (P,3; row stride ld_rgb), sigma (P; stride ld_sigma), z (R,S), d (R,3), beta (1); noise (R,S) and
+ * mask (R,S uint8, 1 = alpha forced to 0, :210-215) optional; xa/xb (R,S,3) optional pair for the cycle
+ * term out_cyc = sum_s |xa-xb| w.  Outputs: out_rgb (R,3), out_depth (R), out_sil (R), out_w (R,S),
+ * out_vis (R,S) = transmittance. */
+int moda_composite_fwd(const float* rgb, int ld_rgb, const float* sigma, int ld_sigma, const float* z,
+                       const float* d, const float* beta, const float* noise, const unsigned char* mask,
+                       const float* xa, const float* xb, float* out_rgb, float* out_depth, float* out_sil,
+                       float* out_w, float* out_vis, float* out_cyc, int R, int S, cudaStream_t stream);
+/* vis = saved transmittance; g_* incoming (NULL = zero); g_rgbs/g_sigma/g_nd/g_xa/g_xb overwritten,
+ * g_beta accumulated.  g_nd (R) is the gradient w.r.t. |d| (feed it to moda_sample_rays_bwd). */
+int moda_composite_bwd(const float* rgb, int ld_rgb, const float* sigma, int ld_sigma, const float* z,
+                       const float* d, const float* beta, const float* noise, const unsigned char* mask,
+                       const float* xa, const float* xb, const float* vis, const float* g_rgb,
+                       const float* g_depth, const float* g_sil, const float* g_cyc, const float* g_w,
+                       float* g_rgbs, int ld_grgb, float* g_sigma, int ld_gsigma, float* g_beta, float* g_nd,
+                       float* g_xa, float* g_xb, int R, int S, cudaStream_t stream);
+
+/* ---- linear layers of NeRF.forward (nnutils/nerf.py:147-198) with evaluate_mlp's input assembly
+ * (nnutils/geom_utils.py:19-57) folded in.  The A operand is a virtual row-wise concatenation of nseg
+ * (<=3) column segments described by HOST arrays: seg_ptr[i] device pointer, seg_ld[i] row stride,
+ * seg_width[i] columns, seg_type[i] (0 dense matrix; 1 per-ray rows broadcast over seg_aux[i] samples;
+ * 2 positional encoding of points with seg_aux[i] channels, computed on the fly), win = HOST PE window.
+ * W is nn.Linear's (N, ldw) row-major weight, read in place. */
+int moda_linear_fwd(int M, int N, int nseg, const float* const* seg_ptr, const int* seg_ld, const int* seg_width,
+                    const int* seg_type, const int* seg_aux, const float* win, int n_win, const float* W, int ldw,
+                    const float* bias, int act /* 0 none, 1 relu, 2 sigmoid */, float* Y, int ldy,
+                    cudaStream_t stream);
+/* dA (M,Kseg) (= or +=) dY (M,N) W[:, k0:k0+Kseg], then zeroed where mask<=0 (relu of the producer) */
+int moda_linear_dgrad(int M, int N, int Kseg, const float* dY, int ldy, const float* W, int ldw, int k0,
+                      const float* mask, int ldm, int accumulate, float* dA, int lda, cudaStream_t stream);
+/* dW[:, k0:k0+K] += dY^T A ; dbias += colsum(dY) (dbias may be NULL).  Accumulates: zero dW first. */
+int moda_linear_wgrad(int M, int N, int nseg, const float* const* seg_ptr, const int* seg_ld,
+                      const int* seg_width, const int* seg_type, const int* seg_aux, const float* win, int n_win,
+                      const float* dY, int ldy, float* dW, int ldw, int k0, float* dbias, cudaStream_t stream);
+/* out (R,N) = per-ray sums over S consecutive rows of in (R*S, N) */
+int moda_segsum(const float* in, int ld, float* out, int R, int S, int N, cudaStream_t stream);
+/* out = g * act'(y): kind 1 relu, 2 sigmoid; row-strided (M,N) views */
+int moda_act_bwd(int kind, const float* y, int ldy, const float* g, int ldg, float* out, int ldo, long long M,
+                 int N, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODA_B200_H */

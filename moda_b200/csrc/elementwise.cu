@@ -241,8 +241,8 @@ extern "C" int moda_embed_fwd(const float* x, int ldx, float* out, int ldo, long
                               const float* win, cudaStream_t stream) {
   Window w;
   if (int e = fill_window(w, win, F)) return e;
-  MODA_REQUIRE(x && out && ldx >= C && ldo >= C * (1 + 2 * F), "embed_fwd: bad arguments");
   if (M * C == 0) return 0;
+  MODA_REQUIRE(x && out && ldx >= C && ldo >= C * (1 + 2 * F), "embed_fwd: bad arguments");
   embed_fwd_kernel<<<cdiv(M * C, 256), 256, 0, stream>>>(x, ldx, out, ldo, M, C, F, w);
   return check_launch("embed_fwd");
 }
@@ -252,8 +252,8 @@ extern "C" int moda_embed_bwd(const float* x, int ldx, const float* gout, int ld
                               cudaStream_t stream) {
   Window w;
   if (int e = fill_window(w, win, F)) return e;
-  MODA_REQUIRE(x && gout && gx && ldx >= C && ldg >= C && ldo >= C * (1 + 2 * F), "embed_bwd: bad arguments");
   if (M * C == 0) return 0;
+  MODA_REQUIRE(x && gout && gx && ldx >= C && ldg >= C && ldo >= C * (1 + 2 * F), "embed_bwd: bad arguments");
   embed_bwd_kernel<<<cdiv(M * C, 256), 256, 0, stream>>>(x, ldx, gout, ldo, gx, ldg, M, C, F, w, accumulate);
   return check_launch("embed_bwd");
 }

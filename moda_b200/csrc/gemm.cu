@@ -100,9 +100,10 @@ struct EpiDgrad {
   int ldm;
   int accumulate;
   __device__ __forceinline__ void operator()(int i, int j, float v) const {
-    if (mask && !(mask[(size_t)i * ldm + j] > 0.f)) v = 0.f;
     float* o = c + (size_t)i * ldc + j;
-    *o = accumulate ? (*o + v) : v;
+    if (accumulate) v += *o;
+    if (mask && !(mask[(size_t)i * ldm + j] > 0.f)) v = 0.f;  // relu' applied to the accumulated total
+    *o = v;
   }
 };
 
@@ -236,15 +237,31 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(PL P, QL Q, EP ep, i
   }
 }
 
-// out[r, n] = sum_{s<S} in[(r*S+s)*ld + n]   (per-ray sums of a per-sample gradient)
-__global__ void segsum_kernel(const float* in, int ld, float* out, int R, int S, int N) {
+// out[r, n] = sum_{s<S} in[(r*S+s)*ld + n]   (per-ray sums of a per-sample gradient).  When S is long
+// (a code shared by every sample, e.g. rest_pose_code) the rows are split over blockIdx.z and combined with
+// atomics into a zero-initialised output.
+__global__ void segsum_kernel(const float* in, int ld, float* out, int R, int S, int N, int s_chunk) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   if (n >= N) return;
-  const float* p = in + (size_t)r * S * ld + n;
+  const int s0 = blockIdx.z * s_chunk;
+  const int s1 = min(S, s0 + s_chunk);
+  const float* p = in + ((size_t)r * S + s0) * ld + n;
   float acc = 0.f;
-  for (int s = 0; s < S; ++s) acc += p[(size_t)s * ld];
-  out[(size_t)r * N + n] = acc;
+  for (int s = s0; s < s1; ++s, p += ld) acc += *p;
+  if (gridDim.z == 1) out[(size_t)r * N + n] = acc;
+  else atomicAdd(out + (size_t)r * N + n, acc);
+}
+
+// out = g * act'(y) for the output activations (sigmoid: y(1-y); relu: y>0); row-strided (M,N) views
+__global__ void act_bwd_kernel(int kind, const float* y, int ldy, const float* g, int ldg, float* out, int ldo,
+                               long long M, int N) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * N) return;
+  const long long m = t / N;
+  const int n = (int)(t % N);
+  const float yy = y[m * ldy + n], gg = g[m * ldg + n];
+  out[m * ldo + n] = (kind == ACT_SIGMOID) ? gg * yy * (1.0f - yy) : ((yy > 0.f) ? gg : 0.f);
 }
 
 // out[n] += sum_m in[m*ld + n]
@@ -364,13 +381,28 @@ extern "C" int moda_linear_wgrad(int M, int N, int nseg, const float* const* seg
 }
 
 extern "C" int moda_segsum(const float* in, int ld, float* out, int R, int S, int N, cudaStream_t stream) {
-  MODA_REQUIRE(in && out && ld >= N, "segsum: bad arguments");
   if (R == 0 || N == 0) return 0;
+  MODA_REQUIRE(in && out && ld >= N, "segsum: bad arguments");
   MODA_REQUIRE(R <= 65535 * 1024, "segsum: too many rows");
+  int splits = 1, s_chunk = S;
+  if (S > 512) {
+    s_chunk = 256;
+    splits = cdiv(S, s_chunk);
+    if (splits > 65535) { splits = 65535; s_chunk = cdiv(S, splits); splits = cdiv(S, s_chunk); }
+    cudaMemsetAsync(out, 0, (size_t)R * N * sizeof(float), stream);
+  }
   for (int r0 = 0; r0 < R; r0 += 65535) {
     const int rc = (R - r0 < 65535) ? R - r0 : 65535;
-    dim3 grid(cdiv(N, 64), rc);
-    segsum_kernel<<<grid, 64, 0, stream>>>(in + (size_t)r0 * S * ld, ld, out + (size_t)r0 * N, rc, S, N);
+    dim3 grid(cdiv(N, 64), rc, splits);
+    segsum_kernel<<<grid, 64, 0, stream>>>(in + (size_t)r0 * S * ld, ld, out + (size_t)r0 * N, rc, S, N, s_chunk);
   }
   return check_launch("segsum");
+}
+
+extern "C" int moda_act_bwd(int kind, const float* y, int ldy, const float* g, int ldg, float* out, int ldo,
+                            long long M, int N, cudaStream_t stream) {
+  MODA_REQUIRE((kind == ACT_RELU || kind == ACT_SIGMOID) && y && g && out, "act_bwd: bad arguments");
+  if (M * N == 0) return 0;
+  act_bwd_kernel<<<cdiv(M * N, 256), 256, 0, stream>>>(kind, y, ldy, g, ldg, out, ldo, M, N);
+  return check_launch("act_bwd");
 }

@@ -1,0 +1,56 @@
+"""Data-parallel plumbing for the ray batch.
+
+Rays are independent, so each rank renders a contiguous shard and the only exchange per training step is
+ONE all-reduce (sum) of the flat fp32 gradient buffer (~2.6 MB for the core config) over NCCL.  The
+reference does the same thing one level up with DistributedDataParallel buckets over every registered
+parameter (nnutils/train_utils.py:48-62, 98-106, 958)."""
+import torch
+import torch.distributed as dist
+
+
+class FlatParams:
+    """Re-homes a list of leaf tensors into one flat parameter buffer and one flat gradient buffer.
+
+    After construction ``p.data`` and ``p.grad`` of every tensor are views into ``self.flat`` /
+    ``self.grad``; autograd accumulates into the views in place, so ``allreduce()`` is a single collective
+    and an optimizer can be built over the single tensor ``self.flat`` (its .grad is ``self.grad``)."""
+
+    def __init__(self, tensors):
+        self.tensors = [t for t in tensors]
+        n = sum(t.numel() for t in self.tensors)
+        dev = self.tensors[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for t in self.tensors:
+            k = t.numel()
+            self.flat[off:off + k].copy_(t.detach().reshape(-1))
+            t.data = self.flat[off:off + k].view(t.shape)
+            t.grad = self.grad[off:off + k].view(t.shape)
+            off += k
+        self.flat.requires_grad_(True)
+        self.flat.grad = self.grad
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def allreduce(self, scale=None):
+        """Sum of the per-rank gradients (each rank scales its loss by its share of the global batch)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+        if scale is not None:
+            self.grad.mul_(scale)
+
+
+def shard_rays(rays, rank, world):
+    """Contiguous N/world slice of every per-ray tensor (the rays dict of geom_utils.py:785-794)."""
+    out = {}
+    for k, v in rays.items():
+        if torch.is_tensor(v) and v.dim() >= 1:
+            n = v.shape[0]
+            per = (n + world - 1) // world
+            out[k] = v[rank * per:min(n, (rank + 1) * per)]
+        else:
+            out[k] = v
+    return out

@@ -29,6 +29,7 @@ def load():
         return _loaded
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF)
+    saved_path = list(sys.path)
     for p in (REF + "/third_party/pytorch3d", REF + "/third_party", REF + "/nnutils", REF):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -47,6 +48,8 @@ def load():
         import dual_quat
     finally:
         os.chdir(cwd)
+        # the reference tree carries generic top-level names (tests/, utils/): do not leave it on the path
+        sys.path[:] = saved_path
     ns = types.SimpleNamespace(rendering=rendering, nerf=nerf, geom_utils=geom_utils,
                                dual_quat=dual_quat, render_rays=rendering.render_rays,
                                NeRF=nerf.NeRF, Embedding=nerf.Embedding)

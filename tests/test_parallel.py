@@ -1,0 +1,81 @@
+"""CPU tests (gloo, world_size 2) of the data-parallel host logic: ray sharding + the single flat-buffer
+all-reduce reproduce the single-process gradient."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from moda_b200.parallel import FlatParams, shard_rays
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _toy_loss(params, rays, n_total):
+    w, b = params
+    pred = rays["x"] @ w + b
+    return ((pred - rays["y"]) ** 2).sum() / n_total  # each rank scales by its share of the global batch
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    rays = {"x": torch.randn(10, 4, generator=g), "y": torch.randn(10, 3, generator=g), "meta": 7}
+    w = torch.randn(4, 3, generator=g).requires_grad_(True)
+    b = torch.randn(3, generator=g).requires_grad_(True)
+    fp = FlatParams([w, b])
+    mine = shard_rays(rays, rank, world)
+    assert mine["meta"] == 7 and mine["x"].shape[0] == 5
+    fp.zero_grad()
+    _toy_loss([w, b], mine, 10).backward()
+    fp.allreduce()
+    ret[rank] = fp.grad.clone()
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_matches_single_process():
+    world = 2
+    port = _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")  # spawned workers import this module
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    rays = {"x": torch.randn(10, 4, generator=g), "y": torch.randn(10, 3, generator=g)}
+    w = torch.randn(4, 3, generator=g).requires_grad_(True)
+    b = torch.randn(3, generator=g).requires_grad_(True)
+    _toy_loss([w, b], rays, 10).backward()
+    ref = torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+    for r in range(world):
+        assert torch.allclose(ret[r], ref, atol=1e-6), r
+
+
+def test_flat_params_views():
+    a = torch.randn(3, 2).requires_grad_(True)
+    b = torch.randn(5).requires_grad_(True)
+    a0, b0 = a.detach().clone(), b.detach().clone()
+    fp = FlatParams([a, b])
+    assert torch.equal(a.detach(), a0) and torch.equal(b.detach(), b0)
+    (a.sum() * 2 + (b ** 2).sum()).backward()
+    assert torch.allclose(fp.grad[:6], torch.full((6,), 2.0))
+    assert torch.allclose(fp.grad[6:], 2 * b0)
+    with torch.no_grad():
+        fp.flat.add_(1.0)
+    assert torch.allclose(a.detach(), a0 + 1)
+
+
+def test_shard_rays_ragged():
+    rays = {"x": torch.arange(10), "k": "v"}
+    parts = [shard_rays(rays, r, 4)["x"] for r in range(4)]
+    assert torch.equal(torch.cat(parts), rays["x"])
+    assert [p.numel() for p in parts] == [3, 3, 3, 1]
