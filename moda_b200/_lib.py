@@ -46,6 +46,9 @@ SIGNATURES = {
     "moda_linear_wgrad": [c_i, c_i, c_i, c_pp, c_ip, c_ip, c_ip, c_ip, c_fp, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
     "moda_segsum": [c_p, c_i, c_p, c_i, c_i, c_i, c_p],
     "moda_sample_pdf": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "moda_tc_linear": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p,
+                       c_p, c_i, c_i, c_p, c_i, c_p, c_p],
+    "moda_tc_wgrad": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 
@@ -104,7 +107,7 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise RuntimeError("moda_b200 ops need CUDA tensors (there is no CPU fallback); got a %s tensor" % t.device)
-    if t.dtype not in (torch.float32, torch.uint8, torch.bool):
+    if t.dtype not in (torch.float32, torch.float16, torch.uint8, torch.bool):
         raise RuntimeError("moda_b200 ops need float32 tensors; got %s" % t.dtype)
     if not t.is_contiguous():
         raise RuntimeError("moda_b200 ops need contiguous tensors")

@@ -1,0 +1,563 @@
+// Tensor-core (tcgen05 / TMEM / TMA) linear layers for the 8x256 trunk MLP (nnutils/nerf.py:147-198).
+//
+//   tc_linear : Y[M,N] = epi( [A1 | A2][M,K] * B[N,K]^T )   fp16 operands, fp32 accumulation in TMEM
+//               used for the forward layers (B = W) and the data-gradient chain (B = W^T), with bias /
+//               per-ray bias / ReLU / ReLU-mask / rank-1 term fused into the epilogue.
+//   tc_wgrad  : dW[N,K] += dY[M,N]^T * X[M,K]                 both operands MN-major straight from the same
+//               row-major activation tiles (no transposes in memory).
+//
+// Structure of tc_linear (one CTA per SM, persistent over 128-row tiles):
+//   warp 0   : TMA producer.  Loads the whole weight matrix once (it stays resident in shared memory for the
+//              life of the CTA: <= 160 KB), then streams 128x64 fp16 activation chunks through a 4-deep ring.
+//   warp 1   : allocates TMEM (2 accumulators x N columns) and issues tcgen05.mma (one elected lane).
+//   warps 2-5: epilogue.  tcgen05.ld the finished accumulator (32 columns at a time), apply the fused
+//              epilogue and write fp16 / fp32 rows, while warp 1 already fills the other accumulator.
+// All shared-memory operand tiles use the 128-byte swizzle that TMA writes and UMMA descriptors read.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace moda {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrives when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor for kind::f16 with fp16 A/B and fp32 D (InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TILE_M = 128;
+constexpr int CHUNK_K = 64;                        // fp16 elements per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * CHUNK_K * 2;  // 16 KB
+constexpr int LIN_MAX_STAGES = 4;
+constexpr int LIN_THREADS = 192;
+
+struct LinEpi {
+  const float* bias;      // (N) or null
+  const float* rowbias;   // (M/rep, N) or null: per-ray bias (hoisted per-ray-constant inputs)
+  int rep;
+  int relu;
+  const __half* mask;     // (M, ldm) or null: output is zeroed where mask <= 0 (ReLU of the producing layer)
+  int ldm;
+  const float* rv;        // (M) or null  } rank-1 term rv[m] * cv[n] * (*rscale) added before masking
+  const float* cv;        // (N)          } (the sigma head's data gradient)
+  const float* rscale;    // device scalar or null (=1)
+  __half* y16;            // (M, ldy16) or null
+  int ldy16;
+  int acc16;              // y16 += result instead of =
+  float* y32;             // (M, ldy32) or null, multiplied by *oscale when given
+  int ldy32;
+  const float* oscale;
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(LIN_THREADS, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                 const __grid_constant__ CUtensorMap mapB, int M, int k1c, int k2c, int LIN_STAGES, LinEpi ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int KC = k1c + k2c;
+  constexpr int B_CHUNK_BYTES = N_TILE * CHUNK_K * 2;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + (size_t)KC * B_CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + LIN_STAGES * A_STAGE_BYTES);
+  uint64_t* full = bars;                    // [LIN_STAGES]
+  uint64_t* empty = bars + LIN_MAX_STAGES;  // [LIN_STAGES]
+  uint64_t* b_full = bars + 2 * LIN_MAX_STAGES; // [1]
+  uint64_t* t_full = b_full + 1;            // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [N_TILE]
+  float* s_cv = s_bias + N_TILE;                             // [N_TILE]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (M + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LIN_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < N_TILE; i += LIN_THREADS) {
+    s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
+    s_cv[i] = ep.cv ? ep.cv[i] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      prefetch_tmap(&mapA1);
+      prefetch_tmap(&mapB);
+      mbar_expect_tx(b_full, (uint32_t)(KC * B_CHUNK_BYTES));
+      for (int kc = 0; kc < KC; ++kc) tma_load_2d(sB + (size_t)kc * B_CHUNK_BYTES, &mapB, b_full, kc * CHUNK_K, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], A_STAGE_BYTES);
+          if (kc < k1c) tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA1, &full[stage], kc * CHUNK_K, t * TILE_M);
+          else tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA2, &full[stage], (kc - k1c) * CHUNK_K, t * TILE_M);
+          if (++stage == LIN_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, N_TILE, 0, 0);
+      mbar_wait(b_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (size_t)kc * B_CHUNK_BYTES);
+#pragma unroll
+          for (int k = 0; k < CHUNK_K / 16; ++k) {
+            const uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the A stage when these MMAs retire
+          if (++stage == LIN_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&t_full[buf]);     // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const float rscale = ep.rscale ? *ep.rscale : 1.0f;
+    const float oscale = ep.oscale ? *ep.oscale : 1.0f;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(&t_full[buf], bphase);
+      tc_fence_after();
+      const int row = t * TILE_M + q * 32 + lane;
+      const bool live = row < M;
+      const float rvv = (ep.rv && live) ? ep.rv[row] * rscale : 0.f;
+      const float* rb = (ep.rowbias && live) ? ep.rowbias + (size_t)(row / ep.rep) * N_TILE : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N_TILE + c0), v);
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + s_bias[c0 + j];
+            if (rb) x += rb[c0 + j];
+            if (ep.rv) x = fmaf(rvv, s_cv[c0 + j], x);
+            if (ep.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+          }
+          if (ep.mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + (size_t)row * ep.ldm + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 mv = mp[j4];
+              const __half2* mh = reinterpret_cast<const __half2*>(&mv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 mf = __half22float2(mh[e]);
+                if (!(mf.x > 0.f)) v[j4 * 8 + 2 * e] = 0.f;
+                if (!(mf.y > 0.f)) v[j4 * 8 + 2 * e + 1] = 0.f;
+              }
+            }
+          }
+          if (ep.y16) {
+            uint4* yp = reinterpret_cast<uint4*>(ep.y16 + (size_t)row * ep.ldy16 + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 o;
+              __half2* oh = reinterpret_cast<__half2*>(&o);
+              if (ep.acc16) {
+                const uint4 old = yp[j4];
+                const __half2* ph = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 pf = __half22float2(ph[e]);
+                  oh[e] = __floats2half2_rn(v[j4 * 8 + 2 * e] + pf.x, v[j4 * 8 + 2 * e + 1] + pf.y);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[j4 * 8 + 2 * e], v[j4 * 8 + 2 * e + 1]);
+              }
+              yp[j4] = o;
+            }
+          }
+          if (ep.y32) {
+            float4* yp = reinterpret_cast<float4*>(ep.y32 + (size_t)row * ep.ldy32 + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              yp[j4] = make_float4(v[j4 * 4] * oscale, v[j4 * 4 + 1] * oscale, v[j4 * 4 + 2] * oscale,
+                                   v[j4 * 4 + 3] * oscale);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * N_TILE);
+  }
+}
+
+// -------------------------------------------------------------------------------------------- wgrad
+// dW[n, k] += oscale * sum_m dY[m, n] X[m, k].  Per stage: 64 rows (samples) of dY (NOUT columns) and of X
+// (KIN columns), each as 64-column TMA boxes of 64 rows x 128 B (8 KB).  As UMMA operands both are MN-major:
+// the 128-byte rows run along M (resp. N) and the row index is K.
+constexpr int WG_ROWS = 64;
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;  // 8 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_THREADS = 192;
+
+template <int NOUT, int KIN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, int M,
+                float* dW, int ldw, const float* oscale_p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int YB = NOUT / 64, XB = KIN / 64;       // boxes per operand per stage
+  constexpr int STAGE_BYTES = (YB + XB) * WG_BOX_BYTES;
+  constexpr int MB = (NOUT + 127) / 128;             // 128-row blocks of the accumulator
+  constexpr int MBLK = 128;                          // UMMA M
+  static_assert(NOUT % 128 == 0, "output channels must come in blocks of 128");
+  constexpr int TCOLS = MB * KIN <= 32 ? 32 : (MB * KIN <= 64 ? 64 : (MB * KIN <= 128 ? 128 : (MB * KIN <= 256 ? 256 : 512)));
+  static_assert(MB * KIN <= 512, "accumulator does not fit TMEM");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WG_STAGES;
+  uint64_t* done = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_chunks = (M + WG_ROWS - 1) / WG_ROWS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < num_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&mapY);
+      prefetch_tmap(&mapX);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
+        uint8_t* s = smem + stage * STAGE_BYTES;
+        for (int b = 0; b < YB; ++b) tma_load_2d(s + b * WG_BOX_BYTES, &mapY, &full[stage], b * 64, c * WG_ROWS);
+        for (int b = 0; b < XB; ++b)
+          tma_load_2d(s + (YB + b) * WG_BOX_BYTES, &mapX, &full[stage], b * 64, c * WG_ROWS);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      constexpr uint32_t idesc = make_idesc(MBLK, KIN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t y_addr = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t x_addr = y_addr + YB * WG_BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_ROWS / 16; ++k) {
+          // K advances by 16 rows = 2048 B; LBO = next 64 MN elements (next box), SBO = next 8 K rows
+          const uint64_t bd = make_desc(x_addr + k * 2048, WG_BOX_BYTES, 1024);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint64_t ad = make_desc(y_addr + mb * 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES, 1024);
+            umma_f16(tmem_base + (uint32_t)(mb * KIN), ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(&empty[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const float oscale = oscale_p ? *oscale_p : 1.0f;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int mb = 0; mb < MB; ++mb) {
+      const int n = mb * 128 + q * 32 + lane;  // output channel (row of dW)
+#pragma unroll 1
+      for (int c0 = 0; c0 < KIN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * KIN + c0), v);
+        if (n < NOUT) {
+          float* o = dW + (size_t)n * ldw + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * oscale);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace moda
+
+using namespace moda;
+using namespace moda::tc;
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major (rows, cols) with row stride ld elements; box = 64 columns x box_rows rows, 128B swizzle
+static int make_map(CUtensorMap* map, const void* ptr, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  MODA_REQUIRE(enc != nullptr, "tc: cuTensorMapEncodeTiled is not available from the driver");
+  MODA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0 && cols % 64 == 0 && ld >= cols,
+               "tc: operand (ptr %p, cols %d, ld %d) violates TMA alignment (16 B base, 16 B row pitch, 64-col chunks)",
+               ptr, cols, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MODA_REQUIRE(r == CUDA_SUCCESS, "tc: cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int N_TILE>
+static int launch_linear(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, int M, int k1c, int k2c,
+                         const LinEpi& ep, cudaStream_t stream) {
+  const int KC = k1c + k2c;
+  int stages = LIN_MAX_STAGES;
+  size_t smem = 0;
+  for (; stages >= 2; --stages) {
+    smem = 1024 + (size_t)KC * N_TILE * CHUNK_K * 2 + (size_t)stages * A_STAGE_BYTES + 256 + 2 * N_TILE * 4;
+    if (smem <= 232448) break;
+  }
+  MODA_REQUIRE(smem <= 232448, "tc_linear: K=%d N=%d needs %zu B of shared memory", KC * 64, N_TILE, smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_linear_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    attr_set = true;
+  }
+  const int tiles = (M + TILE_M - 1) / TILE_M;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  tc_linear_kernel<N_TILE><<<grid, LIN_THREADS, smem, stream>>>(a1, a2, b, M, k1c, k2c, stages, ep);
+  return check_launch("tc_linear");
+}
+
+// Y = epi([A1 | A2] B^T).  A1 (M,K1) ld lda1, A2 (M,K2) ld lda2 (K2 may be 0), B (N, K1+K2) ld ldb; all fp16.
+extern "C" int moda_tc_linear(const void* A1, int lda1, int K1, const void* A2, int lda2, int K2, const void* B,
+                              int ldb, int M, int N, const float* bias, const float* rowbias, int rep, int relu,
+                              const void* mask, int ldm, const float* rv, const float* cv, const float* rscale,
+                              void* y16, int ldy16, int acc16, float* y32, int ldy32, const float* oscale,
+                              cudaStream_t stream) {
+  if (M == 0) return 0;
+  MODA_REQUIRE(A1 && B && K1 > 0 && K1 % 64 == 0 && K2 % 64 == 0 && (K2 == 0 || A2), "tc_linear: bad operands");
+  MODA_REQUIRE(N == 64 || N == 128 || N == 256, "tc_linear: N=%d (supported: 64, 128, 256)", N);
+  MODA_REQUIRE(y16 || y32, "tc_linear: no output");
+  MODA_REQUIRE((!y16 || (ldy16 % 8 == 0)) && (!y32 || (ldy32 % 4 == 0)) && (!mask || (ldm % 8 == 0)),
+               "tc_linear: output / mask row pitch must keep 16-byte alignment");
+  CUtensorMap a1, a2, b;
+  if (int e = make_map(&a1, A1, M, K1, lda1, TILE_M)) return e;
+  if (K2 > 0) { if (int e = make_map(&a2, A2, M, K2, lda2, TILE_M)) return e; } else a2 = a1;
+  if (int e = make_map(&b, B, N, K1 + K2, ldb, N)) return e;
+  LinEpi ep;
+  ep.bias = bias; ep.rowbias = rowbias; ep.rep = rep > 0 ? rep : 1; ep.relu = relu;
+  ep.mask = reinterpret_cast<const __half*>(mask); ep.ldm = ldm; ep.rv = rv; ep.cv = cv; ep.rscale = rscale;
+  ep.y16 = reinterpret_cast<__half*>(y16); ep.ldy16 = ldy16; ep.acc16 = acc16; ep.y32 = y32; ep.ldy32 = ldy32;
+  ep.oscale = oscale;
+  MODA_REQUIRE(!rv || cv, "tc_linear: rank-1 term needs both vectors");
+  if (N == 256) return launch_linear<256>(a1, a2, b, M, K1 / 64, K2 / 64, ep, stream);
+  if (N == 128) return launch_linear<128>(a1, a2, b, M, K1 / 64, K2 / 64, ep, stream);
+  return launch_linear<64>(a1, a2, b, M, K1 / 64, K2 / 64, ep, stream);
+}
+
+template <int NOUT, int KIN>
+static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x, int M, float* dW, int ldw, const float* oscale,
+                        cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_wgrad_kernel<NOUT, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    attr_set = true;
+  }
+  const int chunks = (M + WG_ROWS - 1) / WG_ROWS;
+  const int grid = chunks < sm_count() ? chunks : sm_count();
+  tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(y, x, M, dW, ldw, oscale);
+  return check_launch("tc_wgrad");
+}
+
+// dW (N, ldw) fp32 += oscale * dY (M,N)^T X (M,K); dY, X fp16 row-major.  Accumulates (zero dW first).
+extern "C" int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
+                             const float* oscale, cudaStream_t stream) {
+  if (M == 0) return 0;
+  MODA_REQUIRE(dY && X && dW, "tc_wgrad: null pointer");
+  CUtensorMap y, x;
+  if (int e = make_map(&y, dY, M, N, ldy, WG_ROWS)) return e;
+  if (int e = make_map(&x, X, M, K, ldx, WG_ROWS)) return e;
+  if (N == 256 && K == 256) return launch_wgrad<256, 256>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 256 && K == 64) return launch_wgrad<256, 64>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 256 && K == 128) return launch_wgrad<256, 128>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 128 && K == 256) return launch_wgrad<128, 256>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 128 && K == 128) return launch_wgrad<128, 128>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 128 && K == 64) return launch_wgrad<128, 64>(y, x, M, dW, ldw, oscale, stream);
+  MODA_REQUIRE(false, "tc_wgrad: shape N=%d K=%d not instantiated", N, K);
+  return -1;
+}
