@@ -134,6 +134,44 @@ int moda_segsum(const float* in, int ld, float* out, int R, int S, int N, cudaSt
 int moda_act_bwd(int kind, const float* y, int ldy, const float* g, int ldg, float* out, int ldo, long long M,
                  int N, cudaStream_t stream);
 
+/* ---- tensor-core (tcgen05 / TMEM / TMA) linear layers for the 8x256 trunk: NeRF.forward, nerf.py:147-198 --
+ * fp16 operands (row-major, 16-byte aligned, row pitch multiple of 8 elements, K multiple of 64), fp32
+ * accumulation.  Y[M,N] = epi([A1 | A2][M,K1+K2] B[N,K1+K2]^T), N in {64,128,256}.  Epilogue, in order:
+ * + bias[n] + rowbias[m/rep][n] + rv[m] cv[n] (*rscale);  ReLU;  zero where mask[m][n] <= 0;  then
+ * y16 (=|+= when acc16) and/or y32 = value * (*oscale).  bias/rowbias/rv/cv/rscale/oscale are fp32 device
+ * pointers (scalars for rscale/oscale), any of them may be NULL. */
+int moda_tc_linear(const void* A1, int lda1, int K1, const void* A2, int lda2, int K2, const void* B, int ldb, int M,
+                   int N, const float* bias, const float* rowbias, int rep, int relu, const void* mask, int ldm,
+                   const float* rv, const float* cv, const float* rscale, void* y16, int ldy16, int acc16, float* y32,
+                   int ldy32, const float* oscale, cudaStream_t stream);
+/* dW (N, ldw) fp32 += (*oscale) dY[M,N]^T X[M,K], first k_valid columns only; (N,K) in {256,128} x {64,128,256}.
+ * Both operands are consumed MN-major straight from their row-major fp16 storage. */
+int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
+                  int k_valid, const float* oscale, cudaStream_t stream);
+/* fp16 operand staging for the trunk: positional encoding of (P,3) points into (P,64) [63 channels + zero pad]
+ * (Embedding.forward, nerf.py:35-75) and its adjoint (gxyz (=|+=) (*inv_scale) J^T g16) */
+int moda_pe16_fwd(const float* xyz, void* out16, int ldo, long long P, int F, const float* win, cudaStream_t stream);
+int moda_pe16_bwd(const float* xyz, const void* g16, int ldg, float* gxyz, long long P, int F, const float* win,
+                  const float* inv_scale, int accumulate, cudaStream_t stream);
+/* fp32 weight block in[:, col0:col0+cols] (rows x cols) -> fp16 block of out_rows x width (row pitch ld_out),
+ * zero padded, optionally transposed */
+int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, int ld_out, int out_rows,
+                int width, int transpose, cudaStream_t stream);
+/* sigma (256->1) and rgb (128->3, sigmoid) heads (nerf.py:178, 188-195) on fp16 activations; raw (P,4) fp32 */
+int moda_head_fwd(const void* H8, const void* Dfe, const float* ws, const float* bs, const float* Wr,
+                  const float* br, float* raw, long long P, cudaStream_t stream);
+/* their adjoint: dDfe16 = (*scale) (g_pre Wr) relu'(Dfe), gsig = graw[:,3]; gWr/gbr/gws/gbs accumulated */
+int moda_head_bwd(const void* H8, const void* Dfe, const float* raw, const float* graw, const float* Wr,
+                  const float* scale, void* dDfe, float* gsig, float* gWr, float* gbr, float* gws, float* gbs,
+                  long long P, cudaStream_t stream);
+/* out[n] += (*oscale) sum_m in16[m][n]   /   out (R,N) = (*oscale) per-ray sums of S consecutive rows */
+int moda_colsum16(const void* in16, int ld, float* out, long long M, int N, const float* oscale, cudaStream_t stream);
+int moda_segsum16(const void* in16, int ld, float* out, int R, int S, int N, const float* oscale,
+                  cudaStream_t stream);
+/* scale2 = {S, 1/S}, S = 2^floor(log2(target / max|g|)): loss scale of the fp16 gradient chain; work: 1 uint */
+int moda_loss_scale(const float* g, long long n, float target, unsigned int* work, float* scale2,
+                    cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,17 @@
+"""Run-time switches of the CUDA path.
+
+precision:
+  "fp16"  (default) the 8x256 trunk runs on tcgen05 tensor cores with fp16 operands and fp32 accumulation
+          (csrc/tc_gemm.cu); nerf_skin and all skinning / compositing math stay fp32.
+  "fp32"  every linear layer runs on the fp32 SIMT kernels (csrc/gemm.cu): the exact mode used to pin parity.
+"""
+import os
+
+precision = os.environ.get("MODA_B200_PRECISION", "fp16")
+
+
+def set_precision(p):
+    global precision
+    if p not in ("fp16", "fp32"):
+        raise ValueError("precision must be 'fp16' or 'fp32'")
+    precision = p

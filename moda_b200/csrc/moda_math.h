@@ -172,7 +172,8 @@ MODA_HD void bone_ctx_bwd(const float* bone, float kappa, const float* acc, floa
     gbone[7 + k] += gl;
     ga += gl;
   }
-  *gaux0 += ga;
+  (void)ga;
+  (void)gaux0;  // d/d skin_aux[0] is accumulated per sample in skin_point_bwd (better conditioned)
   float gqh[4] = {0.f, 0.f, 0.f, 0.f};
   quat_to_mat_bwd(qh, gR, gqh);
   const float dot = gqh[0] * qh[0] + gqh[1] * qh[1] + gqh[2] * qh[2] + gqh[3] * qh[3];
@@ -247,7 +248,7 @@ MODA_HD void dq_apply_bwd(const float* c, float inv_n, float px, float py, float
 // ctx: B contexts of CTX_STRIDE floats.  dl: delta logits (B) or null.  win: given weights (B) or null.
 // Returns the blended (weight-normalised, not yet unit) dual quaternion in bl, softmax max / sum for reuse.
 MODA_HD void skin_point_blend(const float* ctx, int B, float px, float py, float pz, const float* dl,
-                              const float* win, float* bl, float* mx_out, float* sum_out) {
+                              const float* win, float* bl, float* mx_out, float* sum_out, float* gref_out = nullptr) {
   for (int i = 0; i < 8; ++i) bl[i] = 0.f;
   if (win) {
     for (int b = 0; b < B; ++b) {
@@ -256,14 +257,16 @@ MODA_HD void skin_point_blend(const float* ctx, int B, float px, float py, float
       for (int i = 0; i < 8; ++i) bl[i] += wb * c[i];
     }
     *mx_out = 0.f; *sum_out = 1.f;
+    if (gref_out) *gref_out = 0.f;
     return;
   }
-  float mx = -INFINITY;
+  float mx = -INFINITY, gref = 0.f;
   for (int b = 0; b < B; ++b) {
-    float l = bone_logit(ctx + b * CTX_STRIDE, px, py, pz);
-    if (dl) l += dl[b];
-    mx = fmaxf(mx, l);
+    const float lg = bone_logit(ctx + b * CTX_STRIDE, px, py, pz);
+    const float l = dl ? lg + dl[b] : lg;
+    if (l > mx) { mx = l; gref = lg; }
   }
+  if (gref_out) *gref_out = gref;
   float sum = 0.f;
   for (int b = 0; b < B; ++b) {
     float l = bone_logit(ctx + b * CTX_STRIDE, px, py, pz);
@@ -286,9 +289,12 @@ MODA_HD void skin_point_blend(const float* ctx, int B, float px, float py, float
 template <class Emit>
 MODA_HD void skin_point_bwd(const float* ctx, int B, float px, float py, float pz, const float* dl,
                             const float* win, const float* gy, const float* gsk, bool live, float* gp,
-                            float* gdl, float* gwin, Emit& emit) {
-  float bl[8], mx, sum;
-  skin_point_blend(ctx, B, px, py, pz, dl, win, bl, &mx, &sum);
+                            float* gdl, float* gwin, float* gaux_pt, Emit& emit) {
+  float bl[8], mx, sum, gref;
+  skin_point_blend(ctx, B, px, py, pz, dl, win, bl, &mx, &sum, &gref);
+  // d/d skin_aux[0] = sum_b gl_b * (Gaussian logit_b).  sum_b gl_b = 0, so the logits are shifted by the
+  // arg-max bone's (gref) before the product: same value, without the cancellation of O(100) offsets.
+  float gaux = 0.f;
   const float inv_sum = 1.0f / sum;
   float gb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   gp[0] = gp[1] = gp[2] = 0.f;
@@ -328,10 +334,11 @@ MODA_HD void skin_point_bwd(const float* ctx, int B, float px, float py, float p
       const float u0 = cb[0] * dx + cb[1] * dy + cb[2] * dz;
       const float u1 = cb[4] * dx + cb[5] * dy + cb[6] * dz;
       const float u2 = cb[8] * dx + cb[9] * dy + cb[10] * dz;
-      float l = -(u0 * u0 + u1 * u1 + u2 * u2);
-      if (dl) l += dl[b];
+      const float lgauss = -(u0 * u0 + u1 * u1 + u2 * u2);
+      const float l = dl ? lgauss + dl[b] : lgauss;
       w = live ? expf(l - mx) * inv_sum : 0.f;
       gl = w * (gw - gs);
+      gaux = fmaf(gl, lgauss - gref, gaux);
       if (gdl && live) gdl[b] = gl;
       const float g0 = -2.f * gl * u0, g1 = -2.f * gl * u1, g2 = -2.f * gl * u2;  // gu
       v[0] = g0 * dx; v[1] = g0 * dy; v[2] = g0 * dz;
@@ -346,6 +353,7 @@ MODA_HD void skin_point_bwd(const float* ctx, int B, float px, float py, float p
     for (int i = 0; i < 8; ++i) v[12 + i] = w * gb[i];
     emit(b, v, (gl != 0.f) || (w != 0.f));
   }
+  *gaux_pt = gaux;
 }
 
 // Everything the first B threads of a CTA do per bone, forward: rest bone + ray DQ -> bone used + context.

@@ -127,16 +127,16 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
   const float* win = a.skin_in ? a.skin_in + pi * B : nullptr;
   const float* gsk = a.gskin ? a.gskin + pi * B : nullptr;
   const float* gy = (a.gy && a.rts) ? a.gy + pi * 3 : nullptr;
-  float gp[3];
+  float gp[3], gaux_pt;
   WarpEmit emit{acc, lane};
   skin_point_bwd(ctx, B, px, py, pz, dl, win, gy, gsk, live, gp, a.gdskin ? a.gdskin + pi * B : nullptr,
-                 a.gskin_in ? a.gskin_in + pi * B : nullptr, emit);
+                 a.gskin_in ? a.gskin_in + pi * B : nullptr, &gaux_pt, emit);
   if (a.gpts && live) { a.gpts[pi * 3] = gp[0]; a.gpts[pi * 3 + 1] = gp[1]; a.gpts[pi * 3 + 2] = gp[2]; }
   __syncthreads();
 
   // ---- per-bone epilogue ----
   const int b = threadIdx.x;
-  float gaux0 = 0.f;
+  float gaux0 = gaux_pt;
   if (b < B) {
     const float kappa = 1000.0f * expf(a.skin_aux[0]);
     const float* bone = a.bones + ((size_t)(a.bones_per_ray ? ray : 0) * B + b) * 10;
@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
       const float* r = a.rts + ((size_t)ray * B + b) * 8;
       for (int i = 0; i < 8; ++i) rr[i] = r[i];
     }
+    float unused = 0.f;
     ray_bone_setup_bwd(bn, a.rts ? rr : nullptr, a.deform, a.invert, kappa, bone_s + b * 10,
-                       acc + b * ACC_STRIDE, gbone, grt, &gaux0);
+                       acc + b * ACC_STRIDE, gbone, grt, &unused);
     if (a.grts && a.rts) {
       float* o = a.grts + ((size_t)ray * B + b) * 8;
       for (int i = 0; i < 8; ++i) atomicAdd(o + i, grt[i]);

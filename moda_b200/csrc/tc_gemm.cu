@@ -329,7 +329,7 @@ constexpr int WG_THREADS = 192;
 template <int NOUT, int KIN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, int M,
-                float* dW, int ldw, const float* oscale_p) {
+                float* dW, int ldw, int k_valid, const float* oscale_p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int YB = NOUT / 64, XB = KIN / 64;       // boxes per operand per stage
@@ -416,7 +416,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
         if (n < NOUT) {
           float* o = dW + (size_t)n * ldw + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j] * oscale);
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < k_valid) atomicAdd(o + j, v[j] * oscale);
         }
       }
     }
@@ -530,8 +531,8 @@ extern "C" int moda_tc_linear(const void* A1, int lda1, int K1, const void* A2, 
 }
 
 template <int NOUT, int KIN>
-static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x, int M, float* dW, int ldw, const float* oscale,
-                        cudaStream_t stream) {
+static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x, int M, float* dW, int ldw, int k_valid,
+                        const float* oscale, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -540,24 +541,25 @@ static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x, int M, float
   }
   const int chunks = (M + WG_ROWS - 1) / WG_ROWS;
   const int grid = chunks < sm_count() ? chunks : sm_count();
-  tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(y, x, M, dW, ldw, oscale);
+  tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(y, x, M, dW, ldw, k_valid, oscale);
   return check_launch("tc_wgrad");
 }
 
 // dW (N, ldw) fp32 += oscale * dY (M,N)^T X (M,K); dY, X fp16 row-major.  Accumulates (zero dW first).
+// Only the first k_valid columns are written (X may carry zero padding columns).
 extern "C" int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
-                             const float* oscale, cudaStream_t stream) {
+                             int k_valid, const float* oscale, cudaStream_t stream) {
   if (M == 0) return 0;
   MODA_REQUIRE(dY && X && dW, "tc_wgrad: null pointer");
   CUtensorMap y, x;
   if (int e = make_map(&y, dY, M, N, ldy, WG_ROWS)) return e;
   if (int e = make_map(&x, X, M, K, ldx, WG_ROWS)) return e;
-  if (N == 256 && K == 256) return launch_wgrad<256, 256>(y, x, M, dW, ldw, oscale, stream);
-  if (N == 256 && K == 64) return launch_wgrad<256, 64>(y, x, M, dW, ldw, oscale, stream);
-  if (N == 256 && K == 128) return launch_wgrad<256, 128>(y, x, M, dW, ldw, oscale, stream);
-  if (N == 128 && K == 256) return launch_wgrad<128, 256>(y, x, M, dW, ldw, oscale, stream);
-  if (N == 128 && K == 128) return launch_wgrad<128, 128>(y, x, M, dW, ldw, oscale, stream);
-  if (N == 128 && K == 64) return launch_wgrad<128, 64>(y, x, M, dW, ldw, oscale, stream);
+  if (N == 256 && K == 256) return launch_wgrad<256, 256>(y, x, M, dW, ldw, k_valid, oscale, stream);
+  if (N == 256 && K == 64) return launch_wgrad<256, 64>(y, x, M, dW, ldw, k_valid, oscale, stream);
+  if (N == 256 && K == 128) return launch_wgrad<256, 128>(y, x, M, dW, ldw, k_valid, oscale, stream);
+  if (N == 128 && K == 256) return launch_wgrad<128, 256>(y, x, M, dW, ldw, k_valid, oscale, stream);
+  if (N == 128 && K == 128) return launch_wgrad<128, 128>(y, x, M, dW, ldw, k_valid, oscale, stream);
+  if (N == 128 && K == 64) return launch_wgrad<128, 64>(y, x, M, dW, ldw, k_valid, oscale, stream);
   MODA_REQUIRE(false, "tc_wgrad: shape N=%d K=%d not instantiated", N, K);
   return -1;
 }

@@ -6,6 +6,7 @@ SURVEY.md section 8(f).
 """
 import torch
 
+from . import config, trunk_tc
 from .ops import (BoneTransformFn, SkinWarpFn, SEG_DENSE, SEG_BCAST, SEG_PE)
 
 
@@ -72,6 +73,13 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
             inputs.append(c)
             segs.append((SEG_BCAST, len(inputs) - 1, c.shape[-1], nbins, 0))
     cx = model.in_channels_xyz
+    # tensor-core fast path for the reference's nerf_coarse on [PE(xyz) | per-ray dir | per-ray env]
+    if (config.precision == "fp16" and not sigma_only and len(segs) in (2, 3) and segs[0][0] == SEG_PE
+            and all(sg[0] == SEG_BCAST and sg[3] == nbins for sg in segs[1:])
+            and trunk_tc.supported(model, sum(sg[2] for sg in segs[1:])) and embed_xyz.N_freqs == 10 and k == 3):
+        env = inputs[2] if len(segs) == 3 else None
+        out = trunk_tc.TrunkTcFn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
+        return out.reshape(Bn, nbins, 4)
     xyz_segs, dir_segs = _split_segments(segs, cx)
     if len(xyz_segs) > 2 or len(dir_segs) > 2:
         raise NotImplementedError("more than two column segments per input group")

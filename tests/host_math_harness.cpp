@@ -70,11 +70,12 @@ void h_skin_warp_bwd(const float* pts, const float* bones, const float* rts, con
     HostEmit emit{acc.data()};
     for (int s = 0; s < S; ++s) {
       const size_t pi = (size_t)r * S + s;
-      float gp[3];
+      float gp[3], gaux_pt = 0.f;
       skin_point_bwd(ctx.data(), B, pts[pi * 3], pts[pi * 3 + 1], pts[pi * 3 + 2],
                      dskin ? dskin + pi * B : nullptr, skin_in ? skin_in + pi * B : nullptr,
                      (gy && rts) ? gy + pi * 3 : nullptr, gskin ? gskin + pi * B : nullptr, true, gp,
-                     gdskin ? gdskin + pi * B : nullptr, gskin_in ? gskin_in + pi * B : nullptr, emit);
+                     gdskin ? gdskin + pi * B : nullptr, gskin_in ? gskin_in + pi * B : nullptr, &gaux_pt, emit);
+      if (gaux) gaux[0] += gaux_pt;
       if (gpts) { gpts[pi * 3] = gp[0]; gpts[pi * 3 + 1] = gp[1]; gpts[pi * 3 + 2] = gp[2]; }
     }
     for (int b = 0; b < B; ++b) {
