@@ -85,13 +85,14 @@ int moda_bone_transform_bwd(const float* bones, const float* rts, const float* g
  * pts (R,S,3); rts (R,B,8) or NULL (weights only); dskin / skin_in / y / skin_out (R,S,*) optional. */
 int moda_skin_warp_fwd(const float* pts, const float* bones, const float* rts, const float* skin_aux,
                        const float* dskin, const float* skin_in, float* y, float* skin_out, int R, int S, int B,
-                       int bones_per_ray, int deform, int invert, cudaStream_t stream);
+                       int ld_dskin /* row pitch of dskin, 0 = B */, int bones_per_ray, int deform, int invert,
+                       cudaStream_t stream);
 /* gy (R,S,3) / gskin (R,S,B): incoming gradients (either may be NULL).  gpts, gdskin, gskin_in overwritten;
  * grts (R,B,8), gbones, gaux (2) accumulated (zero them first). */
 int moda_skin_warp_bwd(const float* pts, const float* bones, const float* rts, const float* skin_aux,
                        const float* dskin, const float* skin_in, const float* gy, const float* gskin, float* gpts,
                        float* gdskin, float* gskin_in, float* grts, float* gbones, float* gaux, int R, int S,
-                       int B, int bones_per_ray, int deform, int invert, cudaStream_t stream);
+                       int B, int ld_dskin, int bones_per_ray, int deform, int invert, cudaStream_t stream);
 
 /* ---- compositing: inference, nnutils/rendering.py:183-235 (+ frame_cyc_dis :341,:473) ------------------
  * rgb (P,3; row stride ld_rgb), sigma (P; stride ld_sigma), z (R,S), d (R,3), beta (1); noise (R,S) and
@@ -150,13 +151,28 @@ int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K,
                   int k_valid, const float* oscale, cudaStream_t stream);
 /* fp16 operand staging for the trunk: positional encoding of (P,3) points into (P,64) [63 channels + zero pad]
  * (Embedding.forward, nerf.py:35-75) and its adjoint (gxyz (=|+=) (*inv_scale) J^T g16) */
-int moda_pe16_fwd(const float* xyz, void* out16, int ldo, long long P, int F, const float* win, cudaStream_t stream);
-int moda_pe16_bwd(const float* xyz, const void* g16, int ldg, float* gxyz, long long P, int F, const float* win,
-                  const float* inv_scale, int accumulate, cudaStream_t stream);
+int moda_pe16_fwd(const float* xyz, void* out16, void* out16lo /* NULL, or low half of the split pair */, int ldo,
+                  long long P, int F, const float* win, cudaStream_t stream);
+int moda_pe16_bwd(const float* xyz, const void* g16, const void* g16lo, int ldg, float* gxyz, long long P, int F,
+                  const float* win, const float* inv_scale, int accumulate, cudaStream_t stream);
 /* fp32 weight block in[:, col0:col0+cols] (rows x cols) -> fp16 block of out_rows x width (row pitch ld_out),
  * zero padded, optionally transposed */
-int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, int ld_out, int out_rows,
-                int width, int transpose, cudaStream_t stream);
+int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, void* out16_dup,
+                void* out16_lo, int ld_out, int out_rows, int width, int transpose, cudaStream_t stream);
+/* fp32 (M, cols) * (*scale) -> fp16 (hi, lo) pair, zero padded to `width` columns (lo may be NULL) */
+int moda_split16(const float* in, int ld_in, int cols, const float* scale, void* hi, void* lo, int ld_out, int width,
+                 long long M, cudaStream_t stream);
+/* Split-precision (fp32-class) variants used for nerf_skin: operands are fp16 (hi, lo) pairs, value = hi + lo;
+ * x W^T ~= hi Whi^T + lo Whi^T + hi Wlo^T runs as one GEMM over K = [hi | lo | hi] against B3 = [Whi | Whi | Wlo]
+ * (N, 3K).  Outputs: fp16 (hi, lo) pair and/or fp32. */
+int moda_tc_linear_split(const void* A1hi, const void* A1lo, int lda1, int K1, const void* A2hi, const void* A2lo,
+                         int lda2, int K2, const void* B3, int ldb, int M, int N, const float* bias,
+                         const float* rowbias, int rep, int relu, const void* mask, int ldm, void* yhi, void* ylo,
+                         int ldy16, int acc16, float* y32, int ldy32, const float* oscale, cudaStream_t stream);
+/* dW += (*oscale) (dYhi + dYlo)^T (Xhi + Xlo) (lo*lo dropped); rows >= n_valid / cols >= k_valid not written */
+int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, int N, const void* Xhi, const void* Xlo, int ldx,
+                        int K, int M, float* dW, int ldw, int n_valid, int k_valid, const float* oscale,
+                        cudaStream_t stream);
 /* sigma (256->1) and rgb (128->3, sigmoid) heads (nerf.py:178, 188-195) on fp16 activations; raw (P,4) fp32 */
 int moda_head_fwd(const void* H8, const void* Dfe, const float* ws, const float* bs, const float* Wr,
                   const float* br, float* raw, long long P, cudaStream_t stream);
@@ -166,7 +182,7 @@ int moda_head_bwd(const void* H8, const void* Dfe, const float* raw, const float
                   long long P, cudaStream_t stream);
 /* out[n] += (*oscale) sum_m in16[m][n]   /   out (R,N) = (*oscale) per-ray sums of S consecutive rows */
 int moda_colsum16(const void* in16, int ld, float* out, long long M, int N, const float* oscale, cudaStream_t stream);
-int moda_segsum16(const void* in16, int ld, float* out, int R, int S, int N, const float* oscale,
+int moda_segsum16(const void* in16, int ld, float* out, int R, int S, int N, const float* oscale, int accumulate,
                   cudaStream_t stream);
 /* scale2 = {S, 1/S}, S = 2^floor(log2(target / max|g|)): loss scale of the fp16 gradient chain; work: 1 uint */
 int moda_loss_scale(const float* g, long long n, float target, unsigned int* work, float* scale2,

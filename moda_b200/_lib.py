@@ -37,8 +37,8 @@ SIGNATURES = {
     "moda_dq_mul_bwd": [c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_p],
     "moda_bone_transform_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "moda_bone_transform_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
-    "moda_skin_warp_fwd": [c_p] * 8 + [c_i] * 6 + [c_p],
-    "moda_skin_warp_bwd": [c_p] * 14 + [c_i] * 6 + [c_p],
+    "moda_skin_warp_fwd": [c_p] * 8 + [c_i] * 7 + [c_p],
+    "moda_skin_warp_bwd": [c_p] * 14 + [c_i] * 7 + [c_p],
     "moda_composite_fwd": [c_p, c_i, c_p, c_i] + [c_p] * 13 + [c_i, c_i, c_p],
     "moda_composite_bwd": [c_p, c_i, c_p, c_i] + [c_p] * 13 + [c_p, c_i, c_p, c_i] + [c_p] * 4 + [c_i, c_i, c_p],
     "moda_linear_fwd": [c_i, c_i, c_i, c_pp, c_ip, c_ip, c_ip, c_ip, c_fp, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p],
@@ -49,13 +49,17 @@ SIGNATURES = {
     "moda_tc_linear": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p,
                        c_p, c_i, c_i, c_p, c_i, c_p, c_p],
     "moda_tc_wgrad": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
-    "moda_pe16_fwd": [c_p, c_p, c_i, c_ll, c_i, c_fp, c_p],
-    "moda_pe16_bwd": [c_p, c_p, c_i, c_p, c_ll, c_i, c_fp, c_p, c_i, c_p],
-    "moda_pack16": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
+    "moda_tc_linear_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i,
+                             c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p],
+    "moda_tc_wgrad_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p],
+    "moda_pe16_fwd": [c_p, c_p, c_p, c_i, c_ll, c_i, c_fp, c_p],
+    "moda_pe16_bwd": [c_p, c_p, c_p, c_i, c_p, c_ll, c_i, c_fp, c_p, c_i, c_p],
+    "moda_pack16": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "moda_split16": [c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_ll, c_p],
     "moda_head_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
     "moda_head_bwd": [c_p] * 12 + [c_ll, c_p],
     "moda_colsum16": [c_p, c_i, c_p, c_ll, c_i, c_p, c_p],
-    "moda_segsum16": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p],
+    "moda_segsum16": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
     "moda_loss_scale": [c_p, c_ll, c_f, c_p, c_p, c_p],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }

@@ -26,6 +26,7 @@ struct SkinArgs {
   float* y;               // (R,S,3) or null
   float* skin_out;        // (R,S,B) or null
   int R, S, B;
+  int ldd;            // row pitch of dskin / gdskin (>= B)
   int bones_per_ray;  // bones indexed by ray
   int deform;         // apply bone_transform(bones, rts) first (backward warp)
   int invert;         // blend with dq_inverse(rts) (backward warp)
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_fwd_kernel(SkinArgs a)
   const size_t pi = (size_t)ray * a.S + s;
   const float px = a.pts[pi * 3], py = a.pts[pi * 3 + 1], pz = a.pts[pi * 3 + 2];
   const int B = a.B;
-  const float* dl = a.dskin ? a.dskin + pi * B : nullptr;
+  const float* dl = a.dskin ? a.dskin + pi * a.ldd : nullptr;
   const float* win = a.skin_in ? a.skin_in + pi * B : nullptr;
   float bl[8], mx, sum;
   skin_point_blend(ctx, B, px, py, pz, dl, win, bl, &mx, &sum);
@@ -123,13 +124,13 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
   const size_t pi = (size_t)ray * a.S + (live ? s : 0);
   const int lane = threadIdx.x & 31;
   const float px = a.pts[pi * 3], py = a.pts[pi * 3 + 1], pz = a.pts[pi * 3 + 2];
-  const float* dl = a.dskin ? a.dskin + pi * B : nullptr;
+  const float* dl = a.dskin ? a.dskin + pi * a.ldd : nullptr;
   const float* win = a.skin_in ? a.skin_in + pi * B : nullptr;
   const float* gsk = a.gskin ? a.gskin + pi * B : nullptr;
   const float* gy = (a.gy && a.rts) ? a.gy + pi * 3 : nullptr;
   float gp[3], gaux_pt;
   WarpEmit emit{acc, lane};
-  skin_point_bwd(ctx, B, px, py, pz, dl, win, gy, gsk, live, gp, a.gdskin ? a.gdskin + pi * B : nullptr,
+  skin_point_bwd(ctx, B, px, py, pz, dl, win, gy, gsk, live, gp, a.gdskin ? a.gdskin + pi * a.ldd : nullptr,
                  a.gskin_in ? a.gskin_in + pi * B : nullptr, &gaux_pt, emit);
   if (a.gpts && live) { a.gpts[pi * 3] = gp[0]; a.gpts[pi * 3 + 1] = gp[1]; a.gpts[pi * 3 + 2] = gp[2]; }
   __syncthreads();
@@ -204,7 +205,7 @@ using namespace moda;
 
 static int skin_check(const SkinArgs& a) {
   MODA_REQUIRE(a.B >= 1 && a.B <= MAX_BONES, "skin_warp: B=%d outside [1,%d]", a.B, MAX_BONES);
-  MODA_REQUIRE(a.R >= 0 && a.S >= 1, "skin_warp: bad sizes R=%d S=%d", a.R, a.S);
+  MODA_REQUIRE(a.R >= 0 && a.S >= 1 && a.ldd >= a.B, "skin_warp: bad sizes R=%d S=%d ld_dskin=%d", a.R, a.S, a.ldd);
   MODA_REQUIRE(a.pts && a.bones && a.skin_aux, "skin_warp: null pts/bones/skin_aux");
   MODA_REQUIRE(!(a.deform || a.invert) || a.rts, "skin_warp: deform/invert need rts");
   MODA_REQUIRE(a.R <= 65535 * 1024, "skin_warp: too many rays");
@@ -213,9 +214,10 @@ static int skin_check(const SkinArgs& a) {
 
 extern "C" int moda_skin_warp_fwd(const float* pts, const float* bones, const float* rts,
                                   const float* skin_aux, const float* dskin, const float* skin_in, float* y,
-                                  float* skin_out, int R, int S, int B, int bones_per_ray, int deform,
+                                  float* skin_out, int R, int S, int B, int ld_dskin, int bones_per_ray, int deform,
                                   int invert, cudaStream_t stream) {
   SkinArgs a = {};
+  a.ldd = ld_dskin > 0 ? ld_dskin : B;
   a.pts = pts; a.bones = bones; a.rts = rts; a.skin_aux = skin_aux; a.dskin = dskin; a.skin_in = skin_in;
   a.y = y; a.skin_out = skin_out; a.R = R; a.S = S; a.B = B; a.bones_per_ray = bones_per_ray;
   a.deform = deform; a.invert = invert;
@@ -229,7 +231,7 @@ extern "C" int moda_skin_warp_fwd(const float* pts, const float* bones, const fl
     const size_t po = (size_t)r0 * S;
     c.pts += po * 3; if (c.rts) c.rts += (size_t)r0 * B * 8;
     if (c.bones_per_ray) c.bones += (size_t)r0 * B * 10;
-    if (c.dskin) c.dskin += po * B; if (c.skin_in) c.skin_in += po * B;
+    if (c.dskin) c.dskin += po * c.ldd; if (c.skin_in) c.skin_in += po * B;
     if (c.y) c.y += po * 3; if (c.skin_out) c.skin_out += po * B;
     c.R = rc;
     dim3 grid(cdiv(S, SKIN_THREADS), rc);
@@ -242,8 +244,10 @@ extern "C" int moda_skin_warp_bwd(const float* pts, const float* bones, const fl
                                   const float* skin_aux, const float* dskin, const float* skin_in,
                                   const float* gy, const float* gskin, float* gpts, float* gdskin,
                                   float* gskin_in, float* grts, float* gbones, float* gaux, int R, int S,
-                                  int B, int bones_per_ray, int deform, int invert, cudaStream_t stream) {
+                                  int B, int ld_dskin, int bones_per_ray, int deform, int invert,
+                                  cudaStream_t stream) {
   SkinArgs a = {};
+  a.ldd = ld_dskin > 0 ? ld_dskin : B;
   a.pts = pts; a.bones = bones; a.rts = rts; a.skin_aux = skin_aux; a.dskin = dskin; a.skin_in = skin_in;
   a.R = R; a.S = S; a.B = B; a.bones_per_ray = bones_per_ray; a.deform = deform; a.invert = invert;
   a.gy = gy; a.gskin = gskin; a.gpts = gpts; a.gdskin = gdskin; a.gskin_in = gskin_in; a.grts = grts;
@@ -256,9 +260,9 @@ extern "C" int moda_skin_warp_bwd(const float* pts, const float* bones, const fl
     const size_t po = (size_t)r0 * S;
     c.pts += po * 3; if (c.rts) c.rts += (size_t)r0 * B * 8;
     if (c.bones_per_ray) { c.bones += (size_t)r0 * B * 10; if (c.gbones) c.gbones += (size_t)r0 * B * 10; }
-    if (c.dskin) c.dskin += po * B; if (c.skin_in) c.skin_in += po * B;
+    if (c.dskin) c.dskin += po * c.ldd; if (c.skin_in) c.skin_in += po * B;
     if (c.gy) c.gy += po * 3; if (c.gskin) c.gskin += po * B;
-    if (c.gpts) c.gpts += po * 3; if (c.gdskin) c.gdskin += po * B; if (c.gskin_in) c.gskin_in += po * B;
+    if (c.gpts) c.gpts += po * 3; if (c.gdskin) c.gdskin += po * c.ldd; if (c.gskin_in) c.gskin_in += po * B;
     if (c.grts) c.grts += (size_t)r0 * B * 8;
     c.R = rc;
     dim3 grid(cdiv(S, SKIN_THREADS), rc);

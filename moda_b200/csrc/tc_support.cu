@@ -12,35 +12,47 @@ namespace moda {
 struct Win16 { float w[16]; };
 
 // out (P, 64) fp16 = [x(3) | w_k sin(2^k x) | w_k cos(2^k x)]_{k<10} | 0     (63 channels + one zero pad)
-__global__ void pe16_fwd_kernel(const float* __restrict__ xyz, __half* __restrict__ out, long long P, int F,
-                                int ldo, Win16 win) {
+__global__ void pe16_fwd_kernel(const float* __restrict__ xyz, __half* __restrict__ out, __half* __restrict__ out_lo,
+                                long long P, int F, int ldo, Win16 win) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float x[3] = {xyz[p * 3], xyz[p * 3 + 1], xyz[p * 3 + 2]};
   __half* o = out + p * ldo;
   __align__(16) __half buf[64];
-  buf[0] = __float2half_rn(x[0]); buf[1] = __float2half_rn(x[1]); buf[2] = __float2half_rn(x[2]);
+  __align__(16) __half lob[64];
+  auto put = [&](int i, float v) {
+    const __half h = __float2half_rn(v);
+    buf[i] = h;
+    lob[i] = __float2half_rn(v - __half2float(h));
+  };
+  put(0, x[0]); put(1, x[1]); put(2, x[2]);
   for (int k = 0; k < F; ++k) {
     const float f = (float)(1 << k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float sn, cs;
       sincosf(x[c] * f, &sn, &cs);
-      buf[3 + 6 * k + c] = __float2half_rn(win.w[k] * sn);
-      buf[3 + 6 * k + 3 + c] = __float2half_rn(win.w[k] * cs);
+      put(3 + 6 * k + c, win.w[k] * sn);
+      put(3 + 6 * k + 3 + c, win.w[k] * cs);
     }
   }
-  for (int i = 3 + 6 * F; i < 64; ++i) buf[i] = __float2half_rn(0.f);
+  for (int i = 3 + 6 * F; i < 64; ++i) put(i, 0.f);
   const uint4* b4 = reinterpret_cast<const uint4*>(buf);
   uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o4[i] = b4[i];
+  if (out_lo) {
+    const uint4* l4 = reinterpret_cast<const uint4*>(lob);
+    uint4* ol4 = reinterpret_cast<uint4*>(out_lo + p * ldo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ol4[i] = l4[i];
+  }
 }
 
 // gxyz (P,3) (=|+=) inv_scale * dPE/dx^T g16
-__global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __restrict__ g16, int ldg,
-                                float* __restrict__ gxyz, long long P, int F, Win16 win, const float* inv_scale,
-                                int accumulate) {
+__global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __restrict__ g16,
+                                const __half* __restrict__ g16lo, int ldg, float* __restrict__ gxyz, long long P, int F,
+                                Win16 win, const float* inv_scale, int accumulate) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float is = inv_scale ? *inv_scale : 1.0f;
@@ -49,15 +61,23 @@ __global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __r
   uint4* b4 = reinterpret_cast<uint4*>(buf);
 #pragma unroll
   for (int i = 0; i < 8; ++i) b4[i] = g4[i];
+  __align__(16) __half lob[64];
+  if (g16lo) {
+    const uint4* l4 = reinterpret_cast<const uint4*>(g16lo + p * ldg);
+    uint4* lb4 = reinterpret_cast<uint4*>(lob);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lb4[i] = l4[i];
+  }
+  auto get = [&](int i) { return g16lo ? __half2float(buf[i]) + __half2float(lob[i]) : __half2float(buf[i]); };
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float x = xyz[p * 3 + c];
-    float acc = __half2float(buf[c]);
+    float acc = get(c);
     for (int k = 0; k < F; ++k) {
       const float f = (float)(1 << k);
       float sn, cs;
       sincosf(x * f, &sn, &cs);
-      acc += win.w[k] * f * (cs * __half2float(buf[3 + 6 * k + c]) - sn * __half2float(buf[3 + 6 * k + 3 + c]));
+      acc += win.w[k] * f * (cs * get(3 + 6 * k + c) - sn * get(3 + 6 * k + 3 + c));
     }
     acc *= is;
     float* o = gxyz + p * 3 + c;
@@ -66,15 +86,35 @@ __global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __r
 }
 
 // fp32 (rows, ld_in) columns [col0, col0+cols) -> fp16 block of out_rows x width (row pitch ld_out), zero padded.
-// transpose=0: out[r][c] = in[r][col0+c]; transpose=1: out[c][r] = in[r][col0+c].
+// transpose=0: out[r][c] = in[r][col0+c]; transpose=1: out[c][r] = in[r][col0+c].  Optionally a second copy of
+// the block (out2) and the low half of the split-precision pair (out_lo = fp16(v - fp16(v))).
 __global__ void pack16_kernel(const float* __restrict__ in, int ld_in, int rows, int cols, int col0,
-                              __half* __restrict__ out, int ld_out, int out_rows, int width, int transpose) {
+                              __half* __restrict__ out, __half* __restrict__ out2, __half* __restrict__ out_lo,
+                              int ld_out, int out_rows, int width, int transpose) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= out_rows * width) return;
   const int orow = t / width, ocol = t % width;
   const int r = transpose ? ocol : orow, c = transpose ? orow : ocol;
   const float v = (r < rows && c < cols) ? in[(size_t)r * ld_in + col0 + c] : 0.f;
-  out[(size_t)orow * ld_out + ocol] = __float2half_rn(v);
+  const __half h = __float2half_rn(v);
+  const size_t o = (size_t)orow * ld_out + ocol;
+  out[o] = h;
+  if (out2) out2[o] = h;
+  if (out_lo) out_lo[o] = __float2half_rn(v - __half2float(h));
+}
+
+// fp32 (M, cols; row pitch ld_in) * (*scale) -> fp16 (hi, lo) pair of width `width` (zero padded), pitch ld_out
+__global__ void split16_kernel(const float* __restrict__ in, int ld_in, int cols, const float* scale_p,
+                               __half* __restrict__ hi, __half* __restrict__ lo, int ld_out, int width, long long M) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * width) return;
+  const long long m = t / width;
+  const int c = (int)(t % width);
+  const float sc = scale_p ? *scale_p : 1.0f;
+  const float v = (c < cols) ? in[m * ld_in + c] * sc : 0.f;
+  const __half h = __float2half_rn(v);
+  hi[m * ld_out + c] = h;
+  if (lo) lo[m * ld_out + c] = __float2half_rn(v - __half2float(h));
 }
 
 // ---- output heads, one warp per sample ----------------------------------------------------------------
@@ -230,7 +270,7 @@ __global__ void colsum16_kernel(const __half* __restrict__ in, int ld, float* ou
 
 // out (R,N) fp32 = oscale * per-ray sums of S consecutive fp16 rows
 __global__ void segsum16_kernel(const __half* __restrict__ in, int ld, float* out, int R, int S, int N,
-                                const float* oscale) {
+                                const float* oscale, int accumulate) {
   const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   if (n2 * 2 >= N) return;
@@ -241,8 +281,9 @@ __global__ void segsum16_kernel(const __half* __restrict__ in, int ld, float* ou
     a += f.x; b += f.y;
   }
   const float sc = oscale ? *oscale : 1.0f;
-  out[(size_t)r * N + n2 * 2] = a * sc;
-  out[(size_t)r * N + n2 * 2 + 1] = b * sc;
+  float* o = out + (size_t)r * N + n2 * 2;
+  o[0] = accumulate ? o[0] + a * sc : a * sc;
+  o[1] = accumulate ? o[1] + b * sc : b * sc;
 }
 
 // amax over |g| -> power-of-two loss scale {S, 1/S} with S * amax ~ target
@@ -273,34 +314,46 @@ static void fill_win16(Win16& w, const float* win, int F) {
   for (int i = 0; i < 16; ++i) w.w[i] = (win && i < F) ? win[i] : 1.0f;
 }
 
-extern "C" int moda_pe16_fwd(const float* xyz, void* out16, int ldo, long long P, int F, const float* win,
-                             cudaStream_t stream) {
+extern "C" int moda_pe16_fwd(const float* xyz, void* out16, void* out16lo, int ldo, long long P, int F,
+                             const float* win, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && out16 && F >= 0 && 3 + 6 * F <= 64 && ldo >= 64 && ldo % 8 == 0, "pe16_fwd: bad arguments");
   Win16 w; fill_win16(w, win, F);
-  pe16_fwd_kernel<<<cdiv(P, 128), 128, 0, stream>>>(xyz, reinterpret_cast<__half*>(out16), P, F, ldo, w);
+  pe16_fwd_kernel<<<cdiv(P, 128), 128, 0, stream>>>(xyz, reinterpret_cast<__half*>(out16),
+                                                   reinterpret_cast<__half*>(out16lo), P, F, ldo, w);
   return check_launch("pe16_fwd");
 }
 
-extern "C" int moda_pe16_bwd(const float* xyz, const void* g16, int ldg, float* gxyz, long long P, int F,
-                             const float* win, const float* inv_scale, int accumulate, cudaStream_t stream) {
+extern "C" int moda_pe16_bwd(const float* xyz, const void* g16, const void* g16lo, int ldg, float* gxyz, long long P,
+                             int F, const float* win, const float* inv_scale, int accumulate, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && g16 && gxyz && 3 + 6 * F <= 64 && ldg >= 64 && ldg % 8 == 0, "pe16_bwd: bad arguments");
   Win16 w; fill_win16(w, win, F);
-  pe16_bwd_kernel<<<cdiv(P, 128), 128, 0, stream>>>(xyz, reinterpret_cast<const __half*>(g16), ldg, gxyz, P, F, w,
+  pe16_bwd_kernel<<<cdiv(P, 128), 128, 0, stream>>>(xyz, reinterpret_cast<const __half*>(g16),
+                                                   reinterpret_cast<const __half*>(g16lo), ldg, gxyz, P, F, w,
                                                    inv_scale, accumulate);
   return check_launch("pe16_bwd");
 }
 
-extern "C" int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, int ld_out,
-                           int out_rows, int width, int transpose, cudaStream_t stream) {
+extern "C" int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, void* out16_dup,
+                           void* out16_lo, int ld_out, int out_rows, int width, int transpose, cudaStream_t stream) {
   MODA_REQUIRE(in && out16 && rows > 0 && cols > 0 && ld_out >= width && width > 0 && out_rows > 0,
                "pack16: bad arguments");
   MODA_REQUIRE(transpose ? (width >= rows && out_rows >= cols) : (width >= cols && out_rows >= rows),
                "pack16: output block too small");
   pack16_kernel<<<cdiv((long long)out_rows * width, 256), 256, 0, stream>>>(
-      in, ld_in, rows, cols, col0, reinterpret_cast<__half*>(out16), ld_out, out_rows, width, transpose);
+      in, ld_in, rows, cols, col0, reinterpret_cast<__half*>(out16), reinterpret_cast<__half*>(out16_dup),
+      reinterpret_cast<__half*>(out16_lo), ld_out, out_rows, width, transpose);
   return check_launch("pack16");
+}
+
+extern "C" int moda_split16(const float* in, int ld_in, int cols, const float* scale, void* hi, void* lo, int ld_out,
+                            int width, long long M, cudaStream_t stream) {
+  if (M == 0) return 0;
+  MODA_REQUIRE(in && hi && width >= cols && ld_out >= width, "split16: bad arguments");
+  split16_kernel<<<cdiv(M * width, 256), 256, 0, stream>>>(in, ld_in, cols, scale, reinterpret_cast<__half*>(hi),
+                                                         reinterpret_cast<__half*>(lo), ld_out, width, M);
+  return check_launch("split16");
 }
 
 extern "C" int moda_head_fwd(const void* H8, const void* Dfe, const float* ws, const float* bs, const float* Wr,
@@ -336,14 +389,14 @@ extern "C" int moda_colsum16(const void* in16, int ld, float* out, long long M, 
 }
 
 extern "C" int moda_segsum16(const void* in16, int ld, float* out, int R, int S, int N, const float* oscale,
-                             cudaStream_t stream) {
+                             int accumulate, cudaStream_t stream) {
   if (R == 0 || N == 0) return 0;
   MODA_REQUIRE(in16 && out && N % 2 == 0 && ld % 2 == 0, "segsum16: bad arguments");
   for (int r0 = 0; r0 < R; r0 += 65535) {
     const int rc = (R - r0 < 65535) ? R - r0 : 65535;
     dim3 grid(cdiv(N / 2, 64), rc);
     segsum16_kernel<<<grid, 64, 0, stream>>>(reinterpret_cast<const __half*>(in16) + (size_t)r0 * S * ld, ld,
-                                            out + (size_t)r0 * N, rc, S, N, oscale);
+                                            out + (size_t)r0 * N, rc, S, N, oscale, accumulate);
   }
   return check_launch("segsum16");
 }

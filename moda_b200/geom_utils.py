@@ -6,7 +6,7 @@ SURVEY.md section 8(f).
 """
 import torch
 
-from . import config, trunk_tc
+from . import config, skin_tc, trunk_tc
 from .ops import (BoneTransformFn, SkinWarpFn, SEG_DENSE, SEG_BCAST, SEG_PE)
 
 
@@ -29,7 +29,7 @@ def _split_segments(segs, cx):
 
 
 def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=32 * 1024, xyz=None, code=None,
-                 appearance_code=None, sigma_only=False, use_semantic=False):
+                 appearance_code=None, sigma_only=False, use_semantic=False, _pitched=False):
     """geom_utils.py:19-57.  xyz_embedded: (B,nbins,k) points (if ``embed_xyz`` is given) or features.
 
     The reference concatenates [PE | dir | code | appearance] per ray-chunk and calls the MLP; here the
@@ -80,6 +80,12 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
         env = inputs[2] if len(segs) == 3 else None
         out = trunk_tc.TrunkTcFn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
         return out.reshape(Bn, nbins, 4)
+    # tensor-core (split-precision) path for the reference's nerf_skin on [PE(xyz) | pose code]
+    if (config.precision == "fp16" and not sigma_only and len(segs) == 2 and segs[0][0] == SEG_PE
+            and segs[1][0] == SEG_BCAST and segs[1][3] in (nbins, M) and k == 3 and embed_xyz.N_freqs == 10
+            and skin_tc.supported(model, segs[1][2])):
+        out = skin_tc.SkinMlpTcFn.apply(pts2, inputs[1], nbins, win, *model.param_list()).reshape(Bn, nbins, 32)
+        return out if _pitched else out[..., :model.out_channels]
     xyz_segs, dir_segs = _split_segments(segs, cx)
     if len(xyz_segs) > 2 or len(dir_segs) > 2:
         raise NotImplementedError("more than two column segments per input group")
@@ -119,11 +125,13 @@ def skinning(bones, pts, dskin=None, skin_aux=None):
     return skin
 
 
-def mlp_skinning(mlp, code, pts_embed, embed_xyz=None):
-    """geom_utils.py:219-229: delta skinning logits from nerf_skin."""
+def mlp_skinning(mlp, code, pts_embed, embed_xyz=None, _pitched=False):
+    """geom_utils.py:219-229: delta skinning logits from nerf_skin.  With ``_pitched`` (internal callers that
+    hand the result straight to the skinning kernels) the tensor-core path returns its zero-padded 32-column
+    rows instead of a sliced view."""
     if mlp is None:
         return None
-    return evaluate_mlp(mlp, pts_embed, embed_xyz=embed_xyz, code=code, chunk=8 * 1024)
+    return evaluate_mlp(mlp, pts_embed, embed_xyz=embed_xyz, code=code, chunk=8 * 1024, _pitched=_pitched)
 
 
 def gauss_mlp_skinning(xyz, embedding_xyz, bones, pose_code, nerf_skin, skin_aux=None):
@@ -132,7 +140,7 @@ def gauss_mlp_skinning(xyz, embedding_xyz, bones, pose_code, nerf_skin, skin_aux
     N_rays = xyz.shape[0]
     if pose_code.dim() == 2 and pose_code.shape[0] != N_rays:
         pose_code = pose_code.reshape(1, -1)
-    dskin = mlp_skinning(nerf_skin, pose_code, xyz, embed_xyz=embedding_xyz)
+    dskin = mlp_skinning(nerf_skin, pose_code, xyz, embed_xyz=embedding_xyz, _pitched=True)
     return skinning(bones, xyz, dskin, skin_aux=skin_aux)
 
 

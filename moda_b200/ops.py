@@ -363,30 +363,43 @@ class SkinWarpFn(torch.autograd.Function):
         rts_ = f32(rts).reshape(R, B, 8) if rts is not None else None
         aux = f32(skin_aux) if skin_aux is not None else torch.zeros(2, device=pts.device)
         dsk = f32(dskin) if dskin is not None else None
+        ldd = 0
+        if dsk is not None:
+            # delta logits may arrive zero-padded to a wider row pitch (the tensor-core nerf_skin path writes 32
+            # columns for 25 bones): the kernels take the pitch, nothing is compacted
+            if dsk.shape[-1] < B:
+                raise RuntimeError("dskin has %d channels for %d bones" % (dsk.shape[-1], B))
+            if dsk.shape[-1] > B:
+                ldd = dsk.shape[-1]
         sin = f32(skin_in) if skin_in is not None else None
         y = torch.empty_like(pts) if want_y else None
         skin = torch.empty(R, S, B, device=pts.device, dtype=torch.float32) if want_skin else None
         call("moda_skin_warp_fwd", ptr(pts), ptr(bones), ptr(rts_), ptr(aux), ptr(dsk), ptr(sin), ptr(y),
-             ptr(skin), R, S, B, per_ray, int(deform), int(invert), stream())
+             ptr(skin), R, S, B, ldd, per_ray, int(deform), int(invert), stream())
         ctx.save_for_backward(pts, bones, rts_, aux, dsk, sin)
         ctx.meta = (R, S, B, per_ray, int(deform), int(invert), rts.shape if rts is not None else None,
-                    skin_aux is not None)
+                    skin_aux is not None, ldd)
         return y, skin
 
     @staticmethod
     def backward(ctx, gy, gskin):
         pts, bones, rts_, aux, dsk, sin = ctx.saved_tensors
-        R, S, B, per_ray, deform, invert, rshape, has_aux = ctx.meta
+        R, S, B, per_ray, deform, invert, rshape, has_aux, ldd = ctx.meta
         gy = f32(gy) if gy is not None else None
         gskin = f32(gskin) if gskin is not None else None
         gpts = torch.empty_like(pts)
-        gdsk = torch.empty_like(dsk) if dsk is not None else None
+        if dsk is None:
+            gdsk = None
+        elif ldd:
+            gdsk = torch.zeros_like(dsk)  # pitched: pad columns must stay zero
+        else:
+            gdsk = torch.empty_like(dsk)
         gsin = torch.empty_like(sin) if sin is not None else None
         grts = torch.zeros_like(rts_) if rts_ is not None else None
         gbones = torch.zeros_like(bones)
         gaux = torch.zeros(2, device=pts.device, dtype=torch.float32)
         call("moda_skin_warp_bwd", ptr(pts), ptr(bones), ptr(rts_), ptr(aux), ptr(dsk), ptr(sin), ptr(gy),
-             ptr(gskin), ptr(gpts), ptr(gdsk), ptr(gsin), ptr(grts), ptr(gbones), ptr(gaux), R, S, B, per_ray,
+             ptr(gskin), ptr(gpts), ptr(gdsk), ptr(gsin), ptr(grts), ptr(gbones), ptr(gaux), R, S, B, ldd, per_ray,
              deform, invert, stream())
         return (gpts, gbones, grts.reshape(rshape) if grts is not None else None, gaux if has_aux else None,
                 gdsk, gsin, None, None, None, None)

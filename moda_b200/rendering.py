@@ -129,12 +129,12 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
         nerf_skin = models.get("nerf_skin")
         time_embedded = rays["time_embedded"]
         # backward warp (rendering.py:303-322): delta logits, then skinning + DQ blend fused in one kernel
-        dskin_bw = G.mlp_skinning(nerf_skin, time_embedded, xyz_coarse_sampled, embed_xyz=embedding_xyz)
+        dskin_bw = G.mlp_skinning(nerf_skin, time_embedded, xyz_coarse_sampled, embed_xyz=embedding_xyz, _pitched=True)
         xyz_coarse_sampled = G.warp_points(xyz_coarse_sampled, bones_rst, bone_rts_fw, skin_aux, dskin_bw,
                                            backward=True)
         if fine_iter:
             # cycle forward warp (rendering.py:330-341)
-            dskin_fw = G.mlp_skinning(nerf_skin, rest_pose_code, xyz_coarse_sampled, embed_xyz=embedding_xyz)
+            dskin_fw = G.mlp_skinning(nerf_skin, rest_pose_code, xyz_coarse_sampled, embed_xyz=embedding_xyz, _pitched=True)
             xyz_coarse_frame_cyc = G.warp_points(xyz_coarse_sampled, bones_rst, bone_rts_fw, skin_aux, dskin_fw,
                                                  backward=False)
             cyc_pair = (xyz_coarse_frame, xyz_coarse_frame_cyc)

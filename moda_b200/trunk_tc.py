@@ -38,8 +38,8 @@ def _wgrad(dY, N, X, K, M, dW, col0, k_valid, oscale):
 
 
 def _pack(src, cols, col0, out, out_col0, out_rows, width, transpose):
-    call("moda_pack16", ptr(src), src.stride(0), src.shape[0], cols, col0, ptr(out) + 2 * out_col0, out.stride(0),
-         out_rows, width, int(transpose), stream())
+    call("moda_pack16", ptr(src), src.stride(0), src.shape[0], cols, col0, ptr(out) + 2 * out_col0, None, None,
+         out.stride(0), out_rows, width, int(transpose), stream())
 
 
 class PackedWeights:
@@ -105,7 +105,7 @@ class TrunkTcFn(torch.autograd.Function):
         wa, nw = _win_array(win)
         F = len(win)
         A0 = h16(64)
-        call("moda_pe16_fwd", ptr(xyz), ptr(A0), 64, P, F, wa, stream())
+        call("moda_pe16_fwd", ptr(xyz), ptr(A0), None, 64, P, F, wa, stream())
         # per-ray bias of the direction layer: Wd[:, 256:] [dir | env] + bd   (tiny fp32 GEMM, M = rays)
         rb = torch.empty(R, 128, device=dev, dtype=torch.float32)
         one = lambda v: (ctypes.c_int * 1)(v)
@@ -158,7 +158,7 @@ class TrunkTcFn(torch.autograd.Function):
              ptr(g[22]), ptr(g[23]), ptr(g[20]), ptr(g[21]), P, stream())
         # direction layer: hoisted per-ray part (fp32, M = rays) ...
         grb = torch.empty(R, 128, device=dev, dtype=torch.float32)
-        call("moda_segsum16", ptr(d_dfe), 128, ptr(grb), R, S, 128, ptr(isc), stream())
+        call("moda_segsum16", ptr(d_dfe), 128, ptr(grb), R, S, 128, ptr(isc), 0, stream())
         gcode = torch.empty(R, cc, device=dev, dtype=torch.float32)
         call("moda_linear_dgrad", R, 128, cc, ptr(grb), 128, ptr(Wd), Wd.shape[1], 256, None, 0, 0, ptr(gcode), cc,
              stream())
@@ -195,7 +195,7 @@ class TrunkTcFn(torch.autograd.Function):
                 cur = nxt
         gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
-        call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
+        call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
         ctx.act = None
         gdir = gcode[:, :cd].contiguous()
         genv = gcode[:, cd:].contiguous() if has_env else None

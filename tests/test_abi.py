@@ -50,7 +50,7 @@ def test_argument_checks_fail_loudly_without_gpu(libpath):
     """Argument validation happens before any launch, so it is testable on a CPU-only box."""
     from moda_b200 import _lib
     L = _lib.lib()
-    rc = L.moda_skin_warp_fwd(None, None, None, None, None, None, None, None, 4, 8, 200, 0, 0, 0, None)
+    rc = L.moda_skin_warp_fwd(None, None, None, None, None, None, None, None, 4, 8, 200, 0, 0, 0, 0, None)
     assert rc < 0 and b"B=200" in L.moda_last_error()
 
 

@@ -341,7 +341,43 @@ def test_tensor_core_trunk_matches_simt_trunk():
     assert max_abs(b[0], a[0]) < 5e-3
     # norm-wise agreement at fp16 level (gxyz is amplified by 2^9 through the highest PE band)
     nrel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
-    for i, nm in ((1, "gxyz"), (2, "gdir"), (3, "genv")):
-        assert nrel(b[i], a[i]) < 2e-2, (nm, nrel(b[i], a[i]))
+    for i, nm, tol in ((1, "gxyz", 6e-2), (2, "gdir", 2e-2), (3, "genv", 2e-2)):
+        assert nrel(b[i], a[i]) < tol, (nm, nrel(b[i], a[i]))
     worst = max(nrel(b[4][k], a[4][k]) for k in a[4])
     assert worst < 2e-2, worst
+
+
+def test_split_precision_skin_mlp_matches_fp32_simt():
+    """nerf_skin on tensor cores with (hi, lo) fp16 operand pairs must be fp32-class: the delta logits feed a
+    softmax over O(100) Gaussian logits, so fp16/TF32 operand rounding (1e-3 relative) would not do."""
+    from moda_b200 import config, geom_utils as G
+    from moda_b200.nerf import Embedding, NeRF
+    nets = load_npz("nets_seed0.npz")
+    sd = {k[len("nerf_skin."):]: torch.from_numpy(v) for k, v in nets.items() if k.startswith("nerf_skin.")}
+    skin = NeRF(in_channels_xyz=63 + 128, D=5, W=64, in_channels_dir=0, out_channels=25, raw_feat=True, in_channels_code=128)
+    skin.load_state_dict(sd)
+    skin = skin.to(DEV)
+    emb = Embedding(3, 10, alpha=10)
+    gen = torch.Generator().manual_seed(5)
+    R, S = 200, 128
+    pts = (torch.rand(R, S, 3, generator=gen) * 0.6 - 0.3).to(DEV)
+    gout = torch.randn(R, S, 25, generator=gen).to(DEV) * 1e-3
+    for code in ((0.1 * torch.randn(R, 128, generator=gen)).to(DEV), torch.randn(1, 128, generator=gen).to(DEV)):
+        outs = {}
+        for mode in ("fp32", "fp16"):
+            config.set_precision(mode)
+            skin.zero_grad()
+            p, c = pts.clone().requires_grad_(True), code.clone().requires_grad_(True)
+            out = G.evaluate_mlp(skin, p, embed_xyz=emb, code=c)
+            assert out.shape == (R, S, 25)
+            (out * gout).sum().backward()
+            outs[mode] = (out.detach(), p.grad, c.grad, {k: v.grad.clone() for k, v in skin.named_parameters() if v.grad is not None})
+        a, b = outs["fp32"], outs["fp16"]
+        nrel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
+        assert max_abs(b[0], a[0]) < 2e-5, max_abs(b[0], a[0])
+        # the PE adjoint amplifies by 2^9 with cancellation: both fp32-class paths carry ~1e-3 noise there
+        assert nrel(b[1], a[1]) < 5e-3, ("gpts", nrel(b[1], a[1]))
+        assert nrel(b[2], a[2]) < 2e-4, ("gcode", nrel(b[2], a[2]))
+        assert set(a[3]) == set(b[3])
+        worst = max((nrel(b[3][k], a[3][k]), k) for k in a[3])
+        assert worst[0] < 2e-4, worst

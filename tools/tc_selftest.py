@@ -21,7 +21,7 @@ def tc_linear(A1, A2, B, bias=None, rowbias=None, rep=1, relu=0, mask=None, rv=N
 
 
 def check(name, got, ref, tol):
-    err = float((got.float() - ref).abs().max())
+    err = float((got.double() - ref.double()).abs().max())
     scale = float(ref.abs().max())
     ok = err <= tol * max(scale, 1.0)
     print("%-46s max|err| %.3e (scale %.2e) %s" % (name, err, scale, "ok" if ok else "FAIL"))
@@ -69,9 +69,45 @@ for (M, N, K) in [(1000, 256, 256), (64, 256, 64), (5000, 128, 256), (100000, 25
     X = (torch.randn(M, K, device=dev) * 0.5).half()
     dW = torch.zeros(N, K, device=dev)
     osc = torch.tensor([0.5], device=dev)
-    call("moda_tc_wgrad", ptr(dY), N, N, ptr(X), K, K, M, ptr(dW), K, ptr(osc), stream())
+    call("moda_tc_wgrad", ptr(dY), N, N, ptr(X), K, K, M, ptr(dW), K, K, ptr(osc), stream())
     ref = 0.5 * (dY.float().t() @ X.float())
     ok &= check("wgrad M%d N%d K%d" % (M, N, K), dW, ref, 1e-4)
+
+# split precision (hi/lo fp16 pairs): fp32-class accuracy
+def split(x):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi.contiguous(), lo.contiguous()
+
+for (M, N, K1, K2) in [(1000, 64, 64, 0), (777, 64, 64, 64), (300, 32, 64, 0)]:
+    X1 = torch.randn(M, K1, device=dev) * 0.5
+    X2 = torch.randn(M, K2, device=dev) * 0.5 if K2 else None
+    W = torch.randn(N, K1 + K2, device=dev) / (K1 + K2) ** 0.5
+    x1h, x1l = split(X1)
+    x2h, x2l = split(X2) if K2 else (None, None)
+    wh, wl = split(W)
+    B3 = torch.cat([wh, wh, wl], 1).contiguous()
+    bias = torch.randn(N, device=dev)
+    X = torch.cat([X1, X2], 1) if K2 else X1
+    ref = torch.relu(X.double() @ W.double().t() + bias.double())
+    yh = torch.zeros(M, N, device=dev, dtype=torch.float16)
+    yl = torch.zeros(M, N, device=dev, dtype=torch.float16)
+    y32 = torch.zeros(M, N, device=dev)
+    call("moda_tc_linear_split", ptr(x1h), ptr(x1l), K1, K1, ptr(x2h) if K2 else None, ptr(x2l) if K2 else None, K2, K2,
+         ptr(B3), B3.stride(0), M, N, ptr(bias), None, 1, 1, None, 0, ptr(yh), ptr(yl), N, 0, ptr(y32), N, None, stream())
+    ok &= check("split linear M%d N%d K%d+%d fp32 out" % (M, N, K1, K2), y32.double(), ref, 3e-6)
+    ok &= check("split linear M%d N%d K%d+%d hi+lo out" % (M, N, K1, K2), yh.double() + yl.double(), ref, 3e-6)
+for (M, N, K, nv, kv) in [(1000, 64, 64, 64, 64), (5000, 64, 64, 25, 32), (3000, 64, 128, 64, 128)]:
+    dY = torch.randn(M, N, device=dev) * 0.1
+    X = torch.randn(M, K, device=dev) * 0.5
+    yh, yl = split(dY)
+    xh, xl = split(X)
+    dW = torch.zeros(N, K, device=dev)
+    call("moda_tc_wgrad_split", ptr(yh), ptr(yl), N, N, ptr(xh), ptr(xl), K, K, M, ptr(dW), K, nv, kv, None, stream())
+    ref = (dY.double().t() @ X.double())
+    ref[nv:] = 0
+    ref[:, kv:] = 0
+    ok &= check("split wgrad M%d N%d K%d valid %dx%d" % (M, N, K, nv, kv), dW.double(), ref, 3e-6)
 
 print("ALL OK" if ok else "SOME FAILED")
 
@@ -93,7 +129,7 @@ ms = t(lambda: tc_linear(A1, None, B, bias=bias, relu=1, y16=y16))
 print("tc_linear 1M x 256 x 256: %.3f ms  %.1f TFLOP/s  %.1f GB/s" % (ms, 2 * M * 256 * 256 / ms / 1e9, 2 * M * 512 / ms / 1e6))
 ms = t(lambda: tc_linear(A1, None, B, mask=A1, y16=y16))
 print("tc_linear (dgrad+mask)  : %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
-ms = t(lambda: call("moda_tc_wgrad", ptr(y16), 256, 256, ptr(A1), 256, 256, M, ptr(dW), 256, None, stream()))
+ms = t(lambda: call("moda_tc_wgrad", ptr(y16), 256, 256, ptr(A1), 256, 256, M, ptr(dW), 256, 256, None, stream()))
 print("tc_wgrad  1M x 256 x 256: %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
 ms = t(lambda: torch.matmul(A1, B.t()))
 print("torch fp16 matmul       : %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
