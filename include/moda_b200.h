@@ -148,7 +148,8 @@ int moda_tc_linear(const void* A1, int lda1, int K1, const void* A2, int lda2, i
 /* dW (N, ldw) fp32 += (*oscale) dY[M,N]^T X[M,K], first k_valid columns only; (N,K) in {256,128} x {64,128,256}.
  * Both operands are consumed MN-major straight from their row-major fp16 storage. */
 int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
-                  int k_valid, const float* oscale, cudaStream_t stream);
+                  int n_valid, int k_valid, const float* oscale, float* dbias /* NULL, or (N) += colsum(dY) */,
+                  cudaStream_t stream);
 /* fp16 operand staging for the trunk: positional encoding of (P,3) points into (P,64) [63 channels + zero pad]
  * (Embedding.forward, nerf.py:35-75) and its adjoint (gxyz (=|+=) (*inv_scale) J^T g16) */
 int moda_pe16_fwd(const float* xyz, void* out16, void* out16lo /* NULL, or low half of the split pair */, int ldo,
@@ -172,7 +173,7 @@ int moda_tc_linear_split(const void* A1hi, const void* A1lo, int lda1, int K1, c
 /* dW += (*oscale) (dYhi + dYlo)^T (Xhi + Xlo) (lo*lo dropped); rows >= n_valid / cols >= k_valid not written */
 int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, int N, const void* Xhi, const void* Xlo, int ldx,
                         int K, int M, float* dW, int ldw, int n_valid, int k_valid, const float* oscale,
-                        cudaStream_t stream);
+                        float* dbias, cudaStream_t stream);
 /* sigma (256->1) and rgb (128->3, sigmoid) heads (nerf.py:178, 188-195) on fp16 activations; raw (P,4) fp32 */
 int moda_head_fwd(const void* H8, const void* Dfe, const float* ws, const float* bs, const float* Wr,
                   const float* br, float* raw, long long P, cudaStream_t stream);

@@ -48,10 +48,10 @@ SIGNATURES = {
     "moda_sample_pdf": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "moda_tc_linear": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p,
                        c_p, c_i, c_i, c_p, c_i, c_p, c_p],
-    "moda_tc_wgrad": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
+    "moda_tc_wgrad": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "moda_tc_linear_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i,
                              c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p],
-    "moda_tc_wgrad_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p],
+    "moda_tc_wgrad_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "moda_pe16_fwd": [c_p, c_p, c_p, c_i, c_ll, c_i, c_fp, c_p],
     "moda_pe16_bwd": [c_p, c_p, c_p, c_i, c_p, c_ll, c_i, c_fp, c_p, c_i, c_p],
     "moda_pack16": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],

@@ -449,7 +449,7 @@ struct WgMaps { CUtensorMap y[WG_MAX_PAIRS]; CUtensorMap x[WG_MAX_PAIRS]; };
 template <int NOUT, int KIN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW, int ldw, int n_valid, int k_valid,
-                const float* oscale_p) {
+                const float* oscale_p, float* dbias) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int YB = NOUT / 64, XB = KIN / 64;       // boxes per operand per stage
@@ -469,7 +469,8 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW
   const int num_chunks = (M + WG_ROWS - 1) / WG_ROWS;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // a stage is released by the MMA commit and, when bias gradients are wanted, by the 4 column-sum warps
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], dbias ? 5 : 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -537,6 +538,41 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW
   } else if (has_work) {
     const int q = warp & 3;
     const float oscale = oscale_p ? *oscale_p : 1.0f;
+    if (dbias) {
+      // bias gradient = column sums of dY, taken from the operand boxes while the tensor core consumes them
+      // (pairs 0 and 1 carry dY's hi and lo halves; pair 2 repeats hi).  Box = 64 rows x 128 B, 128-byte swizzle:
+      // element (r, c) lives at r*128 + (((c >> 3) ^ (r & 7)) << 4) + (c & 7) * 2.
+      constexpr int PAIRS = NOUT / 2;            // column pairs
+      constexpr int GROUPS = 128 / PAIRS;        // row groups sharing the 128 threads
+      constexpr int RPG = WG_ROWS / GROUPS;      // rows per group
+      const int t = threadIdx.x - 64;
+      const int cp = t % PAIRS, grp = t / PAIRS;
+      const int box = cp >> 5, j = cp & 31;      // 32 column pairs per 64-column box
+      float s0 = 0.f, s1 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+        for (int p = 0; p < npair; ++p) {
+          mbar_wait(&full[stage], phase);
+          if (p < 2) {
+            const uint8_t* yb = smem + stage * STAGE_BYTES + box * WG_BOX_BYTES;
+#pragma unroll 8
+            for (int rr = 0; rr < RPG; ++rr) {
+              const int r = grp * RPG + rr;
+              const __half2 h = *reinterpret_cast<const __half2*>(yb + r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + (j & 3) * 4);
+              const float2 f = __half22float2(h);
+              s0 += f.x; s1 += f.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      const int col = cp * 2;
+      if (col < n_valid) atomicAdd(dbias + col, s0 * oscale);
+      if (col + 1 < n_valid) atomicAdd(dbias + col + 1, s1 * oscale);
+    }
     mbar_wait(done, 0);
     tc_fence_after();
     for (int mb = 0; mb < MB; ++mb) {
@@ -736,7 +772,7 @@ extern "C" int moda_tc_linear_split(const void* A1hi, const void* A1lo, int lda1
 
 template <int NOUT, int KIN>
 static int launch_wgrad(const WgMaps& maps, int npair, int M, float* dW, int ldw, int n_valid, int k_valid,
-                        const float* oscale, cudaStream_t stream) {
+                        const float* oscale, float* dbias, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + WG_BOX_BYTES + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -745,13 +781,14 @@ static int launch_wgrad(const WgMaps& maps, int npair, int M, float* dW, int ldw
   }
   const int chunks = (M + WG_ROWS - 1) / WG_ROWS;
   const int grid = chunks < sm_count() ? chunks : sm_count();
-  tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(maps, npair, M, dW, ldw, n_valid, k_valid, oscale);
+  tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(maps, npair, M, dW, ldw, n_valid, k_valid, oscale,
+                                                                    dbias);
   return check_launch("tc_wgrad");
 }
 
 static int dispatch_wgrad(const WgMaps& maps, int npair, int N, int K, int M, float* dW, int ldw, int n_valid,
-                          int k_valid, const float* oscale, cudaStream_t stream) {
-#define MODA_WG(NN, KK) if (N == NN && K == KK) return launch_wgrad<NN, KK>(maps, npair, M, dW, ldw, n_valid, k_valid, oscale, stream)
+                          int k_valid, const float* oscale, float* dbias, cudaStream_t stream) {
+#define MODA_WG(NN, KK) if (N == NN && K == KK) return launch_wgrad<NN, KK>(maps, npair, M, dW, ldw, n_valid, k_valid, oscale, dbias, stream)
   MODA_WG(256, 256); MODA_WG(256, 64); MODA_WG(256, 128); MODA_WG(128, 256); MODA_WG(128, 128); MODA_WG(128, 64);
   MODA_WG(64, 64); MODA_WG(64, 128);
 #undef MODA_WG
@@ -760,9 +797,10 @@ static int dispatch_wgrad(const WgMaps& maps, int npair, int N, int K, int M, fl
 }
 
 // dW (N, ldw) fp32 += oscale * dY (M,N)^T X (M,K); dY, X fp16 row-major.  Accumulates (zero dW first).
-// Only the first k_valid columns are written (X may carry zero padding columns).
+// Only the first n_valid rows / k_valid columns are written (operands may carry zero padding).  dbias (N) or NULL:
+// += oscale * column sums of dY (the bias gradient), taken from the operand tiles already in shared memory.
 extern "C" int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
-                             int k_valid, const float* oscale, cudaStream_t stream) {
+                             int n_valid, int k_valid, const float* oscale, float* dbias, cudaStream_t stream) {
   if (M == 0) return 0;
   MODA_REQUIRE(dY && X && dW, "tc_wgrad: null pointer");
   WgMaps maps;
@@ -770,14 +808,14 @@ extern "C" int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int 
   if (int e = make_map(&maps.x[0], X, M, K, ldx, WG_ROWS)) return e;
   maps.y[1] = maps.y[2] = maps.y[0];
   maps.x[1] = maps.x[2] = maps.x[0];
-  return dispatch_wgrad(maps, 1, N, K, M, dW, ldw, N, k_valid, oscale, stream);
+  return dispatch_wgrad(maps, 1, N, K, M, dW, ldw, n_valid, k_valid, oscale, dbias, stream);
 }
 
 // Split-precision weight gradient: dW += oscale * (dYhi + dYlo)^T (Xhi + Xlo) without the lo*lo term.
 // Rows >= n_valid and columns >= k_valid of the padded 64-wide operands are not written.
 extern "C" int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, int N, const void* Xhi,
                                    const void* Xlo, int ldx, int K, int M, float* dW, int ldw, int n_valid,
-                                   int k_valid, const float* oscale, cudaStream_t stream) {
+                                   int k_valid, const float* oscale, float* dbias, cudaStream_t stream) {
   if (M == 0) return 0;
   MODA_REQUIRE(dYhi && dYlo && Xhi && Xlo && dW, "tc_wgrad_split: null pointer");
   WgMaps maps;
@@ -787,5 +825,5 @@ extern "C" int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, 
   if (int e = make_map(&maps.x[0], Xhi, M, K, ldx, WG_ROWS)) return e;
   maps.x[1] = maps.x[0];
   if (int e = make_map(&maps.x[2], Xlo, M, K, ldx, WG_ROWS)) return e;
-  return dispatch_wgrad(maps, 3, N, K, M, dW, ldw, n_valid, k_valid, oscale, stream);
+  return dispatch_wgrad(maps, 3, N, K, M, dW, ldw, n_valid, k_valid, oscale, dbias, stream);
 }

@@ -32,9 +32,10 @@ def _tcl(A1, K1, A2, K2, B, M, N, bias=None, rowbias=None, rep=1, relu=0, mask=N
          ptr(oscale), stream())
 
 
-def _wgrad(dY, N, X, K, M, dW, col0, k_valid, oscale):
+def _wgrad(dY, N, X, K, M, dW, col0, k_valid, oscale, dbias=None):
+    """dW[:, col0:col0+k_valid] += dY^T X; with ``dbias`` also the bias gradient (column sums of dY)."""
     call("moda_tc_wgrad", ptr(dY), dY.stride(0), N, ptr(X), X.stride(0), K, M, ptr(dW) + 4 * col0, dW.stride(0),
-         k_valid, ptr(oscale), stream())
+         N, k_valid, ptr(oscale), ptr(dbias), stream())
 
 
 def _pack(src, cols, col0, out, out_col0, out_rows, width, transpose):
@@ -170,8 +171,7 @@ class TrunkTcFn(torch.autograd.Function):
         d_fin = h16(256)
         _tcl(d_dfe, 128, None, 0, pk.WdT, P, 256, y16=d_fin)
         # final layer (no activation) + sigma head's rank-1 data gradient, masked by relu(H8)
-        _wgrad(d_fin, 256, H[7], 256, P, g[16], 0, 256, isc)
-        call("moda_colsum16", ptr(d_fin), 256, ptr(g[17]), P, 256, ptr(isc), stream())
+        _wgrad(d_fin, 256, H[7], 256, P, g[16], 0, 256, isc, dbias=g[17])
         bufs = [h16(256), d_fin]  # d_fin's storage is recycled once consumed
         dY = bufs[0]
         _tcl(d_fin, 256, None, 0, pk.WfT, P, 256, mask=H[7], rv=gsig, cv=Ws.reshape(-1), rscale=sc, y16=dY)
@@ -179,17 +179,16 @@ class TrunkTcFn(torch.autograd.Function):
         d_pe = h16(64)
         for i in range(7, -1, -1):
             dY = bufs[cur]
-            call("moda_colsum16", ptr(dY), 256, ptr(g[2 * i + 1]), P, 256, ptr(isc), stream())
             if i == 0:
-                _wgrad(dY, 256, A0, 64, P, g[0], 0, 63, isc)
+                _wgrad(dY, 256, A0, 64, P, g[0], 0, 63, isc, dbias=g[1])
                 _tcl(dY, 256, None, 0, pk.T_pe1, P, 64, y16=d_pe, acc16=1)
             else:
                 if i == 4:
                     _wgrad(dY, 256, A0, 64, P, g[8], 0, 63, isc)
-                    _wgrad(dY, 256, H[3], 256, P, g[8], 63, 256, isc)
+                    _wgrad(dY, 256, H[3], 256, P, g[8], 63, 256, isc, dbias=g[9])
                     _tcl(dY, 256, None, 0, pk.T_pe5, P, 64, y16=d_pe)
                 else:
-                    _wgrad(dY, 256, H[i - 1], 256, P, g[2 * i], 0, 256, isc)
+                    _wgrad(dY, 256, H[i - 1], 256, P, g[2 * i], 0, 256, isc, dbias=g[2 * i + 1])
                 nxt = 1 - cur
                 _tcl(dY, 256, None, 0, pk.T[i], P, 256, mask=H[i - 1], y16=bufs[nxt])
                 cur = nxt

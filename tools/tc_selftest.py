@@ -68,10 +68,25 @@ for (M, N, K) in [(1000, 256, 256), (64, 256, 64), (5000, 128, 256), (100000, 25
     dY = (torch.randn(M, N, device=dev) * 0.1).half()
     X = (torch.randn(M, K, device=dev) * 0.5).half()
     dW = torch.zeros(N, K, device=dev)
+    db = torch.zeros(N, device=dev)
     osc = torch.tensor([0.5], device=dev)
-    call("moda_tc_wgrad", ptr(dY), N, N, ptr(X), K, K, M, ptr(dW), K, K, ptr(osc), stream())
+    call("moda_tc_wgrad", ptr(dY), N, N, ptr(X), K, K, M, ptr(dW), K, N, K, ptr(osc), ptr(db), stream())
     ref = 0.5 * (dY.float().t() @ X.float())
     ok &= check("wgrad M%d N%d K%d" % (M, N, K), dW, ref, 1e-4)
+    ok &= check("wgrad bias M%d N%d K%d" % (M, N, K), db, 0.5 * dY.float().sum(0), 1e-4)
+for (M, N, K, nv, kv) in [(1000, 64, 64, 64, 64), (5000, 64, 64, 25, 32), (3000, 64, 128, 64, 128)]:
+    dY = (torch.randn(M, N, device=dev) * 0.1).half()
+    X = (torch.randn(M, K, device=dev) * 0.5).half()
+    dW = torch.zeros(N, K, device=dev)
+    db = torch.zeros(N, device=dev)
+    call("moda_tc_wgrad", ptr(dY), N, N, ptr(X), K, K, M, ptr(dW), K, nv, kv, None, ptr(db), stream())
+    ref = dY.float().t() @ X.float()
+    ref[nv:] = 0
+    ref[:, kv:] = 0
+    rb = dY.float().sum(0)
+    rb[nv:] = 0
+    ok &= check("wgrad64 M%d N%d K%d valid %dx%d" % (M, N, K, nv, kv), dW, ref, 1e-4)
+    ok &= check("wgrad64 bias", db, rb, 1e-4)
 
 # split precision (hi/lo fp16 pairs): fp32-class accuracy
 def split(x):
@@ -103,11 +118,15 @@ for (M, N, K, nv, kv) in [(1000, 64, 64, 64, 64), (5000, 64, 64, 25, 32), (3000,
     yh, yl = split(dY)
     xh, xl = split(X)
     dW = torch.zeros(N, K, device=dev)
-    call("moda_tc_wgrad_split", ptr(yh), ptr(yl), N, N, ptr(xh), ptr(xl), K, K, M, ptr(dW), K, nv, kv, None, stream())
+    db = torch.zeros(N, device=dev)
+    call("moda_tc_wgrad_split", ptr(yh), ptr(yl), N, N, ptr(xh), ptr(xl), K, K, M, ptr(dW), K, nv, kv, None, ptr(db), stream())
     ref = (dY.double().t() @ X.double())
     ref[nv:] = 0
     ref[:, kv:] = 0
+    rb = dY.double().sum(0)
+    rb[nv:] = 0
     ok &= check("split wgrad M%d N%d K%d valid %dx%d" % (M, N, K, nv, kv), dW.double(), ref, 3e-6)
+    ok &= check("split wgrad bias", db.double(), rb, 3e-6)
 
 print("ALL OK" if ok else "SOME FAILED")
 
@@ -129,7 +148,7 @@ ms = t(lambda: tc_linear(A1, None, B, bias=bias, relu=1, y16=y16))
 print("tc_linear 1M x 256 x 256: %.3f ms  %.1f TFLOP/s  %.1f GB/s" % (ms, 2 * M * 256 * 256 / ms / 1e9, 2 * M * 512 / ms / 1e6))
 ms = t(lambda: tc_linear(A1, None, B, mask=A1, y16=y16))
 print("tc_linear (dgrad+mask)  : %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
-ms = t(lambda: call("moda_tc_wgrad", ptr(y16), 256, 256, ptr(A1), 256, 256, M, ptr(dW), 256, 256, None, stream()))
+ms = t(lambda: call("moda_tc_wgrad", ptr(y16), 256, 256, ptr(A1), 256, 256, M, ptr(dW), 256, 256, 256, None, ptr(bias), stream()))
 print("tc_wgrad  1M x 256 x 256: %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
 ms = t(lambda: torch.matmul(A1, B.t()))
 print("torch fp16 matmul       : %.3f ms  %.1f TFLOP/s" % (ms, 2 * M * 256 * 256 / ms / 1e9))
