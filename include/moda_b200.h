@@ -189,6 +189,30 @@ int moda_segsum16(const void* in16, int ld, float* out, int R, int S, int N, con
 int moda_loss_scale(const float* g, long long n, float target, unsigned int* work, float* scale2,
                     cudaStream_t stream);
 
+/* ---- fused layer chains (csrc/chain.cu): one persistent tcgen05 kernel per MLP pass; activations stay in shared
+ * memory / TMEM across all layers.  Replaces, per 128-sample tile, the whole of NeRF.forward (nnutils/nerf.py:147-198)
+ * on the input evaluate_mlp assembles (nnutils/geom_utils.py:19-57), resp. its adjoint.
+ * Packed-weight chunk orders are documented at the definitions.  Saved outputs may be NULL (inference). */
+int moda_chain_trunk_fwd(const float* xyz, long long P, int rep /* samples per ray */, int F, const float* win,
+                         const void* wpack /* fp16 (256, 38*64) */, const float* const* biases /* b1..b8, bfinal */,
+                         const float* rowbias /* (P/rep,128) per-ray part of the dir layer */, const float* ws,
+                         const float* bs, const float* Wr, const float* br, void* A0 /* (P,64) fp16 PE */,
+                         void* H /* (8,P,256) */, void* fin /* (P,256) */, void* dfe /* (P,128) */,
+                         unsigned int* maskbits /* (8,tiles,8,128) ReLU sign bits */, float* raw /* (P,4) */,
+                         cudaStream_t stream);
+int moda_chain_trunk_bwd(const void* d_dfe /* (P,128) fp16 */, const float* gsig /* (P) */, const float* ws,
+                         const float* rscale, const void* wpackT /* fp16 (256, 42*64) */,
+                         const unsigned int* maskbits, long long P, void* d_fin /* (P,256) */,
+                         void* dY /* (8,P,256) */, void* d_pe /* (P,64) */, cudaStream_t stream);
+int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const float* win,
+                        const void* wpack /* fp16 (64, 18*64): [Whi | Wlo] per layer */,
+                        const float* const* biases /* rb1, b2, b3, b4, rb5, bfinal, bdir64, brgb64 */, void* A0,
+                        void* H /* (5,P,64) */, void* fin, void* dfe, unsigned int* maskbits /* (6,tiles,2,128) */,
+                        float* y32 /* (P,32) delta skinning logits */, cudaStream_t stream);
+int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
+                        const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
+                        void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

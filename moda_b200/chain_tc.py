@@ -1,0 +1,302 @@
+"""Fused-chain execution of ``nerf_coarse`` and ``nerf_skin`` (csrc/chain.cu): one persistent tcgen05 kernel per
+pass keeps the activations of all layers on chip; only what the other pass needs goes to HBM (fp16 activations
+for the weight gradients, ReLU sign bits for the adjoint, fp16 pre-activation gradients for the weight gradients).
+
+Same mathematics, same precision policy and the same autograd interface as the layer-by-layer modules
+``trunk_tc`` / ``skin_tc`` (which stay as the reference implementation the chain kernels are tested against):
+  nerf_coarse  nnutils/nerf.py:147-198 on [PE(xyz) | dir | env]    fp16 operands, fp32 accumulation
+  nerf_skin    same class, 5x64, raw_feat (moda.py:325-329)        forward in split (hi, lo) fp16 precision,
+                                                                   adjoint on plain fp16 operands
+"""
+import ctypes
+
+import torch
+
+from ._lib import call, ptr, stream, f32
+from .ops import _win_array
+
+HALF = torch.float16
+TILE = 128
+
+
+def _pack(src, cols, col0, out, out_col0, out_rows, width, transpose, lo_col0=None):
+    """fp32 block -> fp16 block of ``out`` at column ``out_col0`` (and its low half at ``lo_col0``), zero padded."""
+    base = ptr(out)
+    call("moda_pack16", ptr(src), src.stride(0), src.shape[0], cols, col0, base + 2 * out_col0, None,
+         (base + 2 * lo_col0) if lo_col0 is not None else None, out.stride(0), out_rows, width, int(transpose), stream())
+
+
+def _wgrad(dY, N, X, K, M, dW, col0, n_valid, k_valid, oscale, dbias=None):
+    call("moda_tc_wgrad", ptr(dY), dY.stride(0), N, ptr(X), X.stride(0), K, M, ptr(dW) + 4 * col0, dW.stride(0),
+         n_valid, k_valid, ptr(oscale), ptr(dbias), stream())
+
+
+def _one(v):
+    return (ctypes.c_int * 1)(v)
+
+
+def _small_linear(code, Wl, col0, bias, n):
+    """(R, n) fp32 = code Wl[:, col0:col0+nc]^T + bias: the per-ray-constant input columns as a per-ray bias."""
+    R, nc = code.shape
+    rb = torch.empty(R, n, device=code.device, dtype=torch.float32)
+    call("moda_linear_fwd", R, n, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(nc), _one(nc), _one(0), _one(1), None, 0,
+         ptr(Wl) + 4 * col0, Wl.shape[1], ptr(bias), 0, ptr(rb), n, stream())
+    return rb
+
+
+def _loss_scale(g):
+    scale2 = torch.empty(2, device=g.device, dtype=torch.float32)
+    work = torch.empty(1, device=g.device, dtype=torch.int32)
+    call("moda_loss_scale", ptr(g), g.numel(), 1024.0, work.data_ptr(), ptr(scale2), stream())
+    return scale2[0:1], scale2[1:2]
+
+
+# ------------------------------------------------------------------------------------------------ nerf_coarse
+def pack_trunk_fwd(params):
+    """(256, 38*64) fp16, chunk order documented at moda_chain_trunk_fwd (csrc/chain.cu)."""
+    W = [params[2 * i] for i in range(8)]
+    Wf, Wd = params[16], params[18]
+    out = torch.zeros(256, 38 * 64, device=W[0].device, dtype=HALF)
+    col = 0
+    for i in range(8):
+        if i == 0:
+            _pack(W[0], 63, 0, out, col, 256, 64, False); col += 64
+        elif i == 4:
+            _pack(W[4], 63, 0, out, col, 256, 64, False); col += 64
+            _pack(W[4], 256, 63, out, col, 256, 256, False); col += 256
+        else:
+            _pack(W[i], 256, 0, out, col, 256, 256, False); col += 256
+    _pack(Wf, 256, 0, out, col, 256, 256, False); col += 256
+    _pack(Wd, 256, 0, out, col, 128, 256, False); col += 256
+    assert col == 38 * 64
+    return out
+
+
+def pack_trunk_bwd(params):
+    """(256, 42*64) fp16 transposed weights, chunk order documented at moda_chain_trunk_bwd."""
+    W = [params[2 * i] for i in range(8)]
+    Wf, Wd = params[16], params[18]
+    out = torch.zeros(256, 42 * 64, device=W[0].device, dtype=HALF)
+    col = 0
+    _pack(Wd, 256, 0, out, col, 256, 128, True); col += 128
+    _pack(Wf, 256, 0, out, col, 256, 256, True); col += 256
+    for i in (7, 6, 5):
+        _pack(W[i], 256, 0, out, col, 256, 256, True); col += 256
+    _pack(W[4], 63, 0, out, col, 64, 256, True); col += 256
+    _pack(W[4], 256, 63, out, col, 256, 256, True); col += 256
+    for i in (3, 2, 1):
+        _pack(W[i], 256, 0, out, col, 256, 256, True); col += 256
+    _pack(W[0], 63, 0, out, col, 64, 256, True); col += 256
+    assert col == 42 * 64
+    return out
+
+
+class TrunkChainFn(torch.autograd.Function):
+    """apply(xyz (P,3), dir_embedded (R,cd), env_code (R,ce) | None, S, win, *params) -> raw (P,4) [rgb | sigma]."""
+
+    @staticmethod
+    def forward(ctx, xyz, dir_emb, env, S, win, *params):
+        xyz_shape = xyz.shape
+        xyz = f32(xyz).reshape(-1, 3)
+        P, dev = xyz.shape[0], xyz.device
+        params = [f32(p) for p in params]
+        need_bw = any(ctx.needs_input_grad)
+        Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
+        code = f32(dir_emb) if env is None else torch.cat([f32(dir_emb), f32(env)], -1)
+        R, cc = code.shape
+        assert R * S == P and Wd.shape[1] == 256 + cc
+        T = (P + TILE - 1) // TILE
+        wa, _ = _win_array(win)
+        rb = _small_linear(code, Wd, 256, bd, 128)
+        wpack = pack_trunk_fwd(params)
+        biases = (ctypes.c_void_p * 9)(*([ptr(params[2 * i + 1]) for i in range(8)] + [ptr(bf)]))
+        raw = torch.empty(P, 4, device=dev, dtype=torch.float32)
+        if need_bw:
+            A0 = torch.empty(P, 64, device=dev, dtype=HALF)
+            H = torch.empty(8, P, 256, device=dev, dtype=HALF)
+            fin = torch.empty(P, 256, device=dev, dtype=HALF)
+            dfe = torch.empty(P, 128, device=dev, dtype=HALF)
+            bits = torch.empty(8, T, 8, TILE, device=dev, dtype=torch.int32)
+        else:
+            A0 = H = fin = dfe = bits = None
+        call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(Ws), ptr(bs), ptr(Wr),
+             ptr(br), ptr(A0), ptr(H), ptr(fin), ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(raw),
+             stream())
+        if need_bw:
+            ctx.save_for_backward(xyz, code, raw, *params)
+            ctx.act = (A0, H, fin, dfe, bits)
+            ctx.meta = (S, win, dir_emb.shape[-1], env is not None, xyz_shape)
+        return raw
+
+    @staticmethod
+    def backward(ctx, graw):
+        xyz, code, raw = ctx.saved_tensors[:3]
+        params = list(ctx.saved_tensors[3:])
+        A0, H, fin, dfe, bits = ctx.act
+        S, win, cd, has_env, xyz_shape = ctx.meta
+        P, dev = xyz.shape[0], xyz.device
+        R, cc = code.shape
+        Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
+        g = [torch.zeros_like(p) for p in params]
+        graw = f32(graw).reshape(P, 4)
+        sc, isc = _loss_scale(graw)
+        # heads: d_dfe (scaled, masked by dfe > 0), gsig, and the head parameter gradients
+        d_dfe = torch.empty(P, 128, device=dev, dtype=HALF)
+        gsig = torch.empty(P, device=dev, dtype=torch.float32)
+        call("moda_head_bwd", ptr(H[7]), ptr(dfe), ptr(raw), ptr(graw), ptr(Wr), ptr(sc), ptr(d_dfe), ptr(gsig),
+             ptr(g[22]), ptr(g[23]), ptr(g[20]), ptr(g[21]), P, stream())
+        # direction layer, hoisted per-ray part (fp32, M = rays)
+        grb = torch.empty(R, 128, device=dev, dtype=torch.float32)
+        call("moda_segsum16", ptr(d_dfe), 128, ptr(grb), R, S, 128, ptr(isc), 0, stream())
+        gcode = torch.empty(R, cc, device=dev, dtype=torch.float32)
+        call("moda_linear_dgrad", R, 128, cc, ptr(grb), 128, ptr(Wd), Wd.shape[1], 256, None, 0, 0, ptr(gcode), cc,
+             stream())
+        call("moda_linear_wgrad", R, 128, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(cc), _one(cc), _one(0), _one(1), None,
+             0, ptr(grb), 128, ptr(g[18]), Wd.shape[1], 256, ptr(g[19]), stream())
+        # the whole data-gradient chain in one kernel
+        wpackT = pack_trunk_bwd(params)
+        d_fin = torch.empty(P, 256, device=dev, dtype=HALF)
+        dY = torch.empty(8, P, 256, device=dev, dtype=HALF)
+        d_pe = torch.empty(P, 64, device=dev, dtype=HALF)
+        call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(Ws.reshape(-1)), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
+             ptr(d_fin), ptr(dY), ptr(d_pe), stream())
+        # weight gradients (bias gradients ride along as column sums of the dY operand)
+        _wgrad(d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+        _wgrad(d_fin, 256, H[7], 256, P, g[16], 0, 256, 256, isc, dbias=g[17])
+        for i in range(7, 0, -1):
+            if i == 4:
+                _wgrad(dY[4], 256, A0, 64, P, g[8], 0, 256, 63, isc)
+                _wgrad(dY[4], 256, H[3], 256, P, g[8], 63, 256, 256, isc, dbias=g[9])
+            else:
+                _wgrad(dY[i], 256, H[i - 1], 256, P, g[2 * i], 0, 256, 256, isc, dbias=g[2 * i + 1])
+        _wgrad(dY[0], 256, A0, 64, P, g[0], 0, 256, 63, isc, dbias=g[1])
+        gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        wa, _ = _win_array(win)
+        call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
+        ctx.act = None
+        gdir = gcode[:, :cd].contiguous()
+        genv = gcode[:, cd:].contiguous() if has_env else None
+        return (gxyz.reshape(xyz_shape), gdir, genv, None, None) + tuple(g)
+
+
+# -------------------------------------------------------------------------------------------------- nerf_skin
+WD = 64
+
+
+def pack_skin_fwd(params, nc):
+    """(64, 18*64) fp16: per layer [Whi | Wlo], order documented at moda_chain_skin_fwd."""
+    W = [params[2 * i] for i in range(5)]
+    Wf, Wd, Wr = params[10], params[12], params[16]
+    out = torch.zeros(64, 18 * 64, device=W[0].device, dtype=HALF)
+    blocks = [(W[0], 63, 0), (W[1], 64, 0), (W[2], 64, 0), (W[3], 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc),
+              (Wf, 64, 0), (Wd, 64, 0), (Wr, 32, 0)]
+    for i, (w, cols, col0) in enumerate(blocks):
+        _pack(w, cols, col0, out, 128 * i, 64, 64, False, lo_col0=128 * i + 64)
+    return out
+
+
+def pack_skin_bwd(params, nc):
+    """(64, 9*64) fp16 transposed (hi) weights, order documented at moda_chain_skin_bwd."""
+    W = [params[2 * i] for i in range(5)]
+    Wf, Wd, Wr = params[10], params[12], params[16]
+    out = torch.zeros(64, 9 * 64, device=W[0].device, dtype=HALF)
+    blocks = [(Wr, 32, 0), (Wd, 64, 0), (Wf, 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc), (W[3], 64, 0), (W[2], 64, 0),
+              (W[1], 64, 0), (W[0], 63, 0)]
+    for i, (w, cols, col0) in enumerate(blocks):
+        _pack(w, cols, col0, out, 64 * i, 64, 64, True)
+    return out
+
+
+class SkinChainFn(torch.autograd.Function):
+    """apply(pts (..,3), code (Rc,nc) with Rc in {rays, 1}, S, win, *params) -> (P, 32) fp32 delta logits,
+    columns >= out_channels are zero (a row pitch the skinning kernels accept directly)."""
+
+    @staticmethod
+    def forward(ctx, pts, code, S, win, *params):
+        pshape = pts.shape
+        pts = f32(pts).reshape(-1, 3)
+        P, dev = pts.shape[0], pts.device
+        params = [f32(p) for p in params]
+        code = f32(code).reshape(-1, code.shape[-1])
+        Rc, nc = code.shape
+        rep = S if Rc * S == P else P
+        assert Rc * rep == P, "pose code rows do not match the points"
+        need_bw = any(ctx.needs_input_grad)
+        W = [params[2 * i] for i in range(5)]
+        b = [params[2 * i + 1] for i in range(5)]
+        bf, bd, br = params[11], params[13], params[17]
+        oc = br.shape[0]
+        T = (P + TILE - 1) // TILE
+        wa, _ = _win_array(win)
+        rb1 = _small_linear(code, W[0], 63, b[0], 64)
+        rb5 = _small_linear(code, W[4], 63, b[4], 64)
+        pad = torch.zeros(2, 64, device=dev, dtype=torch.float32)
+        pad[0, :bd.shape[0]] = bd
+        pad[1, :oc] = br
+        wpack = pack_skin_fwd(params, nc)
+        biases = (ctypes.c_void_p * 8)(ptr(rb1), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(rb5), ptr(bf), ptr(pad[0]), ptr(pad[1]))
+        out = torch.empty(P, 32, device=dev, dtype=torch.float32)
+        if need_bw:
+            A0 = torch.empty(P, WD, device=dev, dtype=HALF)
+            H = torch.empty(5, P, WD, device=dev, dtype=HALF)
+            fin = torch.empty(P, WD, device=dev, dtype=HALF)
+            dfe = torch.empty(P, WD, device=dev, dtype=HALF)
+            bits = torch.empty(6, T, 2, TILE, device=dev, dtype=torch.int32)
+        else:
+            A0 = H = fin = dfe = bits = None
+        call("moda_chain_skin_fwd", ptr(pts), P, rep, len(win), wa, ptr(wpack), biases, ptr(A0), ptr(H), ptr(fin),
+             ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(out), stream())
+        if need_bw:
+            ctx.save_for_backward(pts, code, *params)
+            ctx.act = (A0, H, fin, dfe, bits)
+            ctx.meta = (S, win, rep, pshape, oc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pts, code = ctx.saved_tensors[:2]
+        params = list(ctx.saved_tensors[2:])
+        A0, H, fin, dfe, bits = ctx.act
+        S, win, rep, pshape, oc = ctx.meta
+        P, dev = pts.shape[0], pts.device
+        Rc, nc = code.shape
+        W = [params[2 * i] for i in range(5)]
+        g = [torch.zeros_like(p) for p in params]
+        gout = f32(gout).reshape(P, 32)
+        sc, isc = _loss_scale(gout)
+        wpackT = pack_skin_bwd(params, nc)
+        h16 = lambda: torch.empty(P, WD, device=dev, dtype=HALF)
+        G, d_dfe, d_fin, d_pe = h16(), h16(), h16(), h16()
+        dY = torch.empty(5, P, WD, device=dev, dtype=HALF)
+        call("moda_chain_skin_bwd", ptr(gout), ptr(sc), ptr(wpackT), bits.data_ptr(), P, ptr(G), ptr(d_dfe), ptr(d_fin),
+             ptr(dY), ptr(d_pe), stream())
+        gcode = torch.zeros_like(code)
+
+        def code_part(dYl, Wl, gW, gb):
+            """hoisted pose-code columns of layers 1 / 5: everything happens at ray (or single-row) level in fp32"""
+            rbg = torch.zeros(Rc, 64, device=dev, dtype=torch.float32)
+            if Rc == 1:
+                call("moda_colsum16", ptr(dYl), WD, ptr(rbg), P, WD, ptr(isc), stream())
+            else:
+                call("moda_segsum16", ptr(dYl), WD, ptr(rbg), Rc, rep, 64, ptr(isc), 0, stream())
+            call("moda_linear_dgrad", Rc, 64, nc, ptr(rbg), 64, ptr(Wl), Wl.shape[1], 63, None, 0, 1, ptr(gcode), nc,
+                 stream())
+            call("moda_linear_wgrad", Rc, 64, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(nc), _one(nc), _one(0), _one(1),
+                 None, 0, ptr(rbg), 64, ptr(gW), Wl.shape[1], 63, ptr(gb), stream())
+
+        _wgrad(G, WD, dfe, WD, P, g[16], 0, oc, 32, isc, dbias=g[17])
+        _wgrad(d_dfe, WD, fin, WD, P, g[12], 0, 32, 64, isc, dbias=g[13])
+        _wgrad(d_fin, WD, H[4], WD, P, g[10], 0, 64, 64, isc, dbias=g[11])
+        _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc)
+        _wgrad(dY[4], WD, H[3], WD, P, g[8], 63 + nc, 64, 64, isc)
+        code_part(dY[4], W[4], g[8], g[9])
+        for i in (3, 2, 1):
+            _wgrad(dY[i], WD, H[i - 1], WD, P, g[2 * i], 0, 64, 64, isc, dbias=g[2 * i + 1])
+        _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc)
+        code_part(dY[0], W[0], g[0], g[1])
+        gpts = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        wa, _ = _win_array(win)
+        call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0, stream())
+        ctx.act = None
+        g[14] = g[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
+        return (gpts.reshape(pshape), gcode, None, None) + tuple(g)

@@ -8,6 +8,10 @@ precision:
 import os
 
 precision = os.environ.get("MODA_B200_PRECISION", "fp16")
+# fused: in "fp16" precision, run each MLP pass as ONE chain kernel that keeps activations on chip
+# (csrc/chain.cu); False selects the layer-by-layer tensor-core kernels (csrc/tc_gemm.cu), kept as the reference
+# implementation the chain kernels are tested against.
+fused = os.environ.get("MODA_B200_FUSED", "1") != "0"
 
 
 def set_precision(p):

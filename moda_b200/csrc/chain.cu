@@ -1,0 +1,961 @@
+// Fused layer chains on tcgen05: a whole MLP pass over a 128-sample tile runs inside ONE persistent CTA, with the
+// activations living in shared memory (as the next layer's A operand) and TMEM (accumulators), never in HBM
+// except for what the other pass needs (fp16 copies for the weight gradients, ReLU sign bits for the adjoint).
+//
+//   nerf_coarse forward  : PE(xyz) -> 8 x (256, ReLU, skip at layer 5) -> final -> dir layer (+ per-ray bias) -> heads
+//                          (nnutils/nerf.py:147-198 on the input evaluate_mlp assembles, geom_utils.py:19-57)
+//   nerf_coarse adjoint  : d_dfe -> d_fin -> dY[7] ... dY[0] and dPE, ReLU masks from the saved sign bits
+//   nerf_skin forward    : the same engine at width 64 with split-precision (hi, lo) fp16 operands
+//   nerf_skin adjoint    : plain fp16 chain
+//
+// One engine, table driven ("Program": a list of Steps).  Per CTA (one per SM):
+//   warp 0       weight producer: streams the packed fp16 weight chunks (K = 64 columns each) of every step through
+//                a shared-memory ring with TMA; it depends on nothing but ring slots, so it runs far ahead.
+//   warp 1       MMA issuer: for every step, waits for the A chunks it needs (written by the previous step's
+//                epilogue or by the PE producers), issues tcgen05.mma into one of two TMEM accumulators.
+//   warps 2-9    epilogue: tcgen05.ld -> bias / per-ray bias / rank-1 term / ReLU / sign-bit mask -> fp16 ->
+//                (a) the 128-byte-swizzled shared-memory chunk that is the next step's A operand, written IN PLACE
+//                (the step that read it has completed), (b) a TMA store of that same chunk to HBM for the other
+//                pass, (c) heads.  Chunk by chunk: the next step's MMAs start on chunk 0 while chunks 1-3 of the
+//                current step are still being drained, so the tensor core only idles for one chunk per layer.
+//   warps 10-13  positional-encoding producers (forward programs): sincosf in fp32, fp16 (hi[, lo]) rows written
+//                straight into the swizzled A chunk of the NEXT tile while the current tile is in flight.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace moda {
+namespace chain {
+
+using namespace moda::tc;
+
+constexpr int TILE_M = 128;
+constexpr int CHUNK_BYTES = TILE_M * 64 * 2;  // one A chunk: 128 rows x 64 fp16 (128-byte rows, SWIZZLE_128B)
+constexpr int MAX_STEPS = 14;
+constexpr int MAX_KC = 6;
+constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_SAVE_MAPS = 14;
+constexpr int MAX_STAGES = 8;
+constexpr int HEAD_SMEM = 4 * 128 * 4 * 4;    // [warp-of-quarter][row][4] floats
+
+// Epilogue flavour bits.  The complete flag word selects ONE compile-time specialisation of the epilogue
+// (run_step<F>), so the hot loop has no flag tests; flavours in use are listed in dispatch_step().
+enum : int {
+  E_RELU = 1,          // max(v, 0)
+  E_RANK1 = 2,         // v += gsig[row] * rscale * cvec[col]
+  E_MASK_IN = 4,       // v = bit ? v : 0 with the saved sign bits of slot mask_slot
+  E_MASK_OUT = 8,      // save sign bits (v > 0) into slot mask_slot
+  E_ADD_SX = 16,       // v += fp16 partial parked in the out chunk by an earlier step (same thread, same columns)
+  E_HEAD_SIGMA = 32,   // sigma = v . ws + bs (kept until the rgb step)
+  E_HEAD_RGB = 64,     // raw[row] = (sigmoid(v Wr^T + br), sigma)
+  E_OUT_F32 = 128,     // write columns < ld_y32 of the result to y32 (fp32, global)
+  E_LOAD16 = 256,      // no MMA: the tile's rows of an fp16 (M, n) global matrix become the out chunks
+  E_LOAD32 = 512,      // no MMA: fp32 (M, load_cols) * (*load_scale) -> fp16, zero padded to n
+  E_BIAS = 1024,       // + bias[col] (staged in shared memory)
+  E_ROWBIAS = 2048,    // + rowbias[row / rep][col]
+  E_SMEM = 4096,       // fp16 result -> shared-memory chunk(s) out_chunk.. (next step's A operand / TMA store source)
+  E_LO = 8192,         // also fp16(v - fp16(v)) -> out_lo_chunk.. (split precision)
+};
+
+struct Step {
+  int n;               // result width (accumulator columns): 64, 128 or 256
+  int kc;              // K chunks (0: load step)
+  int flags;
+  int out_chunk;       // first shared-memory chunk receiving the fp16 result, -1: none
+  int out_lo_chunk;    // chunk receiving fp16(v - fp16(v)) (split precision), -1: none
+  int save_map;        // TMA-store descriptor for the fp16 result, -1: not saved
+  int mask_slot;
+  int release_pe;      // last step of the tile that reads the PE chunks
+  int bias_row;        // row of the shared-memory bias table holding `bias`
+  const float* bias;     // (n) or null
+  const float* rowbias;  // (M / rep, n) or null
+  unsigned char a_chunk[MAX_KC];   // shared-memory chunk feeding K chunk kc
+  unsigned char a_gen[MAX_KC];     // which write of that chunk within the tile it must see
+  unsigned short b_col[MAX_KC];    // chunk index (64-column block) in the packed weights
+};
+
+struct Program {
+  int nsteps, num_tiles, rep, nchunks, stages, nbias;
+  long long M;
+  int wpt[MAX_CHUNKS];   // writes per tile of each chunk (ready-barrier phases per tile)
+  // positional-encoding producers
+  int pe_chunk;          // chunk of the hi half (-1: program has no PE producers), lo half in pe_chunk + 1
+  int pe_lo, pe_save_map, F;
+  float win[10];
+  const float* xyz;
+  // heads (nerf_coarse forward)
+  const float* ws; const float* bs; const float* Wr; const float* br; float* raw;
+  // rank-1 term (nerf_coarse adjoint): gsig (M), cvec (n), rscale (device scalar)
+  const float* gsig; const float* cvec; const float* rscale;
+  // load steps
+  const void* load_src; int load_ld; int load_cols; const float* load_scale;
+  // fp32 output
+  float* y32; int ld_y32;
+  unsigned int* maskbits;
+  Step st[MAX_STEPS];
+};
+
+struct Maps {
+  CUtensorMap w;                     // packed weights, box = 64 columns x BOX_ROWS rows
+  CUtensorMap save[MAX_SAVE_MAPS];   // fp16 outputs, box = 64 columns x 128 rows
+};
+
+// spin on an mbarrier phase; a wait that lasts seconds means a protocol bug: trap instead of hanging the GPU
+__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) {
+      printf("moda chain: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             addr, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2_lo(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  return *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void tma_store_2d_u32(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// per-thread state of an epilogue warp that does not change within a tile
+struct EpiCtx {
+  uint32_t sA;          // shared-window address of chunk 0
+  uint32_t s_bias;      // shared-window address of the bias table
+  uint32_t tmem_row;    // TMEM address of this warp's lane quarter, column 0
+  int trow, sw, h;      // row within the tile, its swizzle phase, first sub-block of this warp within a chunk
+  int tile, T;
+  long long row;
+  bool live, lead;
+  float rscale, lscale;
+};
+
+// One step's epilogue for this warp, specialised on the flavour F.  Sub-blocks of 16 columns are processed
+// chunk-major with the TMEM load of the next sub-block in flight; after each completed 64-column chunk:
+// proxy fence, barrier among the epilogue warps, then the lead thread hands the chunk to the tensor core
+// (mbarrier) and to TMA (store for the other pass).  NH warps share a TMEM lane quarter: warp h owns the
+// sub-blocks {h, h + NH, ..} < 4 of every chunk.
+template <int F, int NH, int ACC_STRIDE, int EPI_THREADS>
+__device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
+                                         uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1, float& hs2) {
+  constexpr int NCH16 = ACC_STRIDE / 16;
+  constexpr int SPC = 4 / NH;                  // sub-blocks per chunk for this warp
+  constexpr bool MMA = !(F & (E_LOAD16 | E_LOAD32));
+  const int n = st.n;
+  const int nch = n >> 6;
+  const int nsub = nch * SPC;
+  const uint32_t t_addr = cx.tmem_row + acc_col;
+  auto col_of = [&](int i) { return (i / SPC) * 64 + (cx.h + NH * (i % SPC)) * 16; };
+  float va[16], vb[16];
+  if (MMA) tmem_ld16_issue(t_addr + (uint32_t)col_of(0), va);
+  float rvv = 0.f;
+  if (F & E_RANK1) rvv = cx.live ? pg.gsig[cx.row] * cx.rscale : 0.f;
+  const float* rb = nullptr;
+  if (F & E_ROWBIAS) rb = st.rowbias + (size_t)((cx.live ? cx.row : 0) / pg.rep) * n;
+  const uint32_t sb = cx.s_bias + (uint32_t)(st.bias_row * ACC_STRIDE * 4);
+  if ((F & E_SMEM) && nch == 1) {
+    // single-chunk steps rewrite the chunk the previous step saved: its TMA store must have read it
+    if (cx.lead) bulk_wait_read0();
+    named_bar(3, EPI_THREADS);
+  }
+  auto sub = [&](const int i, float* __restrict__ v, float* __restrict__ vn) {
+    const int cc = col_of(i);                // first of this thread's 16 columns
+    const int c64 = cc >> 6;                 // chunk within the result
+    const int p0 = (cc & 63) >> 3;           // first 16-byte piece within the chunk row (2 pieces per sub-block)
+    const int chunk = st.out_chunk + c64;
+    const uint32_t crow = cx.sA + (uint32_t)(chunk * CHUNK_BYTES + cx.trow * 128);
+    const bool last_of_chunk = (i % SPC) == SPC - 1;
+    if (F & E_LOAD16) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(pg.load_src) +
+                                                        (size_t)cx.row * pg.load_ld + cc);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint4 o = cx.live ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
+        sts128(crow + (((p0 + j) ^ cx.sw) << 4), o.x, o.y, o.z, o.w);
+      }
+    } else {
+      if (F & E_LOAD32) {
+        const bool in = cx.live && cc < pg.load_cols;
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pg.load_src) +
+                                                            (size_t)cx.row * pg.load_ld + cc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = in ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j] = f.x * cx.lscale; v[4 * j + 1] = f.y * cx.lscale;
+          v[4 * j + 2] = f.z * cx.lscale; v[4 * j + 3] = f.w * cx.lscale;
+        }
+      } else {
+        tmem_ld_wait();
+        if (i + 1 < nsub) tmem_ld16_issue(t_addr + (uint32_t)col_of(i + 1), vn);
+      }
+      unsigned int mbits = 0;
+      unsigned short* mp = nullptr;
+      if (F & (E_MASK_IN | E_MASK_OUT)) {
+        // 16 bits per (row, 16 columns); column j <-> bit 15 - j; bit set = pre-activation >= 0
+        mp = reinterpret_cast<unsigned short*>(pg.maskbits) +
+             (((size_t)st.mask_slot * cx.T + cx.tile) * NCH16 + (cc >> 4)) * TILE_M + cx.trow;
+        if (F & E_MASK_IN) mbits = *mp;
+      }
+      if (F & E_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = lds128f(sb + (uint32_t)((cc + 4 * j) * 4));
+          v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+        }
+      }
+      if (F & E_ROWBIAS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(rb + cc) + j);
+          v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+        }
+      }
+      if (F & E_RANK1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(pg.cvec + cc) + j);
+          v[4 * j] = fmaf(rvv, f.x, v[4 * j]); v[4 * j + 1] = fmaf(rvv, f.y, v[4 * j + 1]);
+          v[4 * j + 2] = fmaf(rvv, f.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(rvv, f.w, v[4 * j + 3]);
+        }
+      }
+      if (F & E_MASK_IN) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (mbits & (0x8000u >> j)) ? v[j] : 0.f;
+      }
+      if (F & E_MASK_OUT) {
+        // sign bits by funnel shift, two independent 8-element chains (one instruction per element)
+        unsigned int n0 = 0, n1 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          n0 = __funnelshift_l(__float_as_uint(v[j]), n0, 1);
+          n1 = __funnelshift_l(__float_as_uint(v[8 + j]), n1, 1);
+        }
+        *mp = (unsigned short)(~((n0 << 8) | n1));
+      }
+      if (F & E_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (F & E_ADD_SX) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 o = lds128(crow + (((p0 + j) ^ cx.sw) << 4));
+          const __half2* oh = reinterpret_cast<const __half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(oh[e]);
+            v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y;
+          }
+        }
+      }
+      if (F & E_HEAD_SIGMA) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(pg.ws + cc) + j);
+          hs0 = fmaf(v[4 * j], f.x, hs0); hs0 = fmaf(v[4 * j + 1], f.y, hs0);
+          hs0 = fmaf(v[4 * j + 2], f.z, hs0); hs0 = fmaf(v[4 * j + 3], f.w, hs0);
+        }
+      }
+      if (F & E_HEAD_RGB) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pg.Wr + cc) + j);
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pg.Wr + n + cc) + j);
+          const float4 f2 = __ldg(reinterpret_cast<const float4*>(pg.Wr + 2 * n + cc) + j);
+          hs0 = fmaf(v[4 * j], f0.x, hs0); hs0 = fmaf(v[4 * j + 1], f0.y, hs0);
+          hs0 = fmaf(v[4 * j + 2], f0.z, hs0); hs0 = fmaf(v[4 * j + 3], f0.w, hs0);
+          hs1 = fmaf(v[4 * j], f1.x, hs1); hs1 = fmaf(v[4 * j + 1], f1.y, hs1);
+          hs1 = fmaf(v[4 * j + 2], f1.z, hs1); hs1 = fmaf(v[4 * j + 3], f1.w, hs1);
+          hs2 = fmaf(v[4 * j], f2.x, hs2); hs2 = fmaf(v[4 * j + 1], f2.y, hs2);
+          hs2 = fmaf(v[4 * j + 2], f2.z, hs2); hs2 = fmaf(v[4 * j + 3], f2.w, hs2);
+        }
+      }
+      if (F & E_OUT_F32) {
+        if (cx.live && cc < pg.ld_y32) {
+          float4* yp = reinterpret_cast<float4*>(pg.y32 + (size_t)cx.row * pg.ld_y32 + cc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      if (F & E_SMEM) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          sts128(crow + (((p0 + j) ^ cx.sw) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                 pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+        if (F & E_LO) {
+          const uint32_t crow_lo = cx.sA + (uint32_t)((st.out_lo_chunk + c64) * CHUNK_BYTES + cx.trow * 128);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            sts128(crow_lo + (((p0 + j) ^ cx.sw) << 4), pack2_lo(v[8 * j], v[8 * j + 1]),
+                   pack2_lo(v[8 * j + 2], v[8 * j + 3]), pack2_lo(v[8 * j + 4], v[8 * j + 5]),
+                   pack2_lo(v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+    }
+    if ((F & E_SMEM) && last_of_chunk) {
+      fence_async_smem();   // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
+      // every earlier TMA store of the lead thread has read its source before anyone passes this barrier:
+      // together with the chunk-major order this protects the in-place rewrite of multi-chunk results
+      if (cx.lead) bulk_wait_read0();
+      named_bar(3, EPI_THREADS);
+      if (cx.lead) {
+        if (st.save_map >= 0) {
+          tma_store_2d_u32(&maps.save[st.save_map], cx.sA + (uint32_t)(chunk * CHUNK_BYTES), c64 * 64, cx.tile * TILE_M);
+          bulk_commit();
+        }
+        mbar_arrive(&ready[chunk]);
+        if (F & E_LO) mbar_arrive(&ready[st.out_lo_chunk + c64]);
+      }
+    }
+  };
+#pragma unroll 1
+  for (int i2 = 0; i2 < nsub; i2 += 2) {
+    sub(i2, va, vb);
+    if (i2 + 1 < nsub) sub(i2 + 1, vb, va);
+  }
+}
+
+// BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
+// 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
+// the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__((2 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
+chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
+  constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;       // TMEM columns per accumulator
+  constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr int BOX_BYTES = BOX_ROWS * 128;
+  constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_BYTES : BOX_BYTES;
+  constexpr int NH = EPI_WARPS / 4;                              // warps sharing one TMEM lane quarter
+  constexpr int EPI_THREADS = EPI_WARPS * 32;
+  constexpr int PE_THREADS = PE_WARPS * 32;
+  constexpr int PE_ROWS = TILE_M / PE_THREADS;                   // rows per producer thread
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                            // nchunks x 16 KB
+  uint8_t* sB = sA + (size_t)pg.nchunks * CHUNK_BYTES;           // stages x STAGE_BYTES
+  float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);
+  float* s_bias = s_head + HEAD_SMEM / 4;                        // nbias x ACC_STRIDE floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.nbias * ACC_STRIDE);
+  uint64_t* w_full = bars;                       // [MAX_STAGES]
+  uint64_t* w_empty = w_full + MAX_STAGES;       // [MAX_STAGES]
+  uint64_t* ready = w_empty + MAX_STAGES;        // [MAX_CHUNKS] chunk (re)written and visible to the tensor core
+  uint64_t* acc_full = ready + MAX_CHUNKS;       // [2]
+  uint64_t* acc_free = acc_full + 2;             // [2]
+  uint64_t* pe_free = acc_free + 2;              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pe_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = pg.num_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS); }
+    mbar_init(pe_free, 1);
+    fence_barrier_init();
+  }
+  // biases of every step, staged once (step s reads row bias_row[s])
+  for (int s = 0; s < pg.nsteps; ++s) {
+    const Step& st = pg.st[s];
+    if (st.bias)
+      for (int i = threadIdx.x; i < st.n; i += blockDim.x) s_bias[st.bias_row * ACC_STRIDE + i] = st.bias[i];
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== weight producer
+    if (lane == 0) {
+      prefetch_tmap(&maps.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+        for (int s = 0; s < pg.nsteps; ++s) {
+          const Step& st = pg.st[s];
+          const int boxes = st.n > BOX_ROWS ? st.n / BOX_ROWS : 1;
+          for (int kc = 0; kc < st.kc; ++kc) {
+            wait_or_trap(&w_empty[stage], phase ^ 1);
+            mbar_expect_tx(&w_full[stage], (uint32_t)(boxes * BOX_BYTES));
+            for (int bx = 0; bx < boxes; ++bx)
+              tma_load_2d(sB + (size_t)stage * STAGE_BYTES + bx * BOX_BYTES, &maps.w, &w_full[stage],
+                          (int)st.b_col[kc] * 64, bx * BOX_ROWS);
+            if (++stage == pg.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, mma_ctr = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
+        for (int s = 0; s < pg.nsteps; ++s) {
+          const Step& st = pg.st[s];
+          if (st.kc == 0) continue;
+          const int b = mma_ctr & 1;
+          wait_or_trap(&acc_free[b], ((mma_ctr >> 1) & 1) ^ 1);   // epilogue of two MMA steps ago has drained it
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
+          const uint32_t idesc = make_idesc(TILE_M, st.n, 0, 0);
+          for (int kc = 0; kc < st.kc; ++kc) {
+            const int c = st.a_chunk[kc];
+            const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + st.a_gen[kc];
+            wait_or_trap(&ready[c], gen & 1);
+            wait_or_trap(&w_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + (size_t)c * CHUNK_BYTES);
+            const uint32_t b_addr = smem_u32(sB + (size_t)stage * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
+              umma_f16(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[stage]);
+            if (++stage == pg.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[b]);
+          if (st.release_pe) umma_commit(pe_free);
+          ++mma_ctr;
+        }
+      }
+    }
+  } else if (warp < 2 + EPI_WARPS) {
+    // ================================================================== epilogue
+    // Column assignment is chunk-major: for every 64-column chunk of the result, warp (q, h) owns the 32-column
+    // sub-blocks {h, h + NH, ..} < 2 of lane quarter q.  All warps therefore finish chunk 0 first, and the next
+    // step's MMAs start on it while chunks 1.. are still being drained.
+    const int ew = warp - 2;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    EpiCtx cx;
+    cx.sA = smem_u32(sA);
+    cx.s_bias = smem_u32(s_bias);
+    cx.tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    cx.h = ew >> 2;
+    cx.trow = q * 32 + lane;
+    cx.sw = cx.trow & 7;
+    cx.lead = (ew == 0) && lane == 0;
+    cx.rscale = pg.rscale ? *pg.rscale : 1.0f;
+    cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
+    cx.T = T;
+    const int h = cx.h, trow = cx.trow;
+    uint32_t mma_ctr = 0;
+    float sig_keep = 0.f;
+    for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+      cx.tile = tile;
+      cx.row = (long long)tile * TILE_M + trow;
+      cx.live = cx.row < pg.M;
+      for (int s = 0; s < pg.nsteps; ++s) {
+        const Step& st = pg.st[s];
+        const int flags = st.flags;
+        int b = 0;
+        if (st.kc > 0) {
+          b = mma_ctr & 1;
+          wait_or_trap(&acc_full[b], (mma_ctr >> 1) & 1);
+          tc_fence_after();
+        }
+        float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
+        const uint32_t acc_col = (uint32_t)(b * ACC_STRIDE);
+#define MODA_STEP(FL) case (FL): run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2); break
+        if (BOX_ROWS == 128) {
+          switch (flags) {
+            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM);                  // hidden layer (training)
+            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_HEAD_SIGMA);   // last hidden layer + sigma head
+            MODA_STEP(E_BIAS | E_RELU | E_SMEM);                               // hidden layer (inference)
+            MODA_STEP(E_BIAS | E_RELU | E_SMEM | E_HEAD_SIGMA);
+            MODA_STEP(E_BIAS | E_SMEM);                                        // xyz_encoding_final
+            MODA_STEP(E_ROWBIAS | E_RELU | E_SMEM | E_HEAD_RGB);               // dir_encoding + rgb head
+            MODA_STEP(E_LOAD16 | E_SMEM);                                      // adjoint: d_dfe tile
+            MODA_STEP(E_SMEM);                                                 // adjoint: d_fin, dPE partial
+            MODA_STEP(E_RANK1 | E_MASK_IN | E_SMEM);                           // adjoint: dY[7]
+            MODA_STEP(E_MASK_IN | E_SMEM);                                     // adjoint: dY[l]
+            MODA_STEP(E_ADD_SX | E_SMEM);                                      // adjoint: dPE
+            default: __trap();
+          }
+        } else {
+          switch (flags) {
+            MODA_STEP(E_ROWBIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);        // layers 1 / 5 (pose code as row bias)
+            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);           // hidden layers, dir layer
+            MODA_STEP(E_ROWBIAS | E_RELU | E_SMEM | E_LO);                     // same, inference
+            MODA_STEP(E_BIAS | E_RELU | E_SMEM | E_LO);
+            MODA_STEP(E_BIAS | E_SMEM | E_LO);                                 // xyz_encoding_final
+            MODA_STEP(E_BIAS | E_OUT_F32);                                     // delta-logit output
+            MODA_STEP(E_LOAD32 | E_SMEM);                                      // adjoint: scaled output gradient
+            MODA_STEP(E_MASK_IN | E_SMEM);
+            MODA_STEP(E_SMEM);
+            MODA_STEP(E_ADD_SX | E_SMEM);
+            default: __trap();
+          }
+        }
+#undef MODA_STEP
+        if (st.kc > 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[b]);
+          ++mma_ctr;
+        }
+        if (flags & E_HEAD_SIGMA) {
+          s_head[(h * 128 + trow) * 4 + 3] = hs0;
+          named_bar(4, EPI_THREADS);
+          if (h == 0) {
+            sig_keep = pg.bs[0];
+#pragma unroll
+            for (int k = 0; k < NH; ++k) sig_keep += s_head[(k * 128 + trow) * 4 + 3];
+          }
+        }
+        if (flags & E_HEAD_RGB) {
+          float* mine = s_head + (h * 128 + trow) * 4;
+          mine[0] = hs0; mine[1] = hs1; mine[2] = hs2;
+          named_bar(4, EPI_THREADS);
+          if (h == 0 && cx.live) {
+            float o0 = pg.br[0], o1 = pg.br[1], o2 = pg.br[2];
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+              const float* part = s_head + (k * 128 + trow) * 4;
+              o0 += part[0]; o1 += part[1]; o2 += part[2];
+            }
+            float4 o;
+            o.x = 1.0f / (1.0f + expf(-o0));
+            o.y = 1.0f / (1.0f + expf(-o1));
+            o.z = 1.0f / (1.0f + expf(-o2));
+            o.w = sig_keep;
+            *reinterpret_cast<float4*>(pg.raw + cx.row * 4) = o;
+          }
+          named_bar(4, EPI_THREADS);   // s_head is reused by the next tile's sigma partials
+        }
+      }
+    }
+    if (cx.lead) bulk_wait_all0();
+  } else {
+    // ================================================================== positional-encoding producers
+    if (pg.pe_chunk >= 0) {
+      const int pw = warp - 2 - EPI_WARPS;
+      const bool lead = (pw == 0) && lane == 0;
+      int it = 0;
+      const uint32_t pe_base = smem_u32(sA) + (uint32_t)(pg.pe_chunk * CHUNK_BYTES);
+      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
+        // channels: [x(3) | w_k sin(2^k x)(3) | w_k cos(2^k x)(3)]_k, zero padded to 64 (nnutils/nerf.py:35-75)
+        if (BOX_ROWS == 128) {
+          // one row per thread, fp16 only: the row is computed into 32 packed registers BEFORE waiting for the
+          // chunk, i.e. while the previous tile is still in flight; afterwards only 8 stores remain
+          const int trow = pw * 32 + lane;
+          const int sw = trow & 7;
+          const long long row = (long long)tile * TILE_M + trow;
+          float x[3] = {0.f, 0.f, 0.f};
+          if (row < pg.M) { x[0] = pg.xyz[row * 3]; x[1] = pg.xyz[row * 3 + 1]; x[2] = pg.xyz[row * 3 + 2]; }
+          uint32_t hreg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hreg[j] = 0u;
+          auto put = [&](const int idx, float v) {
+            const uint32_t bits = (uint32_t)__half_as_ushort(__float2half_rn(v));
+            hreg[idx >> 1] |= (idx & 1) ? (bits << 16) : bits;
+          };
+          put(0, x[0]); put(1, x[1]); put(2, x[2]);
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            const float f = (float)(1 << k);
+            const float w = (k < pg.F) ? pg.win[k] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sn, cs;
+              sincosf(x[c] * f, &sn, &cs);
+              put(3 + 6 * k + c, w * sn);
+              put(3 + 6 * k + 3 + c, w * cs);
+            }
+          }
+          wait_or_trap(pe_free, (it & 1) ^ 1);   // the previous tile's last reader of the PE chunk has completed
+          if (lead) bulk_wait_read0();
+          named_bar(5, PE_THREADS);
+          const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(hrow + ((j ^ sw) << 4), hreg[4 * j], hreg[4 * j + 1], hreg[4 * j + 2], hreg[4 * j + 3]);
+        } else {
+          // split precision (hi and lo chunks), PE_ROWS rows per thread, two CTAs per SM hide the latency:
+          // values go straight to shared memory as they are produced
+          wait_or_trap(pe_free, (it & 1) ^ 1);
+          if (lead) bulk_wait_read0();
+          named_bar(5, PE_THREADS);
+#pragma unroll 1
+          for (int rr = 0; rr < PE_ROWS; ++rr) {
+            const int trow = (pw * 32 + lane) * PE_ROWS + rr;
+            const int sw = trow & 7;
+            const long long row = (long long)tile * TILE_M + trow;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (row < pg.M) { x[0] = pg.xyz[row * 3]; x[1] = pg.xyz[row * 3 + 1]; x[2] = pg.xyz[row * 3 + 2]; }
+            const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
+            auto put = [&](const int idx, float v) {
+              const __half hv = __float2half_rn(v);
+              const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + (idx & 7) * 2);
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(hv)) : "memory");
+              if (pg.pe_lo) {
+                const __half lv = __float2half_rn(v - __half2float(hv));
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + CHUNK_BYTES), "h"(__half_as_ushort(lv)) : "memory");
+              }
+            };
+            put(0, x[0]); put(1, x[1]); put(2, x[2]);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+              const float f = (float)(1 << k);
+              const float w = (k < pg.F) ? pg.win[k] : 0.f;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                sincosf(x[c] * f, &sn, &cs);
+                put(3 + 6 * k + c, w * sn);
+                put(3 + 6 * k + 3 + c, w * cs);
+              }
+            }
+            put(63, 0.f);
+          }
+        }
+        fence_async_smem();
+        named_bar(5, PE_THREADS);
+        if (lead) {
+          if (pg.pe_save_map >= 0) {
+            tma_store_2d_u32(&maps.save[pg.pe_save_map], pe_base, 0, tile * TILE_M);
+            bulk_commit();
+          }
+          mbar_arrive(&ready[pg.pe_chunk]);
+          if (pg.pe_lo) mbar_arrive(&ready[pg.pe_chunk + 1]);
+        }
+      }
+      if (lead) bulk_wait_all0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace chain
+}  // namespace moda
+
+// ====================================================================================================== host side
+#include "tc_host.cuh"
+
+using namespace moda;
+using namespace moda::chain;
+
+namespace {
+
+struct Builder {
+  Program pg;
+  Maps maps;
+  int nsave = 0;
+  int gen[MAX_CHUNKS];   // writes issued so far to each chunk within the tile
+  int err = 0;
+
+  Builder() {
+    memset(&pg, 0, sizeof(pg));
+    memset(&maps, 0, sizeof(maps));
+    memset(gen, 0, sizeof(gen));
+    pg.pe_chunk = -1;
+    pg.pe_save_map = -1;
+  }
+  // registers an fp16 (rows, cols) output for TMA stores; returns its descriptor index, -1 when ptr is null
+  int save(const void* ptr, long long rows, int cols) {
+    if (!ptr) return -1;
+    if (nsave >= MAX_SAVE_MAPS) { set_error("chain: too many saved outputs"); err = -1; return -1; }
+    if (int e = make_map(&maps.save[nsave], ptr, rows, cols, cols, TILE_M)) { err = e; return -1; }
+    return nsave++;
+  }
+  Step& add(int n, int flags) {
+    Step& st = pg.st[pg.nsteps++];
+    st.n = n; st.flags = flags; st.kc = 0;
+    st.out_chunk = st.out_lo_chunk = st.save_map = -1;
+    st.mask_slot = 0; st.release_pe = 0; st.bias_row = 0; st.bias = nullptr; st.rowbias = nullptr;
+    return st;
+  }
+  // K chunk: A from shared-memory chunk `a` (its latest write), B from packed-weight chunk `bcol`
+  void k(Step& st, int a, int bcol) {
+    st.a_chunk[st.kc] = (unsigned char)a;
+    st.a_gen[st.kc] = (unsigned char)(gen[a] - 1);
+    st.b_col[st.kc] = (unsigned short)bcol;
+    ++st.kc;
+  }
+  // the step's epilogue writes `count` chunks starting at `first` (and optionally their lo halves)
+  void out(Step& st, int first, int count, int lo_first = -1) {
+    st.out_chunk = first;
+    st.out_lo_chunk = lo_first;
+    st.flags |= E_SMEM | (lo_first >= 0 ? E_LO : 0);
+    for (int i = 0; i < count; ++i) { ++gen[first + i]; if (lo_first >= 0) ++gen[lo_first + i]; }
+  }
+  void pe(int chunk, bool lo, int save_map) {
+    pg.pe_chunk = chunk; pg.pe_lo = lo ? 1 : 0; pg.pe_save_map = save_map;
+    ++gen[chunk];
+    if (lo) ++gen[chunk + 1];
+  }
+  void finish() {
+    for (int i = 0; i < MAX_CHUNKS; ++i) pg.wpt[i] = gen[i];
+    pg.nbias = 0;
+    for (int s = 0; s < pg.nsteps; ++s) {
+      Step& st = pg.st[s];
+      if (st.bias) { st.bias_row = pg.nbias++; st.flags |= E_BIAS; }
+      if (st.rowbias) st.flags |= E_ROWBIAS;
+    }
+  }
+};
+
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
+int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
+  if (b.err) return b.err;
+  b.finish();
+  if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, BOX_ROWS)) return e;
+  constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128;
+  constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;
+  constexpr int THREADS = (2 + EPI_WARPS + PE_WARPS) * 32;
+  const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + HEAD_SMEM +
+                      (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512;
+  const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
+  MODA_REQUIRE(smem <= cap, "chain: needs %zu B of shared memory (limit %zu)", smem, cap);
+  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    attr_set = true;
+  }
+  const int slots = sm_count() * MIN_CTAS;
+  const int grid = b.pg.num_tiles < slots ? b.pg.num_tiles : slots;
+  kern<<<grid, THREADS, smem, stream>>>(b.pg, b.maps);
+  return check_launch("chain");
+}
+
+void fill_win(Program& pg, int F, const float* win) {
+  pg.F = F;
+  for (int i = 0; i < 10; ++i) pg.win[i] = (win && i < F) ? win[i] : 1.0f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- nerf_coarse
+// Packed weights wpack: fp16 (256, 38*64), 64-column chunks in this order (rows = output channel, zero padded):
+//   0: W1[:, :63]   1-4: W2   5-8: W3   9-12: W4   13: W5[:, :63]   14-17: W5[:, 63:]   18-21: W6   22-25: W7
+//   26-29: W8   30-33: Wfinal   34-37: Wdir[:, :256] (128 rows)
+// biases: b1..b8, bfinal.  rowbias (P / rep, 128) = Wdir[:, 256:] [dir | env] + bdir per ray.
+// Saved for the adjoint / weight gradients when non-null: A0 (P,64) = fp16 PE, H (8,P,256), fin (P,256),
+// dfe (P,128), maskbits (8, tiles, 8, 128) uint32 sign bits of H.  raw (P,4) = [sigmoid(rgb) | sigma].
+extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int F, const float* win, const void* wpack,
+                                    const float* const* biases, const float* rowbias, const float* ws, const float* bs,
+                                    const float* Wr, const float* br, void* A0, void* H, void* fin, void* dfe,
+                                    unsigned int* maskbits, float* raw, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(xyz && wpack && biases && rowbias && ws && bs && Wr && br && raw && rep > 0 && F >= 0 && F <= 10,
+               "chain_trunk_fwd: bad arguments");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = 4;
+  pg.xyz = xyz; fill_win(pg, F, win);
+  pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
+  const int PE = 4;
+  const int order[4] = {0, 2, 1, 3};   // chunks 0 and 2 of a 256-wide result are written first
+  b.pe(PE, false, b.save(A0, P, 64));
+  int col = 0;
+  for (int l = 0; l < 8; ++l) {
+    Step& st = b.add(256, E_RELU | (maskbits ? E_MASK_OUT : 0));
+    st.bias = biases[l]; st.mask_slot = l;
+    if (l == 0) { b.k(st, PE, col); col += 1; }
+    else {
+      if (l == 4) { b.k(st, PE, col); col += 1; st.release_pe = 1; }
+      for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
+      col += 4;
+    }
+    if (l == 7) st.flags |= E_HEAD_SIGMA;
+    st.save_map = b.save(H ? (const char*)H + (size_t)l * P * 256 * 2 : nullptr, P, 256);
+    b.out(st, 0, 4);
+  }
+  {
+    Step& st = b.add(256, 0);           // xyz_encoding_final (no activation)
+    st.bias = biases[8];
+    for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
+    col += 4;
+    st.save_map = b.save(fin, P, 256);
+    b.out(st, 0, 4);
+  }
+  {
+    Step& st = b.add(128, E_RELU | E_HEAD_RGB);   // dir_encoding on [fin | per-ray constant part as a bias]
+    st.rowbias = rowbias;
+    for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
+    col += 4;
+    st.save_map = b.save(dfe, P, 128);
+    b.out(st, 0, 2);
+  }
+  return launch<128, 16, 4, 1>(b, wpack, 256, col * 64, stream);
+}
+
+// Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
+// layer (the N of the data-gradient GEMM), columns = its output channel (K):
+//   0-1: Wdir[:, :256]^T (K = 128)   2-5: Wfinal^T   6-9: W8^T   10-13: W7^T   14-17: W6^T
+//   18-21: W5[:, :63]^T (64 rows)   22-25: W5[:, 63:]^T   26-29: W4^T   30-33: W3^T   34-37: W2^T
+//   38-41: W1[:, :63]^T (64 rows)
+// In: d_dfe (P,128) fp16 = scaled gradient at the dir layer's pre-activation (already ReLU-masked), gsig (P),
+// ws (256), rscale (device scalar): dY[7] gets + gsig * ws * rscale before its mask.
+// Out (fp16): d_fin (P,256), dY (8,P,256) with dY[i] = gradient at layer i's pre-activation, d_pe (P,64).
+extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const float* ws, const float* rscale,
+                                    const void* wpackT, const unsigned int* maskbits, long long P, void* d_fin,
+                                    void* dY, void* d_pe, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && d_fin && dY && d_pe, "chain_trunk_bwd: null pointer");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
+  pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
+  pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
+  const int SX = 4;
+  const int order[4] = {0, 2, 1, 3};
+  auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 256 * 2; };
+  { Step& st = b.add(128, E_LOAD16); b.out(st, 0, 2); }
+  {
+    Step& st = b.add(256, 0);                       // d_fin = d_dfe Wdir[:, :256]
+    b.k(st, 0, 0); b.k(st, 1, 1);
+    st.save_map = b.save(d_fin, P, 256);
+    b.out(st, 0, 4);
+  }
+  {
+    Step& st = b.add(256, E_RANK1 | E_MASK_IN);     // dY[7] = (d_fin Wfinal + gsig ws) . [H8 > 0]
+    for (int i = 0; i < 4; ++i) b.k(st, order[i], 2 + order[i]);
+    st.mask_slot = 7; st.save_map = b.save(dy(7), P, 256);
+    b.out(st, 0, 4);
+  }
+  int col = 6;
+  for (int l = 7; l >= 1; --l) {
+    if (l == 4) {
+      Step& sx = b.add(64, 0);                      // dPE partial = dY[4] W5[:, :63], parked in the SX chunk
+      for (int i = 0; i < 4; ++i) b.k(sx, order[i], col + order[i]);
+      col += 4;
+      b.out(sx, SX, 1);
+    }
+    Step& st = b.add(256, E_MASK_IN);               // dY[l-1] = (dY[l] W_{l+1}[:, hidden]) . [H_l > 0]
+    for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
+    col += 4;
+    st.mask_slot = l - 1; st.save_map = b.save(dy(l - 1), P, 256);
+    b.out(st, 0, 4);
+  }
+  {
+    Step& st = b.add(64, E_ADD_SX);                 // dPE = dY[0] W1[:, :63] + partial
+    for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
+    col += 4;
+    st.save_map = b.save(d_pe, P, 64);
+    b.out(st, SX, 1);
+  }
+  return launch<128, 16, 4, 1>(b, wpackT, 256, col * 64, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ nerf_skin
+// Split precision: every operand is an fp16 (hi, lo) pair and  x W^T ~ hi Whi^T + lo Whi^T + hi Wlo^T.
+// Packed weights wpack: fp16 (64, 18*64); per layer the chunks [Whi | Wlo] (rows = output channel, zero padded to 64):
+//   0-1: W1[:, :63]   2-3: W2   4-5: W3   6-7: W4   8-9: W5[:, :63]   10-11: W5[:, 63+nc:]   12-13: Wfinal
+//   14-15: Wdir (32 rows)   16-17: Wrgb (K = 32, rows = out_channels)
+// biases[8]: rb1 (rowbias (P/rep,64): pose-code part of layer 1 + b1), b2, b3, b4, rb5 (rowbias), bfinal,
+// bdir (padded to 64), brgb (padded to 64).  Out: y32 (P,32) fp32 delta logits; saved (hi halves, fp16) when
+// non-null: A0 (P,64), H (5,P,64), fin (P,64), dfe (P,64), maskbits (6, tiles, 2, 128): H1..H5, dfe.
+extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const float* win, const void* wpack,
+                                   const float* const* biases, void* A0, void* H, void* fin, void* dfe,
+                                   unsigned int* maskbits, float* y32, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(xyz && wpack && biases && y32 && rep > 0 && F >= 0 && F <= 10, "chain_skin_fwd: bad arguments");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 4; pg.stages = 4;
+  pg.xyz = xyz; fill_win(pg, F, win);
+  pg.maskbits = maskbits; pg.y32 = y32; pg.ld_y32 = 32;
+  const int PEH = 0, PEL = 1, AH = 2, AL = 3;
+  b.pe(PEH, true, b.save(A0, P, 64));
+  const int mo = maskbits ? E_MASK_OUT : 0;
+  auto split = [&](Step& st, int hi, int lo, int wc) { b.k(st, hi, wc); b.k(st, lo, wc); b.k(st, hi, wc + 1); };
+  for (int l = 0; l < 5; ++l) {
+    Step& st = b.add(64, E_RELU | mo);
+    st.mask_slot = l;
+    if (l == 0) { st.rowbias = biases[0]; split(st, PEH, PEL, 0); }
+    else if (l == 4) { st.rowbias = biases[4]; split(st, PEH, PEL, 8); split(st, AH, AL, 10); st.release_pe = 1; }
+    else { st.bias = biases[l]; split(st, AH, AL, 2 * l); }
+    st.save_map = b.save(H ? (const char*)H + (size_t)l * P * 64 * 2 : nullptr, P, 64);
+    b.out(st, AH, 1, AL);
+  }
+  { Step& st = b.add(64, 0); st.bias = biases[5]; split(st, AH, AL, 12); st.save_map = b.save(fin, P, 64); b.out(st, AH, 1, AL); }
+  { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, 14);
+    st.save_map = b.save(dfe, P, 64); b.out(st, AH, 1, AL); }
+  { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, 16); }
+  return launch<64, 8, 2, 2>(b, wpack, 64, 18 * 64, stream);
+}
+
+// Adjoint chain of nerf_skin on plain fp16 operands.  wpackT: fp16 (64, 9*64), rows = input channel, cols = output:
+//   0: Wrgb^T (rows: 32 dfe channels; K: out_channels)   1: Wdir^T (K = 32)   2: Wfinal^T   3: W5[:, :63]^T
+//   4: W5[:, 63+nc:]^T   5: W4^T   6: W3^T   7: W2^T   8: W1[:, :63]^T
+// In: gout (P,32) fp32 (columns >= out_channels zero), scale (device scalar), maskbits from the forward.
+// Out (fp16, 64 columns): G = scale * gout, d_dfe, d_fin, dY (5,P,64), d_pe.
+extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const void* wpackT,
+                                   const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
+                                   void* dY, void* d_pe, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(gout && wpackT && maskbits && G && d_dfe && d_fin && dY && d_pe, "chain_skin_bwd: null pointer");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 2; pg.stages = 8;
+  pg.maskbits = const_cast<unsigned int*>(maskbits);
+  pg.load_src = gout; pg.load_ld = 32; pg.load_cols = 32; pg.load_scale = scale;
+  const int A = 0, SX = 1;
+  auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 64 * 2; };
+  { Step& st = b.add(64, E_LOAD32); st.save_map = b.save(G, P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, E_MASK_IN); b.k(st, A, 0); st.mask_slot = 5; st.save_map = b.save(d_dfe, P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, 0); b.k(st, A, 1); st.save_map = b.save(d_fin, P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, E_MASK_IN); b.k(st, A, 2); st.mask_slot = 4; st.save_map = b.save(dy(4), P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, 0); b.k(st, A, 3); b.out(st, SX, 1); }
+  for (int l = 4; l >= 1; --l) {
+    Step& st = b.add(64, E_MASK_IN);
+    b.k(st, A, 4 + (4 - l));
+    st.mask_slot = l - 1; st.save_map = b.save(dy(l - 1), P, 64);
+    b.out(st, A, 1);
+  }
+  { Step& st = b.add(64, E_ADD_SX); b.k(st, A, 8); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
+  return launch<64, 8, 2, 2>(b, wpackT, 64, 9 * 64, stream);
+}

@@ -6,7 +6,7 @@ SURVEY.md section 8(f).
 """
 import torch
 
-from . import config, skin_tc, trunk_tc
+from . import chain_tc, config, skin_tc, trunk_tc
 from .ops import (BoneTransformFn, SkinWarpFn, SEG_DENSE, SEG_BCAST, SEG_PE)
 
 
@@ -78,13 +78,15 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
             and all(sg[0] == SEG_BCAST and sg[3] == nbins for sg in segs[1:])
             and trunk_tc.supported(model, sum(sg[2] for sg in segs[1:])) and embed_xyz.N_freqs == 10 and k == 3):
         env = inputs[2] if len(segs) == 3 else None
-        out = trunk_tc.TrunkTcFn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
+        fn = chain_tc.TrunkChainFn if config.fused else trunk_tc.TrunkTcFn
+        out = fn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
         return out.reshape(Bn, nbins, 4)
     # tensor-core (split-precision) path for the reference's nerf_skin on [PE(xyz) | pose code]
     if (config.precision == "fp16" and not sigma_only and len(segs) == 2 and segs[0][0] == SEG_PE
             and segs[1][0] == SEG_BCAST and segs[1][3] in (nbins, M) and k == 3 and embed_xyz.N_freqs == 10
             and skin_tc.supported(model, segs[1][2])):
-        out = skin_tc.SkinMlpTcFn.apply(pts2, inputs[1], nbins, win, *model.param_list()).reshape(Bn, nbins, 32)
+        fn = chain_tc.SkinChainFn if config.fused else skin_tc.SkinMlpTcFn
+        out = fn.apply(pts2, inputs[1], nbins, win, *model.param_list()).reshape(Bn, nbins, 32)
         return out if _pitched else out[..., :model.out_channels]
     xyz_segs, dir_segs = _split_segments(segs, cx)
     if len(xyz_segs) > 2 or len(dir_segs) > 2:
