@@ -209,6 +209,9 @@ int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const flo
                         const float* const* biases /* rb1, b2, b3, b4, rb5, bfinal, bdir64, brgb64 */, void* A0,
                         void* H /* (5,P,64) */, void* fin, void* dfe, unsigned int* maskbits /* (6,tiles,2,128) */,
                         float* y32 /* (P,32) delta skinning logits */, cudaStream_t stream);
+/* debug: device buffer (>= 16004 int64, zeroed) that subsequent chain launches fill with an event timeline of
+ * block 0's third tile (tools/chain_trace.py); NULL switches tracing off */
+int moda_chain_set_trace(long long* buf);
 int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "moda_chain_trunk_bwd": [c_p] * 6 + [c_ll] + [c_p] * 4,
     "moda_chain_skin_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 7,
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,
+    "moda_chain_set_trace": [c_p],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 

@@ -116,7 +116,7 @@ class TrunkChainFn(torch.autograd.Function):
             H = torch.empty(8, P, 256, device=dev, dtype=HALF)
             fin = torch.empty(P, 256, device=dev, dtype=HALF)
             dfe = torch.empty(P, 128, device=dev, dtype=HALF)
-            bits = torch.empty(8, T, 8, TILE, device=dev, dtype=torch.int32)
+            bits = torch.empty(8, T, 4, TILE, device=dev, dtype=torch.int64)
         else:
             A0 = H = fin = dfe = bits = None
         call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(Ws), ptr(bs), ptr(Wr),
@@ -241,7 +241,7 @@ class SkinChainFn(torch.autograd.Function):
             H = torch.empty(5, P, WD, device=dev, dtype=HALF)
             fin = torch.empty(P, WD, device=dev, dtype=HALF)
             dfe = torch.empty(P, WD, device=dev, dtype=HALF)
-            bits = torch.empty(6, T, 2, TILE, device=dev, dtype=torch.int32)
+            bits = torch.empty(6, T, 2, TILE, device=dev, dtype=torch.int64)
         else:
             A0 = H = fin = dfe = bits = None
         call("moda_chain_skin_fwd", ptr(pts), P, rep, len(win), wa, ptr(wpack), biases, ptr(A0), ptr(H), ptr(fin),

@@ -38,10 +38,10 @@ constexpr int MAX_KC = 6;
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_SAVE_MAPS = 14;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_DUTY = 48;
 constexpr int HEAD_SMEM = 4 * 128 * 4 * 4;    // [warp-of-quarter][row][4] floats
 
-// Epilogue flavour bits.  The complete flag word selects ONE compile-time specialisation of the epilogue
-// (run_step<F>), so the hot loop has no flag tests; flavours in use are listed in dispatch_step().
+// Epilogue flavour bits (tested at run time: every branch is uniform across the CTA).
 enum : int {
   E_RELU = 1,          // max(v, 0)
   E_RANK1 = 2,         // v += gsig[row] * rscale * cvec[col]
@@ -69,6 +69,7 @@ struct Step {
   int mask_slot;
   int release_pe;      // last step of the tile that reads the PE chunks
   int bias_row;        // row of the shared-memory bias table holding `bias`
+  int sd_wait;         // stores_done phases (steps with store-warp work) of this tile that precede this step
   const float* bias;     // (n) or null
   const float* rowbias;  // (M / rep, n) or null
   unsigned char a_chunk[MAX_KC];   // shared-memory chunk feeding K chunk kc
@@ -80,6 +81,12 @@ struct Program {
   int nsteps, num_tiles, rep, nchunks, stages, nbias;
   long long M;
   int wpt[MAX_CHUNKS];   // writes per tile of each chunk (ready-barrier phases per tile)
+  int from_pe[MAX_CHUNKS];  // chunk is written by the PE producer warps (else by the epilogue warps)
+  // work list of the store warp, in the order the chunks get written: wait for write `gen` of `chunk`, then (map >= 0)
+  // TMA-store it to columns [64 col, 64 col + 64) of save[map].  Every write of every hi chunk is listed (the
+  // parity waits need to observe each phase), grouped by step.
+  int nduty, sd_per_tile;
+  struct Duty { unsigned char chunk, gen, step, col; signed char map; } duty[MAX_DUTY];
   // positional-encoding producers
   int pe_chunk;          // chunk of the hi half (-1: program has no PE producers), lo half in pe_chunk + 1
   int pe_lo, pe_save_map, F;
@@ -94,6 +101,7 @@ struct Program {
   // fp32 output
   float* y32; int ld_y32;
   unsigned int* maskbits;
+  long long* trace;      // optional event trace of block 0's third tile (tools/chain_trace.py), null: off
   Step st[MAX_STEPS];
 };
 
@@ -102,7 +110,19 @@ struct Maps {
   CUtensorMap save[MAX_SAVE_MAPS];   // fp16 outputs, box = 64 columns x 128 rows
 };
 
+// progress words of the roles (for the timeout report): [0] weight producer, [1] MMA, [2] epilogue warp 0,
+// [3] PE warp 0, [4] store warp duty, [5] store warp state
+// (they live in the last 32 bytes of the CTA's dynamic shared memory: see launch())
+__device__ __forceinline__ int* dbg_words() {
+  extern __shared__ __align__(1024) uint8_t smem_raw_dbg[];
+  uint32_t total;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(total));
+  return reinterpret_cast<int*>(smem_raw_dbg + total - 32);
+}
+#define s_dbg (dbg_words())
+
 // spin on an mbarrier phase; a wait that lasts seconds means a protocol bug: trap instead of hanging the GPU
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
@@ -119,13 +139,29 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (SLEEP_NS > 0 && !ok) __nanosleep(SLEEP_NS);   // service warps: do not compete with the epilogue for issue slots
     if (!ok && clock64() - t0 > 4000000000LL) {
-      printf("moda chain: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             addr, parity);
+      if ((threadIdx.x & 31) == 0)
+        printf("moda chain: mbarrier wait timed out (block %d thread %d bar %u parity %u) progress: prod %d mma %d epi %d "
+               "pe %d store %d/%d\n", blockIdx.x, threadIdx.x, addr, parity, s_dbg[0], s_dbg[1], s_dbg[2], s_dbg[3],
+               s_dbg[4], s_dbg[5]);
       __trap();
     }
   } while (!ok);
 }
+
+// debug timeline: every traced thread appends records of 4 x int64 (event, a, b, SM clock) to its own region
+// (region = event / 10 < 32, 1000 records each; tr[region] counts them).  Plain stores: the trace costs a few cycles.
+__device__ __forceinline__ void trace_rec(long long* tr, int ev, int a, int b) {
+  const int region = ev / 10;
+  const long long i = tr[region];
+  if (i < 1000) {
+    long long* r = tr + 32 + 4 * (region * 1000 + i);
+    r[0] = ev; r[1] = a; r[2] = b; r[3] = clock64();
+    tr[region] = i + 1;
+  }
+}
+#define MODA_TR(on, ev, a, b) do { if (on) trace_rec(pg.trace, (ev), (a), (b)); } while (0)
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -166,21 +202,21 @@ struct EpiCtx {
   int trow, sw, h;      // row within the tile, its swizzle phase, first sub-block of this warp within a chunk
   int tile, T;
   long long row;
-  bool live, lead;
+  bool live, lane0;
   float rscale, lscale;
+  int tr;               // trace event base (0: off)
 };
 
-// One step's epilogue for this warp, specialised on the flavour F.  Sub-blocks of 16 columns are processed
+// One step's epilogue for this warp (flavour F = st.flags).  Sub-blocks of 16 columns are processed
 // chunk-major with the TMEM load of the next sub-block in flight; after each completed 64-column chunk:
-// proxy fence, barrier among the epilogue warps, then the lead thread hands the chunk to the tensor core
-// (mbarrier) and to TMA (store for the other pass).  NH warps share a TMEM lane quarter: warp h owns the
+// proxy fence, then the warp counts itself in on the chunk's mbarrier (no CTA-wide barrier: warps drift freely).  NH warps share a TMEM lane quarter: warp h owns the
 // sub-blocks {h, h + NH, ..} < 4 of every chunk.
-template <int F, int NH, int ACC_STRIDE, int EPI_THREADS>
-__device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
+template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
+__device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
                                          uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1, float& hs2) {
-  constexpr int NCH16 = ACC_STRIDE / 16;
   constexpr int SPC = 4 / NH;                  // sub-blocks per chunk for this warp
-  constexpr bool MMA = !(F & (E_LOAD16 | E_LOAD32));
+  const int F = (CF >= 0) ? CF : Frt;   // CF >= 0: flavour known at compile time (straight-line hot paths)
+  const bool MMA = !(F & (E_LOAD16 | E_LOAD32));
   const int n = st.n;
   const int nch = n >> 6;
   const int nsub = nch * SPC;
@@ -188,16 +224,26 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
   auto col_of = [&](int i) { return (i / SPC) * 64 + (cx.h + NH * (i % SPC)) * 16; };
   float va[16], vb[16];
   if (MMA) tmem_ld16_issue(t_addr + (uint32_t)col_of(0), va);
+  // ReLU sign bits: 16 per sub-block (column j <-> bit 15 - j, set = pre-activation >= 0); this thread's sub-blocks
+  // of the step are packed four to a 64-bit word (at most two words) -> at most two global accesses per thread
+  // and step instead of one per sub-block
+  constexpr int MW = (ACC_STRIDE / 16 / NH + 3) / 4;
+  static_assert(MW <= 2, "mask words per thread");
+  unsigned long long m0 = 0, m1 = 0;
+  unsigned long long* mp = nullptr;
+  if (F & (E_MASK_IN | E_MASK_OUT)) {
+    mp = reinterpret_cast<unsigned long long*>(pg.maskbits) +
+         ((((size_t)st.mask_slot * cx.T + cx.tile) * NH + cx.h) * MW) * TILE_M + cx.trow;
+    if (F & E_MASK_IN) {
+      m0 = __ldg(mp);
+      if (MW == 2 && nsub > 4) m1 = __ldg(mp + TILE_M);
+    }
+  }
   float rvv = 0.f;
   if (F & E_RANK1) rvv = cx.live ? pg.gsig[cx.row] * cx.rscale : 0.f;
   const float* rb = nullptr;
   if (F & E_ROWBIAS) rb = st.rowbias + (size_t)((cx.live ? cx.row : 0) / pg.rep) * n;
   const uint32_t sb = cx.s_bias + (uint32_t)(st.bias_row * ACC_STRIDE * 4);
-  if ((F & E_SMEM) && nch == 1) {
-    // single-chunk steps rewrite the chunk the previous step saved: its TMA store must have read it
-    if (cx.lead) bulk_wait_read0();
-    named_bar(3, EPI_THREADS);
-  }
   auto sub = [&](const int i, float* __restrict__ v, float* __restrict__ vn) {
     const int cc = col_of(i);                // first of this thread's 16 columns
     const int c64 = cc >> 6;                 // chunk within the result
@@ -228,14 +274,6 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
         tmem_ld_wait();
         if (i + 1 < nsub) tmem_ld16_issue(t_addr + (uint32_t)col_of(i + 1), vn);
       }
-      unsigned int mbits = 0;
-      unsigned short* mp = nullptr;
-      if (F & (E_MASK_IN | E_MASK_OUT)) {
-        // 16 bits per (row, 16 columns); column j <-> bit 15 - j; bit set = pre-activation >= 0
-        mp = reinterpret_cast<unsigned short*>(pg.maskbits) +
-             (((size_t)st.mask_slot * cx.T + cx.tile) * NCH16 + (cc >> 4)) * TILE_M + cx.trow;
-        if (F & E_MASK_IN) mbits = *mp;
-      }
       if (F & E_BIAS) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -259,6 +297,7 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
         }
       }
       if (F & E_MASK_IN) {
+        const unsigned int mbits = (unsigned int)(((MW == 2 && i >= 4) ? m1 : m0) >> (16 * (i & 3)));
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = (mbits & (0x8000u >> j)) ? v[j] : 0.f;
       }
@@ -270,7 +309,8 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
           n0 = __funnelshift_l(__float_as_uint(v[j]), n0, 1);
           n1 = __funnelshift_l(__float_as_uint(v[8 + j]), n1, 1);
         }
-        *mp = (unsigned short)(~((n0 << 8) | n1));
+        const unsigned long long w16 = (unsigned long long)((~((n0 << 8) | n1)) & 0xFFFFu) << (16 * (i & 3));
+        if (MW == 2 && i >= 4) m1 |= w16; else m0 |= w16;
       }
       if (F & E_RELU) {
 #pragma unroll
@@ -333,16 +373,12 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
       }
     }
     if ((F & E_SMEM) && last_of_chunk) {
-      fence_async_smem();   // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
-      // every earlier TMA store of the lead thread has read its source before anyone passes this barrier:
-      // together with the chunk-major order this protects the in-place rewrite of multi-chunk results
-      if (cx.lead) bulk_wait_read0();
-      named_bar(3, EPI_THREADS);
-      if (cx.lead) {
-        if (st.save_map >= 0) {
-          tma_store_2d_u32(&maps.save[st.save_map], cx.sA + (uint32_t)(chunk * CHUNK_BYTES), c64 * 64, cx.tile * TILE_M);
-          bulk_commit();
-        }
+      // this warp's part of the chunk is complete: make the generic-proxy writes visible to the async proxy
+      // (tensor core, TMA) and count the warp in; the MMA thread and the store warp wait on the chunk barrier
+      fence_async_smem();
+      __syncwarp();
+      if (cx.lane0) {
+        MODA_TR(cx.tr, cx.tr + 1, c64, 0);
         mbar_arrive(&ready[chunk]);
         if (F & E_LO) mbar_arrive(&ready[st.out_lo_chunk + c64]);
       }
@@ -353,13 +389,32 @@ __device__ __forceinline__ void run_step(const Program& pg, const Maps& maps, co
     sub(i2, va, vb);
     if (i2 + 1 < nsub) sub(i2 + 1, vb, va);
   }
+  if (F & E_MASK_OUT) {
+    *mp = m0;
+    if (MW == 2 && nsub > 4) mp[TILE_M] = m1;
+  }
+}
+
+// hot flavours inline (straight-line code inside the kernel's register allocation) ...
+template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
+__device__ __forceinline__ void run_step(const int Frt, const Program& pg, const Maps& maps, const Step& st,
+                                         const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1,
+                                         float& hs2) {
+  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+}
+// ... the run-time-flag version (a few steps per tile) out of line, so that it does not weigh on them
+template <int NH, int ACC_STRIDE, int EPI_THREADS>
+__device__ __noinline__ void run_step_generic(const int Frt, const Program& pg, const Maps& maps, const Step& st,
+                                              const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0,
+                                              float& hs1, float& hs2) {
+  run_step_body<-1, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
 }
 
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
 template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
-__global__ void __launch_bounds__((2 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
+__global__ void __launch_bounds__((3 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
 chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;       // TMEM columns per accumulator
   constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -368,6 +423,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   constexpr int NH = EPI_WARPS / 4;                              // warps sharing one TMEM lane quarter
   constexpr int EPI_THREADS = EPI_WARPS * 32;
   constexpr int PE_THREADS = PE_WARPS * 32;
+  (void)PE_THREADS;
   constexpr int PE_ROWS = TILE_M / PE_THREADS;                   // rows per producer thread
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -383,14 +439,16 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   uint64_t* acc_full = ready + MAX_CHUNKS;       // [2]
   uint64_t* acc_free = acc_full + 2;             // [2]
   uint64_t* pe_free = acc_free + 2;              // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pe_free + 1);
+  uint64_t* stores_done = pe_free + 1;           // [1] one phase per step: its TMA stores have read their chunks
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = pg.num_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[i], 1);
+    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[i], pg.from_pe[i] ? PE_WARPS : EPI_WARPS);
+    mbar_init(stores_done, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS); }
     mbar_init(pe_free, 1);
     fence_barrier_init();
@@ -417,8 +475,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         for (int s = 0; s < pg.nsteps; ++s) {
           const Step& st = pg.st[s];
           const int boxes = st.n > BOX_ROWS ? st.n / BOX_ROWS : 1;
+          s_dbg[0] = s;
           for (int kc = 0; kc < st.kc; ++kc) {
-            wait_or_trap(&w_empty[stage], phase ^ 1);
+            wait_or_trap<0>(&w_empty[stage], phase ^ 1);
             mbar_expect_tx(&w_full[stage], (uint32_t)(boxes * BOX_BYTES));
             for (int bx = 0; bx < boxes; ++bx)
               tma_load_2d(sB + (size_t)stage * STAGE_BYTES + bx * BOX_BYTES, &maps.w, &w_full[stage],
@@ -432,23 +491,37 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     // ================================================================== MMA issuer
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, mma_ctr = 0;
+      uint32_t phase = 0, mma_ctr = 0, gstep = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
-        for (int s = 0; s < pg.nsteps; ++s) {
+        for (int s = 0; s < pg.nsteps; ++s, ++gstep) {
           const Step& st = pg.st[s];
-          if (st.kc == 0) continue;
+          s_dbg[1] = (int)gstep;
+          // stores_done completes one phase per step that has store-warp work; `sd_need` of them precede this
+          // step.  It grows by at most one per step and is waited for at every step, so no phase is skipped
+          // (parity waits must observe each one), and the store warp cannot run ahead: it only arrives after it
+          // has seen chunks written by an epilogue that was itself released by this thread.
+          const uint32_t sd_need = (uint32_t)it * (uint32_t)pg.sd_per_tile + (uint32_t)st.sd_wait;
+          if (st.kc == 0) {
+            if (sd_need > 0) wait_or_trap(stores_done, (sd_need - 1) & 1);
+            continue;
+          }
           const int b = mma_ctr & 1;
+          const bool tr = pg.trace && blockIdx.x == 0 && it == 2;
+          MODA_TR(tr, 0, s, 0);
           wait_or_trap(&acc_free[b], ((mma_ctr >> 1) & 1) ^ 1);   // epilogue of two MMA steps ago has drained it
           tc_fence_after();
+          MODA_TR(tr, 1, s, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
           const uint32_t idesc = make_idesc(TILE_M, st.n, 0, 0);
           for (int kc = 0; kc < st.kc; ++kc) {
             const int c = st.a_chunk[kc];
             const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + st.a_gen[kc];
             wait_or_trap(&ready[c], gen & 1);
+            MODA_TR(tr, 2, s, kc);
             wait_or_trap(&w_full[stage], phase);
             tc_fence_after();
+            MODA_TR(tr, 3, s, kc);
             const uint32_t a_addr = smem_u32(sA + (size_t)c * CHUNK_BYTES);
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * STAGE_BYTES);
 #pragma unroll
@@ -460,8 +533,12 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             umma_commit(&w_empty[stage]);
             if (++stage == pg.stages) { stage = 0; phase ^= 1; }
           }
+          // In-place rewrite guarantee: the epilogue of THIS step overwrites chunks that TMA stores of earlier steps
+          // read; it starts on acc_full, so that is only signalled once those stores have read their source.
+          if (sd_need > 0) wait_or_trap(stores_done, (sd_need - 1) & 1);
           umma_commit(&acc_full[b]);
           if (st.release_pe) umma_commit(pe_free);
+          MODA_TR(tr, 4, s, 0);
           ++mma_ctr;
         }
       }
@@ -480,60 +557,44 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     cx.h = ew >> 2;
     cx.trow = q * 32 + lane;
     cx.sw = cx.trow & 7;
-    cx.lead = (ew == 0) && lane == 0;
+    cx.lane0 = lane == 0;
     cx.rscale = pg.rscale ? *pg.rscale : 1.0f;
     cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
     cx.T = T;
     const int h = cx.h, trow = cx.trow;
     uint32_t mma_ctr = 0;
     float sig_keep = 0.f;
-    for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
       cx.tile = tile;
+      cx.tr = (pg.trace && blockIdx.x == 0 && it == 2 && lane == 0) ? 40 + 10 * ew : 0;   // regions 4..: one per warp
       cx.row = (long long)tile * TILE_M + trow;
       cx.live = cx.row < pg.M;
       for (int s = 0; s < pg.nsteps; ++s) {
         const Step& st = pg.st[s];
         const int flags = st.flags;
+        if (ew == 0 && lane == 0) s_dbg[2] = it * 100 + s;
         int b = 0;
         if (st.kc > 0) {
           b = mma_ctr & 1;
           wait_or_trap(&acc_full[b], (mma_ctr >> 1) & 1);
           tc_fence_after();
         }
+        MODA_TR(cx.tr, cx.tr, s, 0);
         float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
         const uint32_t acc_col = (uint32_t)(b * ACC_STRIDE);
-#define MODA_STEP(FL) case (FL): run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2); break
-        if (BOX_ROWS == 128) {
-          switch (flags) {
-            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM);                  // hidden layer (training)
-            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_HEAD_SIGMA);   // last hidden layer + sigma head
-            MODA_STEP(E_BIAS | E_RELU | E_SMEM);                               // hidden layer (inference)
-            MODA_STEP(E_BIAS | E_RELU | E_SMEM | E_HEAD_SIGMA);
-            MODA_STEP(E_BIAS | E_SMEM);                                        // xyz_encoding_final
-            MODA_STEP(E_ROWBIAS | E_RELU | E_SMEM | E_HEAD_RGB);               // dir_encoding + rgb head
-            MODA_STEP(E_LOAD16 | E_SMEM);                                      // adjoint: d_dfe tile
-            MODA_STEP(E_SMEM);                                                 // adjoint: d_fin, dPE partial
-            MODA_STEP(E_RANK1 | E_MASK_IN | E_SMEM);                           // adjoint: dY[7]
-            MODA_STEP(E_MASK_IN | E_SMEM);                                     // adjoint: dY[l]
-            MODA_STEP(E_ADD_SX | E_SMEM);                                      // adjoint: dPE
-            default: __trap();
-          }
-        } else {
-          switch (flags) {
-            MODA_STEP(E_ROWBIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);        // layers 1 / 5 (pose code as row bias)
-            MODA_STEP(E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);           // hidden layers, dir layer
-            MODA_STEP(E_ROWBIAS | E_RELU | E_SMEM | E_LO);                     // same, inference
-            MODA_STEP(E_BIAS | E_RELU | E_SMEM | E_LO);
-            MODA_STEP(E_BIAS | E_SMEM | E_LO);                                 // xyz_encoding_final
-            MODA_STEP(E_BIAS | E_OUT_F32);                                     // delta-logit output
-            MODA_STEP(E_LOAD32 | E_SMEM);                                      // adjoint: scaled output gradient
-            MODA_STEP(E_MASK_IN | E_SMEM);
-            MODA_STEP(E_SMEM);
-            MODA_STEP(E_ADD_SX | E_SMEM);
-            default: __trap();
-          }
-        }
-#undef MODA_STEP
+        // the flavours that make up almost all of the work run as straight-line specialisations (a taken branch
+        // costs an instruction-fetch bubble: ~30 of them per sub-block in the generic path); the rest share the
+        // run-time-flag version
+        constexpr int HOT_FWD = (BOX_ROWS == 128) ? (E_BIAS | E_RELU | E_MASK_OUT | E_SMEM)
+                                                  : (E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);
+        constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
+        if (flags == HOT_FWD)
+          run_step<HOT_FWD, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        else if (flags == HOT_BWD)
+          run_step<HOT_BWD, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        else
+          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
         if (st.kc > 0) {
           tc_fence_before();
           __syncwarp();
@@ -571,30 +632,38 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         }
       }
     }
-    if (cx.lead) bulk_wait_all0();
-  } else {
+  } else if (warp < 2 + EPI_WARPS + PE_WARPS) {
     // ================================================================== positional-encoding producers
     if (pg.pe_chunk >= 0) {
       const int pw = warp - 2 - EPI_WARPS;
       const bool lead = (pw == 0) && lane == 0;
+      (void)lead;
       int it = 0;
       const uint32_t pe_base = smem_u32(sA) + (uint32_t)(pg.pe_chunk * CHUNK_BYTES);
       for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
-        // channels: [x(3) | w_k sin(2^k x)(3) | w_k cos(2^k x)(3)]_k, zero padded to 64 (nnutils/nerf.py:35-75)
-        if (BOX_ROWS == 128) {
-          // one row per thread, fp16 only: the row is computed into 32 packed registers BEFORE waiting for the
-          // chunk, i.e. while the previous tile is still in flight; afterwards only 8 stores remain
-          const int trow = pw * 32 + lane;
+        // channels: [x(3) | w_k sin(2^k x)(3) | w_k cos(2^k x)(3)]_k, zero padded to 64 (nnutils/nerf.py:35-75);
+        // values go straight to the swizzled chunk rows as they are produced (PE_ROWS rows per thread)
+        const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && lead;
+        MODA_TR(tr, 30, 0, 0);
+        if (lead) s_dbg[3] = it;
+        wait_or_trap<0>(pe_free, (it & 1) ^ 1);   // the previous tile's last reader of the PE chunk(s) has completed
+        MODA_TR(tr, 31, 0, 0);
+#pragma unroll 1
+        for (int rr = 0; rr < PE_ROWS; ++rr) {
+          const int trow = (pw * 32 + lane) * PE_ROWS + rr;
           const int sw = trow & 7;
           const long long row = (long long)tile * TILE_M + trow;
           float x[3] = {0.f, 0.f, 0.f};
           if (row < pg.M) { x[0] = pg.xyz[row * 3]; x[1] = pg.xyz[row * 3 + 1]; x[2] = pg.xyz[row * 3 + 2]; }
-          uint32_t hreg[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hreg[j] = 0u;
+          const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
           auto put = [&](const int idx, float v) {
-            const uint32_t bits = (uint32_t)__half_as_ushort(__float2half_rn(v));
-            hreg[idx >> 1] |= (idx & 1) ? (bits << 16) : bits;
+            const __half hv = __float2half_rn(v);
+            const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + (idx & 7) * 2);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(hv)) : "memory");
+            if (BOX_ROWS == 64) {   // split precision: low half into the next chunk
+              const __half lv = __float2half_rn(v - __half2float(hv));
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + CHUNK_BYTES), "h"(__half_as_ushort(lv)) : "memory");
+            }
           };
           put(0, x[0]); put(1, x[1]); put(2, x[2]);
 #pragma unroll
@@ -604,69 +673,66 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               float sn, cs;
-              sincosf(x[c] * f, &sn, &cs);
+              if (BOX_ROWS == 128) {
+                // fp16-only consumer (2^-11 relative rounding): SFU sin/cos after a two-term Cody-Waite reduction
+                // to [-pi, pi] (absolute error ~1e-6 for |2^k x| <= 160 rad)
+                const float r = x[c] * f;
+                const float kk = rintf(r * 0.15915494309189535f);
+                float r2 = fmaf(kk, -6.2831854820251465f, r);
+                r2 = fmaf(kk, 1.7484555e-7f, r2);
+                sn = __sinf(r2);
+                cs = __cosf(r2);
+              } else {
+                sincosf(x[c] * f, &sn, &cs);   // split precision needs the full-accuracy path
+              }
               put(3 + 6 * k + c, w * sn);
               put(3 + 6 * k + 3 + c, w * cs);
             }
           }
-          wait_or_trap(pe_free, (it & 1) ^ 1);   // the previous tile's last reader of the PE chunk has completed
-          if (lead) bulk_wait_read0();
-          named_bar(5, PE_THREADS);
-          const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(hrow + ((j ^ sw) << 4), hreg[4 * j], hreg[4 * j + 1], hreg[4 * j + 2], hreg[4 * j + 3]);
-        } else {
-          // split precision (hi and lo chunks), PE_ROWS rows per thread, two CTAs per SM hide the latency:
-          // values go straight to shared memory as they are produced
-          wait_or_trap(pe_free, (it & 1) ^ 1);
-          if (lead) bulk_wait_read0();
-          named_bar(5, PE_THREADS);
-#pragma unroll 1
-          for (int rr = 0; rr < PE_ROWS; ++rr) {
-            const int trow = (pw * 32 + lane) * PE_ROWS + rr;
-            const int sw = trow & 7;
-            const long long row = (long long)tile * TILE_M + trow;
-            float x[3] = {0.f, 0.f, 0.f};
-            if (row < pg.M) { x[0] = pg.xyz[row * 3]; x[1] = pg.xyz[row * 3 + 1]; x[2] = pg.xyz[row * 3 + 2]; }
-            const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
-            auto put = [&](const int idx, float v) {
-              const __half hv = __float2half_rn(v);
-              const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + (idx & 7) * 2);
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(hv)) : "memory");
-              if (pg.pe_lo) {
-                const __half lv = __float2half_rn(v - __half2float(hv));
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + CHUNK_BYTES), "h"(__half_as_ushort(lv)) : "memory");
-              }
-            };
-            put(0, x[0]); put(1, x[1]); put(2, x[2]);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) {
-              const float f = (float)(1 << k);
-              const float w = (k < pg.F) ? pg.win[k] : 0.f;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                float sn, cs;
-                sincosf(x[c] * f, &sn, &cs);
-                put(3 + 6 * k + c, w * sn);
-                put(3 + 6 * k + 3 + c, w * cs);
-              }
-            }
-            put(63, 0.f);
-          }
+          put(63, 0.f);
         }
         fence_async_smem();
-        named_bar(5, PE_THREADS);
-        if (lead) {
-          if (pg.pe_save_map >= 0) {
-            tma_store_2d_u32(&maps.save[pg.pe_save_map], pe_base, 0, tile * TILE_M);
-            bulk_commit();
-          }
+        __syncwarp();
+        if (lane == 0) {
           mbar_arrive(&ready[pg.pe_chunk]);
           if (pg.pe_lo) mbar_arrive(&ready[pg.pe_chunk + 1]);
         }
       }
-      if (lead) bulk_wait_all0();
+    }
+  } else {
+    // ================================================================== store warp
+    // Saves the chunks the other pass needs with TMA, in the order they get written.  The chunk barriers are
+    // shared with the MMA thread (multiple waiters); the PE chunk's save is safe against the next tile's rewrite
+    // because pe_free is committed steps later, after the MMA thread has seen this step's stores_done.
+    if (lane == 0) {
+      const uint32_t sA_u32 = smem_u32(sA);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
+        int d = 0;
+        for (int s = 0; s < pg.nsteps; ++s) {
+          bool any = false, work = false;
+          while (d < pg.nduty && pg.duty[d].step == s) {
+            work = true;
+            const int c = pg.duty[d].chunk;
+            const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + pg.duty[d].gen;
+            s_dbg[4] = it * 1000 + s * 10 + (d % 10); s_dbg[5] = 0;
+            wait_or_trap<0>(&ready[c], gen & 1);
+            s_dbg[5] = 1;
+            if (pg.duty[d].map >= 0) {
+              tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)(c * CHUNK_BYTES), (int)pg.duty[d].col * 64,
+                               tile * TILE_M);
+              bulk_commit();
+              any = true;
+            }
+            ++d;
+          }
+          s_dbg[5] = 2;
+          if (any) bulk_wait_read0();
+          if (work) mbar_arrive(stores_done);
+          s_dbg[5] = 3;
+        }
+      }
+      bulk_wait_all0();
     }
   }
   tc_fence_before();
@@ -685,6 +751,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 
 using namespace moda;
 using namespace moda::chain;
+
+static long long* g_trace = nullptr;
+// debug: device buffer of >= 4 + 4 * 4000 int64 (zeroed by the caller) that the next chain launches fill with a timeline
+extern "C" int moda_chain_set_trace(long long* buf) { g_trace = buf; return 0; }
 
 namespace {
 
@@ -724,19 +794,42 @@ struct Builder {
     ++st.kc;
   }
   // the step's epilogue writes `count` chunks starting at `first` (and optionally their lo halves)
+  void add_duty(int chunk, int g, int step, int col, int map) {
+    if (pg.nduty >= MAX_DUTY) { set_error("chain: store work list overflow"); err = -1; return; }
+    Program::Duty& d = pg.duty[pg.nduty++];
+    d.chunk = (unsigned char)chunk; d.gen = (unsigned char)g; d.step = (unsigned char)step;
+    d.col = (unsigned char)col; d.map = (signed char)map;
+  }
+  // call after st.save_map is set: the step's epilogue writes `count` chunks starting at `first` (and optionally
+  // their lo halves)
   void out(Step& st, int first, int count, int lo_first = -1) {
     st.out_chunk = first;
     st.out_lo_chunk = lo_first;
     st.flags |= E_SMEM | (lo_first >= 0 ? E_LO : 0);
-    for (int i = 0; i < count; ++i) { ++gen[first + i]; if (lo_first >= 0) ++gen[lo_first + i]; }
+    const int step = (int)(&st - pg.st);
+    for (int i = 0; i < count; ++i) {
+      add_duty(first + i, gen[first + i], step, i, st.save_map);
+      ++gen[first + i];
+      if (lo_first >= 0) ++gen[lo_first + i];
+    }
   }
   void pe(int chunk, bool lo, int save_map) {
     pg.pe_chunk = chunk; pg.pe_lo = lo ? 1 : 0; pg.pe_save_map = save_map;
+    pg.from_pe[chunk] = 1;
+    add_duty(chunk, gen[chunk], 0, 0, save_map);
     ++gen[chunk];
-    if (lo) ++gen[chunk + 1];
+    if (lo) { pg.from_pe[chunk + 1] = 1; ++gen[chunk + 1]; }
   }
   void finish() {
     for (int i = 0; i < MAX_CHUNKS; ++i) pg.wpt[i] = gen[i];
+    int phases = 0, d = 0;
+    for (int s = 0; s < pg.nsteps; ++s) {
+      pg.st[s].sd_wait = phases;
+      bool work = false;
+      while (d < pg.nduty && pg.duty[d].step == s) { work = true; ++d; }
+      if (work) ++phases;
+    }
+    pg.sd_per_tile = phases;
     pg.nbias = 0;
     for (int s = 0; s < pg.nsteps; ++s) {
       Step& st = pg.st[s];
@@ -750,12 +843,13 @@ template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
 int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
   if (b.err) return b.err;
   b.finish();
+  b.pg.trace = g_trace;
   if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, BOX_ROWS)) return e;
   constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128;
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;
-  constexpr int THREADS = (2 + EPI_WARPS + PE_WARPS) * 32;
+  constexpr int THREADS = (3 + EPI_WARPS + PE_WARPS) * 32;
   const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + HEAD_SMEM +
-                      (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512;
+                      (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512 + 32;
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
   MODA_REQUIRE(smem <= cap, "chain: needs %zu B of shared memory (limit %zu)", smem, cap);
   auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS>;
@@ -797,7 +891,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
   const int PE = 4;
-  const int order[4] = {0, 2, 1, 3};   // chunks 0 and 2 of a 256-wide result are written first
+  const int order[4] = {0, 1, 2, 3};   // the epilogue finishes the chunks of a result in this order
   b.pe(PE, false, b.save(A0, P, 64));
   int col = 0;
   for (int l = 0; l < 8; ++l) {
@@ -829,7 +923,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  return launch<128, 16, 4, 1>(b, wpack, 256, col * 64, stream);
+  return launch<128, 8, 1, 1>(b, wpack, 256, col * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -851,7 +945,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
   pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
   pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
   const int SX = 4;
-  const int order[4] = {0, 2, 1, 3};
+  const int order[4] = {0, 1, 2, 3};
   auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 256 * 2; };
   { Step& st = b.add(128, E_LOAD16); b.out(st, 0, 2); }
   {
@@ -887,7 +981,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  return launch<128, 16, 4, 1>(b, wpackT, 256, col * 64, stream);
+  return launch<128, 8, 1, 1>(b, wpackT, 256, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin
@@ -925,7 +1019,7 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
   { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, 14);
     st.save_map = b.save(dfe, P, 64); b.out(st, AH, 1, AL); }
   { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, 16); }
-  return launch<64, 8, 2, 2>(b, wpack, 64, 18 * 64, stream);
+  return launch<64, 4, 1, 2>(b, wpack, 64, 18 * 64, stream);
 }
 
 // Adjoint chain of nerf_skin on plain fp16 operands.  wpackT: fp16 (64, 9*64), rows = input channel, cols = output:
@@ -957,5 +1051,5 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
     b.out(st, A, 1);
   }
   { Step& st = b.add(64, E_ADD_SX); b.k(st, A, 8); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
-  return launch<64, 8, 2, 2>(b, wpackT, 64, 9 * 64, stream);
+  return launch<64, 4, 1, 2>(b, wpackT, 64, 9 * 64, stream);
 }
