@@ -183,7 +183,8 @@ def run_ours(args):
         summ = _lib.profile_summary()
         _lib.PROFILE = None
         peaks, src = _peaks()
-        lin_ms = sum(ms for k, (n, ms) in summ.items() if k.startswith("moda_linear") or k.startswith("moda_tc")) / 2
+        lin_ms = sum(ms for k, (n, ms) in summ.items()
+                     if k.startswith(("moda_linear", "moda_tc", "moda_chain"))) / 2
         tot_ms = sum(ms for _, ms in summ.values()) / 2
         achieved = FLOP_PER_RAY_HOISTED * R / (lin_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])

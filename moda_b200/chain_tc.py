@@ -31,6 +31,12 @@ def _wgrad(dY, N, X, K, M, dW, col0, n_valid, k_valid, oscale, dbias=None):
          n_valid, k_valid, ptr(oscale), ptr(dbias), stream())
 
 
+def _al16(t):
+    """The chain kernels read head vectors with 128-bit loads: a parameter that is a view at an odd offset of some
+    larger buffer is copied (a few hundred floats) instead of being refused."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def _one(v):
     return (ctypes.c_int * 1)(v)
 
@@ -119,7 +125,8 @@ class TrunkChainFn(torch.autograd.Function):
             bits = torch.empty(8, T, 4, TILE, device=dev, dtype=torch.int64)
         else:
             A0 = H = fin = dfe = bits = None
-        call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(Ws), ptr(bs), ptr(Wr),
+        call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(_al16(Ws)), ptr(bs),
+             ptr(_al16(Wr)),
              ptr(br), ptr(A0), ptr(H), ptr(fin), ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(raw),
              stream())
         if need_bw:
@@ -158,7 +165,7 @@ class TrunkChainFn(torch.autograd.Function):
         d_fin = torch.empty(P, 256, device=dev, dtype=HALF)
         dY = torch.empty(8, P, 256, device=dev, dtype=HALF)
         d_pe = torch.empty(P, 64, device=dev, dtype=HALF)
-        call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(Ws.reshape(-1)), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
+        call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(_al16(Ws.reshape(-1))), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
              ptr(d_fin), ptr(dY), ptr(d_pe), stream())
         # weight gradients (bias gradients ride along as column sums of the dY operand)
         _wgrad(d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)

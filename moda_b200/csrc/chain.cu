@@ -864,6 +864,9 @@ int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t str
   return check_launch("chain");
 }
 
+// the epilogue reads these operands with 128-bit loads
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 void fill_win(Program& pg, int F, const float* win) {
   pg.F = F;
   for (int i = 0; i < 10; ++i) pg.win[i] = (win && i < F) ? win[i] : 1.0f;
@@ -885,6 +888,8 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && rowbias && ws && bs && Wr && br && raw && rep > 0 && F >= 0 && F <= 10,
                "chain_trunk_fwd: bad arguments");
+  MODA_REQUIRE(al16(rowbias) && al16(ws) && al16(Wr) && al16(raw) && al16(wpack),
+               "chain_trunk_fwd: rowbias, ws, Wr, raw and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = 4;
@@ -939,6 +944,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
                                     void* dY, void* d_pe, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && d_fin && dY && d_pe, "chain_trunk_bwd: null pointer");
+  MODA_REQUIRE(al16(d_dfe) && al16(ws) && al16(wpackT), "chain_trunk_bwd: d_dfe, ws and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
@@ -997,6 +1003,8 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
                                    unsigned int* maskbits, float* y32, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && y32 && rep > 0 && F >= 0 && F <= 10, "chain_skin_fwd: bad arguments");
+  MODA_REQUIRE(al16(biases[0]) && al16(biases[4]) && al16(y32) && al16(wpack),
+               "chain_skin_fwd: row biases, y32 and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 4; pg.stages = 4;
@@ -1032,6 +1040,7 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
                                    void* dY, void* d_pe, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(gout && wpackT && maskbits && G && d_dfe && d_fin && dY && d_pe, "chain_skin_bwd: null pointer");
+  MODA_REQUIRE(al16(gout) && al16(wpackT), "chain_skin_bwd: gout and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 2; pg.stages = 8;

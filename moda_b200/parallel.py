@@ -15,19 +15,26 @@ class FlatParams:
     ``self.grad``; autograd accumulates into the views in place, so ``allreduce()`` is a single collective
     and an optimizer can be built over the single tensor ``self.flat`` (its .grad is ``self.grad``)."""
 
+    ALIGN = 64  # fp32 elements
+
     def __init__(self, tensors):
         self.tensors = [t for t in tensors]
-        n = sum(t.numel() for t in self.tensors)
+        # every tensor starts on a 256-byte boundary: the kernels read weights, biases and head vectors with
+        # 128-bit loads and TMA, exactly as they may for separately allocated nn.Parameters (the padding stays
+        # zero in both buffers, so it is inert under the all-reduce and the optimizer)
+        offs, n = [], 0
+        for t in self.tensors:
+            offs.append(n)
+            n += (t.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         dev = self.tensors[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
-        for t in self.tensors:
+        for t, off in zip(self.tensors, offs):
             k = t.numel()
             self.flat[off:off + k].copy_(t.detach().reshape(-1))
             t.data = self.flat[off:off + k].view(t.shape)
             t.grad = self.grad[off:off + k].view(t.shape)
-            off += k
+        self.offsets = offs
         self.flat.requires_grad_(True)
         self.flat.grad = self.grad
         self.numel = n

@@ -386,3 +386,76 @@ def test_split_precision_skin_mlp_matches_fp32_simt():
         assert set(a[3]) == set(b[3])
         worst = max((nrel(b[3][k], a[3][k]), k) for k in a[3])
         assert worst[0] < 3e-3, worst
+
+
+def test_fused_chains_match_layer_by_layer_kernels():
+    """csrc/chain.cu (one persistent kernel per MLP pass) against csrc/tc_gemm.cu (one kernel per layer): same
+    precision policy, so values and every gradient agree far below the fp16-vs-fp32 gap.  Sizes cover a partial
+    last tile (R*S not a multiple of 128 x SMs) and the single-row pose code of the forward warp."""
+    from moda_b200 import config, geom_utils as G, synth, models as MM
+    config.set_precision("fp16")
+    prob = synth.make_problem(8, seed=0)
+    models, emb, _ = MM.build_models(prob, DEV)
+    nrel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
+
+    def run(model, kind, R, S, fused, single):
+        gen = torch.Generator().manual_seed(7)
+        pts = (torch.rand(R, S, 3, generator=gen) * 0.6 - 0.3).to(DEV).requires_grad_(True)
+        model.zero_grad()
+        config.fused = fused
+        if kind == "trunk":
+            de = torch.randn(R, 27, generator=gen).to(DEV).requires_grad_(True)
+            env = (0.1 * torch.randn(R, 64, generator=gen)).to(DEV).requires_grad_(True)
+            gout = torch.randn(R, S, 4, generator=gen).to(DEV) * 1e-3
+            out = G.evaluate_mlp(model, pts, embed_xyz=emb["xyz"], dir_embedded=de, code=env)
+            (out * gout).sum().backward()
+            grads = {"pts": pts.grad, "dir": de.grad, "env": env.grad}
+        else:
+            code = (0.1 * torch.randn(1 if single else R, 128, generator=gen)).to(DEV).requires_grad_(True)
+            gout = torch.randn(R, S, 25, generator=gen).to(DEV) * 1e-3
+            out = G.evaluate_mlp(model, pts, embed_xyz=emb["xyz"], code=code)
+            (out * gout).sum().backward()
+            grads = {"pts": pts.grad, "code": code.grad}
+        grads.update({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+        return out.detach().clone(), grads
+
+    try:
+        for kind, model in (("trunk", models["coarse"]), ("skin", models["nerf_skin"])):
+            for R, S, single in ((3, 128, False), (301, 128, False), (37, 64, True)):
+                if kind == "trunk" and single:
+                    continue
+                a = run(model, kind, R, S, False, single)
+                b = run(model, kind, R, S, True, single)
+                assert max_abs(b[0], a[0]) < (2e-3 if kind == "trunk" else 2e-5), (kind, R, max_abs(b[0], a[0]))
+                assert set(a[1]) == set(b[1])
+                worst = max((nrel(b[1][k], a[1][k]), k) for k in a[1])
+                assert worst[0] < 2e-2, (kind, R, worst)
+    finally:
+        config.fused = True
+
+
+def test_training_step_on_flat_parameter_buffer():
+    """bench.py / the data-parallel path re-home every parameter into one flat buffer (moda_b200.parallel.FlatParams):
+    the kernels must accept those views (128-bit loads need the 16-byte alignment FlatParams guarantees) and give
+    exactly the result they give on separately allocated parameters."""
+    from moda_b200 import synth, models as MM, config
+    from moda_b200.parallel import FlatParams
+    from moda_b200.rendering import render_rays
+    config.set_precision("fp16")
+    N, S = 160, 128
+    prob = synth.make_problem(N, seed=2)
+    out = []
+    for flat in (False, True):
+        models, emb, rays = MM.build_models(prob, DEV)
+        fp = FlatParams(MM.parameters_of(models)) if flat else None
+        res = render_rays(models, emb, rays, N_samples=S, perturb=0, noise_std=0, opts=synth.default_opts(), img_size=512)
+        loss = ((res["img_coarse"] - 0.3) ** 2).mean() + ((res["sil_coarse"] - 0.5) ** 2).mean() + res["frame_cyc_dis"].mean()
+        loss.backward()
+        out.append((res["img_coarse"].detach().clone(), [p.grad.clone() for p in MM.parameters_of(models) if p.grad is not None]))
+        if flat:
+            assert all(p.data_ptr() % 16 == 0 for p in MM.parameters_of(models))
+            assert float(fp.grad.abs().sum()) > 0
+    assert torch.equal(out[0][0], out[1][0])
+    assert len(out[0][1]) == len(out[1][1])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert rel_err(b, a) < 1e-5   # atomics in the per-bone reductions reorder sums run to run

@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
     fp.zero_grad()
     _toy_loss([w, b], mine, 10).backward()
     fp.allreduce()
-    ret[rank] = fp.grad.clone()
+    ret[rank] = torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)]).clone()
     dist.destroy_process_group()
 
 
@@ -67,8 +67,11 @@ def test_flat_params_views():
     fp = FlatParams([a, b])
     assert torch.equal(a.detach(), a0) and torch.equal(b.detach(), b0)
     (a.sum() * 2 + (b ** 2).sum()).backward()
+    o = fp.offsets
+    assert o[0] == 0 and o[1] % FlatParams.ALIGN == 0
     assert torch.allclose(fp.grad[:6], torch.full((6,), 2.0))
-    assert torch.allclose(fp.grad[6:], 2 * b0)
+    assert torch.allclose(fp.grad[o[1]:o[1] + 5], 2 * b0)
+    assert float(fp.grad[6:o[1]].abs().sum()) == 0  # the alignment padding stays inert
     with torch.no_grad():
         fp.flat.add_(1.0)
     assert torch.allclose(a.detach(), a0 + 1)
