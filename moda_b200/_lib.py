@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmoda_b200.so")
+LIB_PATH = os.environ.get("MODA_B200_LIB") or os.path.join(_HERE, "libmoda_b200.so")  # override: kernel experiments
 
 _lib = None
 

@@ -39,7 +39,7 @@ constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_SAVE_MAPS = 14;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_DUTY = 48;
-constexpr int HEAD_SMEM = 4 * 128 * 4 * 4;    // [warp-of-quarter][row][4] floats
+constexpr int head_smem(int nh) { return nh * 128 * 4 * 4; }   // [warp-of-quarter][row][4] floats
 
 // Epilogue flavour bits (tested at run time: every branch is uniform across the CTA).
 enum : int {
@@ -70,6 +70,7 @@ struct Step {
   int release_pe;      // last step of the tile that reads the PE chunks
   int bias_row;        // row of the shared-memory bias table holding `bias`
   int sd_wait;         // stores_done phases (steps with store-warp work) of this tile that precede this step
+  int tile_bias;       // rowbias is constant over a tile (rep % 128 == 0): staged into bias_row at every tile start
   const float* bias;     // (n) or null
   const float* rowbias;  // (M / rep, n) or null
   unsigned char a_chunk[MAX_KC];   // shared-memory chunk feeding K chunk kc
@@ -79,6 +80,11 @@ struct Step {
 
 struct Program {
   int nsteps, num_tiles, rep, nchunks, stages, nbias;
+  int has_tile_bias;     // some step has tile_bias set
+  // head vectors staged behind the biases in shared memory: vec0 (ws, or cvec of the adjoint) from row vec_row,
+  // vec1 (Wr, (3, n)) from row vec_row1; -1: none
+  int vec_row, vec_row1, vec_len0, vec_len1;
+  const float* vec0; const float* vec1;
   long long M;
   int wpt[MAX_CHUNKS];   // writes per tile of each chunk (ready-barrier phases per tile)
   int from_pe[MAX_CHUNKS];  // chunk is written by the PE producer warps (else by the epilogue warps)
@@ -198,6 +204,7 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
 struct EpiCtx {
   uint32_t sA;          // shared-window address of chunk 0
   uint32_t s_bias;      // shared-window address of the bias table
+  uint32_t s_vec0, s_vec1;  // shared-window addresses of the staged head vectors
   uint32_t tmem_row;    // TMEM address of this warp's lane quarter, column 0
   int trow, sw, h;      // row within the tile, its swizzle phase, first sub-block of this warp within a chunk
   int tile, T;
@@ -291,7 +298,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       if (F & E_RANK1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(pg.cvec + cc) + j);
+          const float4 f = lds128f(cx.s_vec0 + (uint32_t)((cc + 4 * j) * 4));
           v[4 * j] = fmaf(rvv, f.x, v[4 * j]); v[4 * j + 1] = fmaf(rvv, f.y, v[4 * j + 1]);
           v[4 * j + 2] = fmaf(rvv, f.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(rvv, f.w, v[4 * j + 3]);
         }
@@ -331,7 +338,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       if (F & E_HEAD_SIGMA) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(pg.ws + cc) + j);
+          const float4 f = lds128f(cx.s_vec0 + (uint32_t)((cc + 4 * j) * 4));
           hs0 = fmaf(v[4 * j], f.x, hs0); hs0 = fmaf(v[4 * j + 1], f.y, hs0);
           hs0 = fmaf(v[4 * j + 2], f.z, hs0); hs0 = fmaf(v[4 * j + 3], f.w, hs0);
         }
@@ -339,9 +346,9 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       if (F & E_HEAD_RGB) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pg.Wr + cc) + j);
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pg.Wr + n + cc) + j);
-          const float4 f2 = __ldg(reinterpret_cast<const float4*>(pg.Wr + 2 * n + cc) + j);
+          const float4 f0 = lds128f(cx.s_vec1 + (uint32_t)((cc + 4 * j) * 4));
+          const float4 f1 = lds128f(cx.s_vec1 + (uint32_t)((n + cc + 4 * j) * 4));
+          const float4 f2 = lds128f(cx.s_vec1 + (uint32_t)((2 * n + cc + 4 * j) * 4));
           hs0 = fmaf(v[4 * j], f0.x, hs0); hs0 = fmaf(v[4 * j + 1], f0.y, hs0);
           hs0 = fmaf(v[4 * j + 2], f0.z, hs0); hs0 = fmaf(v[4 * j + 3], f0.w, hs0);
           hs1 = fmaf(v[4 * j], f1.x, hs1); hs1 = fmaf(v[4 * j + 1], f1.y, hs1);
@@ -409,11 +416,22 @@ __device__ __noinline__ void run_step_generic(const int Frt, const Program& pg, 
                                               float& hs1, float& hs2) {
   run_step_body<-1, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
 }
+// the flavours that run once or twice per tile: straight-line too, but out of line, each with its own register
+// allocation (inlined next to the hot flavour they push it into spilling)
+template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
+__device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
+                                           uint32_t acc_col, uint64_t* ready, float* hs) {
+  float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
+  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(CF, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+  if (CF & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs[0] = hs0; hs[1] = hs1; hs[2] = hs2; }
+}
 
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
+constexpr int P_FWD = 0, P_BWD = 1;   // which set of straight-line epilogue flavours a kernel instance carries
+
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG>
 __global__ void __launch_bounds__((3 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
 chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;       // TMEM columns per accumulator
@@ -431,7 +449,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   uint8_t* sA = smem;                                            // nchunks x 16 KB
   uint8_t* sB = sA + (size_t)pg.nchunks * CHUNK_BYTES;           // stages x STAGE_BYTES
   float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);
-  float* s_bias = s_head + HEAD_SMEM / 4;                        // nbias x ACC_STRIDE floats
+  float* s_bias = s_head + head_smem(NH) / 4;                    // nbias x ACC_STRIDE floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.nbias * ACC_STRIDE);
   uint64_t* w_full = bars;                       // [MAX_STAGES]
   uint64_t* w_empty = w_full + MAX_STAGES;       // [MAX_STAGES]
@@ -459,6 +477,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     if (st.bias)
       for (int i = threadIdx.x; i < st.n; i += blockDim.x) s_bias[st.bias_row * ACC_STRIDE + i] = st.bias[i];
   }
+  if (pg.vec_row >= 0)
+    for (int i = threadIdx.x; i < pg.vec_len0; i += blockDim.x) s_bias[pg.vec_row * ACC_STRIDE + i] = pg.vec0[i];
+  if (pg.vec_row1 >= 0)
+    for (int i = threadIdx.x; i < pg.vec_len1; i += blockDim.x) s_bias[pg.vec_row1 * ACC_STRIDE + i] = pg.vec1[i];
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -553,6 +575,8 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     EpiCtx cx;
     cx.sA = smem_u32(sA);
     cx.s_bias = smem_u32(s_bias);
+    cx.s_vec0 = cx.s_bias + (uint32_t)((pg.vec_row >= 0 ? pg.vec_row : 0) * ACC_STRIDE * 4);
+    cx.s_vec1 = cx.s_bias + (uint32_t)((pg.vec_row1 >= 0 ? pg.vec_row1 : 0) * ACC_STRIDE * 4);
     cx.tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     cx.h = ew >> 2;
     cx.trow = q * 32 + lane;
@@ -570,6 +594,19 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
       cx.tr = (pg.trace && blockIdx.x == 0 && it == 2 && lane == 0) ? 40 + 10 * ew : 0;   // regions 4..: one per warp
       cx.row = (long long)tile * TILE_M + trow;
       cx.live = cx.row < pg.M;
+      if (pg.has_tile_bias) {
+        // per-ray bias rows (the hoisted per-ray-constant inputs) when a tile never straddles two rays: staged once
+        // per tile and then read like any bias.  First barrier: every warp is done with the previous tile's rows.
+        named_bar(5, EPI_THREADS);
+        const int et = threadIdx.x - 64;
+        const size_t ray = (size_t)(((long long)tile * TILE_M) / pg.rep);
+        for (int s = 0; s < pg.nsteps; ++s) {
+          const Step& st = pg.st[s];
+          if (st.tile_bias)
+            for (int i = et; i < st.n; i += EPI_THREADS) s_bias[st.bias_row * ACC_STRIDE + i] = st.rowbias[ray * st.n + i];
+        }
+        named_bar(5, EPI_THREADS);
+      }
       for (int s = 0; s < pg.nsteps; ++s) {
         const Step& st = pg.st[s];
         const int flags = st.flags;
@@ -583,18 +620,58 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         MODA_TR(cx.tr, cx.tr, s, 0);
         float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
         const uint32_t acc_col = (uint32_t)(b * ACC_STRIDE);
-        // the flavours that make up almost all of the work run as straight-line specialisations (a taken branch
-        // costs an instruction-fetch bubble: ~30 of them per sub-block in the generic path); the rest share the
-        // run-time-flag version
-        constexpr int HOT_FWD = (BOX_ROWS == 128) ? (E_BIAS | E_RELU | E_MASK_OUT | E_SMEM)
-                                                  : (E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | E_LO);
+        // every flavour a program uses runs as a straight-line specialisation (a taken branch costs an
+        // instruction-fetch bubble: ~30 of them per sub-block in the run-time-flag version, which stays as the
+        // out-of-line fallback for the rare combinations, e.g. a forward without saved sign bits)
+        constexpr int LO = (BOX_ROWS == 128) ? 0 : E_LO;
+        constexpr int HOT_FWD = E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | LO;
         constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
-        if (flags == HOT_FWD)
-          run_step<HOT_FWD, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
-        else if (flags == HOT_BWD)
-          run_step<HOT_BWD, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
-        else
+#define MODA_FLAVOUR(FL) \
+  if (flags == (FL)) run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2); else
+#define MODA_COLD(FL) \
+  if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs); \
+                       if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
+#ifndef MODA_CHAIN_DISPATCH
+#define MODA_CHAIN_DISPATCH 0
+#endif
+#if MODA_CHAIN_DISPATCH == 0
+        // the flavour that makes up most of a pass inline, the rest through the inlined run-time-flag version
+        if constexpr (PROG == P_FWD) {
+          MODA_FLAVOUR(HOT_FWD)
           run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        } else {
+          MODA_FLAVOUR(HOT_BWD)
+          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        }
+#else
+        if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
+          MODA_FLAVOUR(HOT_FWD)
+          MODA_COLD(HOT_FWD | E_HEAD_SIGMA)
+          MODA_COLD(E_BIAS | E_SMEM)                                   // xyz_encoding_final
+          MODA_COLD(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM)             // dir layer + rgb head
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        } else if constexpr (PROG == P_FWD) {
+          MODA_FLAVOUR(HOT_FWD)
+          MODA_COLD(E_BIAS | E_SMEM | E_LO)
+          MODA_COLD(E_BIAS | E_OUT_F32)
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        } else if constexpr (BOX_ROWS == 128) {
+          MODA_FLAVOUR(HOT_BWD)
+          MODA_COLD(E_SMEM)
+          MODA_COLD(E_LOAD16 | E_SMEM)
+          MODA_COLD(E_ADD_SX | E_SMEM)
+          MODA_COLD(E_RANK1 | E_MASK_IN | E_SMEM)
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        } else {
+          MODA_FLAVOUR(HOT_BWD)
+          MODA_COLD(E_SMEM)
+          MODA_COLD(E_LOAD32 | E_SMEM)
+          MODA_COLD(E_ADD_SX | E_SMEM)
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+        }
+#endif
+#undef MODA_COLD
+#undef MODA_FLAVOUR
         if (st.kc > 0) {
           tc_fence_before();
           __syncwarp();
@@ -771,6 +848,7 @@ struct Builder {
     memset(gen, 0, sizeof(gen));
     pg.pe_chunk = -1;
     pg.pe_save_map = -1;
+    pg.vec_row = pg.vec_row1 = -1;
   }
   // registers an fp16 (rows, cols) output for TMA stores; returns its descriptor index, -1 when ptr is null
   int save(const void* ptr, long long rows, int cols) {
@@ -783,7 +861,7 @@ struct Builder {
     Step& st = pg.st[pg.nsteps++];
     st.n = n; st.flags = flags; st.kc = 0;
     st.out_chunk = st.out_lo_chunk = st.save_map = -1;
-    st.mask_slot = 0; st.release_pe = 0; st.bias_row = 0; st.bias = nullptr; st.rowbias = nullptr;
+    st.mask_slot = 0; st.release_pe = 0; st.bias_row = 0; st.bias = nullptr; st.rowbias = nullptr; st.tile_bias = 0;
     return st;
   }
   // K chunk: A from shared-memory chunk `a` (its latest write), B from packed-weight chunk `bcol`
@@ -820,7 +898,7 @@ struct Builder {
     ++gen[chunk];
     if (lo) { pg.from_pe[chunk + 1] = 1; ++gen[chunk + 1]; }
   }
-  void finish() {
+  void finish(int acc_stride) {
     for (int i = 0; i < MAX_CHUNKS; ++i) pg.wpt[i] = gen[i];
     int phases = 0, d = 0;
     for (int s = 0; s < pg.nsteps; ++s) {
@@ -834,25 +912,30 @@ struct Builder {
     for (int s = 0; s < pg.nsteps; ++s) {
       Step& st = pg.st[s];
       if (st.bias) { st.bias_row = pg.nbias++; st.flags |= E_BIAS; }
-      if (st.rowbias) st.flags |= E_ROWBIAS;
+      if (st.rowbias) {
+        if (pg.rep % TILE_M == 0) { st.bias_row = pg.nbias++; st.flags |= E_BIAS; st.tile_bias = 1; pg.has_tile_bias = 1; }
+        else st.flags |= E_ROWBIAS;
+      }
     }
+    if (pg.vec0) { pg.vec_row = pg.nbias; pg.nbias += (pg.vec_len0 + acc_stride - 1) / acc_stride; }
+    if (pg.vec1) { pg.vec_row1 = pg.nbias; pg.nbias += (pg.vec_len1 + acc_stride - 1) / acc_stride; }
   }
 };
 
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS>
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG>
 int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
   if (b.err) return b.err;
-  b.finish();
+  b.finish((BOX_ROWS == 128) ? 256 : 64);
   b.pg.trace = g_trace;
   if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, BOX_ROWS)) return e;
   constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128;
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;
   constexpr int THREADS = (3 + EPI_WARPS + PE_WARPS) * 32;
-  const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + HEAD_SMEM +
+  const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + head_smem(EPI_WARPS / 4) +
                       (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512 + 32;
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
   MODA_REQUIRE(smem <= cap, "chain: needs %zu B of shared memory (limit %zu)", smem, cap);
-  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS>;
+  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS, PROG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
@@ -888,13 +971,13 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && rowbias && ws && bs && Wr && br && raw && rep > 0 && F >= 0 && F <= 10,
                "chain_trunk_fwd: bad arguments");
-  MODA_REQUIRE(al16(rowbias) && al16(ws) && al16(Wr) && al16(raw) && al16(wpack),
-               "chain_trunk_fwd: rowbias, ws, Wr, raw and wpack must be 16-byte aligned");
+  MODA_REQUIRE(al16(rowbias) && al16(raw) && al16(wpack), "chain_trunk_fwd: rowbias, raw and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = 4;
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
+  pg.vec0 = ws; pg.vec_len0 = 256; pg.vec1 = Wr; pg.vec_len1 = 3 * 128;
   const int PE = 4;
   const int order[4] = {0, 1, 2, 3};   // the epilogue finishes the chunks of a result in this order
   b.pe(PE, false, b.save(A0, P, 64));
@@ -928,7 +1011,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  return launch<128, 8, 1, 1>(b, wpack, 256, col * 64, stream);
+  return launch<128, 8, 1, 1, P_FWD>(b, wpack, 256, col * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -944,11 +1027,12 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
                                     void* dY, void* d_pe, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && d_fin && dY && d_pe, "chain_trunk_bwd: null pointer");
-  MODA_REQUIRE(al16(d_dfe) && al16(ws) && al16(wpackT), "chain_trunk_bwd: d_dfe, ws and wpackT must be 16-byte aligned");
+  MODA_REQUIRE(al16(d_dfe) && al16(wpackT), "chain_trunk_bwd: d_dfe and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
   pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
   pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
+  pg.vec0 = ws; pg.vec_len0 = 256;
   pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
   const int SX = 4;
   const int order[4] = {0, 1, 2, 3};
@@ -987,7 +1071,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  return launch<128, 8, 1, 1>(b, wpackT, 256, col * 64, stream);
+  return launch<128, 8, 1, 1, P_BWD>(b, wpackT, 256, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin
@@ -1027,7 +1111,7 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
   { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, 14);
     st.save_map = b.save(dfe, P, 64); b.out(st, AH, 1, AL); }
   { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, 16); }
-  return launch<64, 4, 1, 2>(b, wpack, 64, 18 * 64, stream);
+  return launch<64, 4, 1, 2, P_FWD>(b, wpack, 64, 18 * 64, stream);
 }
 
 // Adjoint chain of nerf_skin on plain fp16 operands.  wpackT: fp16 (64, 9*64), rows = input channel, cols = output:
@@ -1060,5 +1144,5 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
     b.out(st, A, 1);
   }
   { Step& st = b.add(64, E_ADD_SX); b.k(st, A, 8); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
-  return launch<64, 4, 1, 2>(b, wpackT, 64, 9 * 64, stream);
+  return launch<64, 4, 1, 2, P_BWD>(b, wpackT, 64, 9 * 64, stream);
 }

@@ -470,9 +470,19 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * KIN + c0), v);
         if (n < n_valid) {
           float* o = dW + (size_t)n * ldw + c0;
+          // 148 CTAs add their partial sums into the same (N, K) block: 128-bit reductions quarter the number of
+          // L2 atomic operations of the tail (rows whose start is not 16-byte aligned fall back to scalar adds)
+          if (c0 + 32 <= k_valid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < k_valid) atomicAdd(o + j, v[j] * oscale);
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j] * oscale),
+                           "f"(v[j + 1] * oscale), "f"(v[j + 2] * oscale), "f"(v[j + 3] * oscale)
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < k_valid) atomicAdd(o + j, v[j] * oscale);
+          }
         }
       }
     }
