@@ -451,11 +451,17 @@ def test_training_step_on_flat_parameter_buffer():
         res = render_rays(models, emb, rays, N_samples=S, perturb=0, noise_std=0, opts=synth.default_opts(), img_size=512)
         loss = ((res["img_coarse"] - 0.3) ** 2).mean() + ((res["sil_coarse"] - 0.5) ** 2).mean() + res["frame_cyc_dis"].mean()
         loss.backward()
-        out.append((res["img_coarse"].detach().clone(), [p.grad.clone() for p in MM.parameters_of(models) if p.grad is not None]))
+        out.append((res["img_coarse"].detach().clone(), [None if p.grad is None else p.grad.clone() for p in MM.parameters_of(models)]))
         if flat:
             assert all(p.data_ptr() % 16 == 0 for p in MM.parameters_of(models))
             assert float(fp.grad.abs().sum()) > 0
     assert torch.equal(out[0][0], out[1][0])
     assert len(out[0][1]) == len(out[1][1])
+    n_checked = 0
     for a, b in zip(out[0][1], out[1][1]):
+        if a is None:   # no gradient reaches it (nerf_skin's discarded sigma head): its flat .grad view stays zero
+            assert float(b.abs().sum()) == 0
+            continue
+        n_checked += 1
         assert rel_err(b, a) < 1e-5   # atomics in the per-bone reductions reorder sums run to run
+    assert n_checked >= 40
