@@ -160,6 +160,10 @@ int moda_pe16_bwd(const float* xyz, const void* g16, const void* g16lo, int ldg,
  * zero padded, optionally transposed */
 int moda_pack16(const float* in, int ld_in, int rows, int cols, int col0, void* out16, void* out16_dup,
                 void* out16_lo, int ld_out, int out_rows, int width, int transpose, cudaStream_t stream);
+/* n pack16 blocks of one packed matrix (shared row pitch ld_out) in one launch; out16_lo[i] may be NULL */
+int moda_pack16_multi(int n, const float* const* in, const int* ld_in, const int* rows, const int* cols,
+                      const int* col0, void* const* out16, void* const* out16_lo, int ld_out, const int* out_rows,
+                      const int* width, const int* transpose, cudaStream_t stream);
 /* fp32 (M, cols) * (*scale) -> fp16 (hi, lo) pair, zero padded to `width` columns (lo may be NULL) */
 int moda_split16(const float* in, int ld_in, int cols, const float* scale, void* hi, void* lo, int ld_out, int width,
                  long long M, cudaStream_t stream);
@@ -198,7 +202,13 @@ int moda_chain_trunk_fwd(const float* xyz, long long P, int rep /* samples per r
                          const float* rowbias /* (P/rep,128) per-ray part of the dir layer */, const float* ws,
                          const float* bs, const float* Wr, const float* br, void* A0 /* (P,64) fp16 PE */,
                          void* H /* (8,P,256) */, void* fin /* (P,256) */, void* dfe /* (P,128) */,
-                         unsigned int* maskbits /* (8,tiles,8,128) ReLU sign bits */, float* raw /* (P,4) */,
+                         unsigned int* maskbits /* (8,tiles,8,128) ReLU sign bits */, float* raw /* Density-only pass of nerf_coarse for grid queries (extract_mesh, nnutils/train_utils.py:1377-1404 with
+ * nerf.py:176-180 sigma_only=True): layers 1-8 + sigma head on tensor cores, nothing saved.  wpack as for
+ * moda_chain_trunk_fwd; sigma (P) fp32. */
+int moda_chain_trunk_sigma(const float* xyz, long long P, int F, const float* win, const void* wpack,
+                           const float* const* biases, const float* ws, const float* bs, float* sigma,
+                           cudaStream_t stream);
+/* (P,4) */,
                          cudaStream_t stream);
 int moda_chain_trunk_bwd(const void* d_dfe /* (P,128) fp16 */, const float* gsig /* (P) */, const float* ws,
                          const float* rscale, const void* wpackT /* fp16 (256, 42*64) */,

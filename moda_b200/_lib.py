@@ -55,6 +55,7 @@ SIGNATURES = {
     "moda_pe16_fwd": [c_p, c_p, c_p, c_i, c_ll, c_i, c_fp, c_p],
     "moda_pe16_bwd": [c_p, c_p, c_p, c_i, c_p, c_ll, c_i, c_fp, c_p, c_i, c_p],
     "moda_pack16": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "moda_pack16_multi": [c_i, c_pp, c_ip, c_ip, c_ip, c_ip, c_pp, c_pp, c_i, c_ip, c_ip, c_ip, c_p],
     "moda_split16": [c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_ll, c_p],
     "moda_head_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
     "moda_head_bwd": [c_p] * 12 + [c_ll, c_p],
@@ -62,6 +63,7 @@ SIGNATURES = {
     "moda_segsum16": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
     "moda_loss_scale": [c_p, c_ll, c_f, c_p, c_p, c_p],
     "moda_chain_trunk_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 12,
+    "moda_chain_trunk_sigma": [c_p, c_ll, c_i, c_fp, c_p, c_pp, c_p, c_p, c_p, c_p],
     "moda_chain_trunk_bwd": [c_p] * 6 + [c_ll] + [c_p] * 4,
     "moda_chain_skin_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 7,
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,

@@ -19,11 +19,26 @@ HALF = torch.float16
 TILE = 128
 
 
-def _pack(src, cols, col0, out, out_col0, out_rows, width, transpose, lo_col0=None):
-    """fp32 block -> fp16 block of ``out`` at column ``out_col0`` (and its low half at ``lo_col0``), zero padded."""
-    base = ptr(out)
-    call("moda_pack16", ptr(src), src.stride(0), src.shape[0], cols, col0, base + 2 * out_col0, None,
-         (base + 2 * lo_col0) if lo_col0 is not None else None, out.stride(0), out_rows, width, int(transpose), stream())
+class _Packer:
+    """Collects the fp32 -> fp16 block copies that build one packed-weight matrix and runs them as ONE launch
+    (moda_pack16_multi): block = src[:, col0:col0+cols] -> out[:out_rows, out_col0:out_col0+width], zero padded,
+    optionally transposed, optionally with the low half of the split-precision pair at column lo_col0."""
+
+    def __init__(self, out):
+        self.out, self.jobs = out, []
+
+    def add(self, src, cols, col0, out_col0, out_rows, width, transpose, lo_col0=None):
+        self.jobs.append((src, cols, col0, out_col0, out_rows, width, transpose, lo_col0))
+
+    def run(self):
+        n, base = len(self.jobs), ptr(self.out)
+        P, I = ctypes.c_void_p * n, ctypes.c_int * n
+        j = self.jobs
+        call("moda_pack16_multi", n, P(*[ptr(x[0]) for x in j]), I(*[x[0].stride(0) for x in j]),
+             I(*[x[0].shape[0] for x in j]), I(*[x[1] for x in j]), I(*[x[2] for x in j]),
+             P(*[base + 2 * x[3] for x in j]), P(*[(base + 2 * x[7]) if x[7] is not None else None for x in j]),
+             self.out.stride(0), I(*[x[4] for x in j]), I(*[x[5] for x in j]), I(*[int(x[6]) for x in j]), stream())
+        return self.out
 
 
 def _wgrad(dY, N, X, K, M, dW, col0, n_valid, k_valid, oscale, dbias=None):
@@ -63,6 +78,8 @@ def pack_trunk_fwd(params):
     W = [params[2 * i] for i in range(8)]
     Wf, Wd = params[16], params[18]
     out = torch.zeros(256, 38 * 64, device=W[0].device, dtype=HALF)
+    pk = _Packer(out)
+    _pack = lambda w, cols, col0, _o, out_col0, out_rows, width, tr: pk.add(w, cols, col0, out_col0, out_rows, width, tr)
     col = 0
     for i in range(8):
         if i == 0:
@@ -75,7 +92,7 @@ def pack_trunk_fwd(params):
     _pack(Wf, 256, 0, out, col, 256, 256, False); col += 256
     _pack(Wd, 256, 0, out, col, 128, 256, False); col += 256
     assert col == 38 * 64
-    return out
+    return pk.run()
 
 
 def pack_trunk_bwd(params):
@@ -83,6 +100,8 @@ def pack_trunk_bwd(params):
     W = [params[2 * i] for i in range(8)]
     Wf, Wd = params[16], params[18]
     out = torch.zeros(256, 42 * 64, device=W[0].device, dtype=HALF)
+    pk = _Packer(out)
+    _pack = lambda w, cols, col0, _o, out_col0, out_rows, width, tr: pk.add(w, cols, col0, out_col0, out_rows, width, tr)
     col = 0
     _pack(Wd, 256, 0, out, col, 256, 128, True); col += 128
     _pack(Wf, 256, 0, out, col, 256, 256, True); col += 256
@@ -94,7 +113,7 @@ def pack_trunk_bwd(params):
         _pack(W[i], 256, 0, out, col, 256, 256, True); col += 256
     _pack(W[0], 63, 0, out, col, 64, 256, True); col += 256
     assert col == 42 * 64
-    return out
+    return pk.run()
 
 
 class TrunkChainFn(torch.autograd.Function):
@@ -197,9 +216,10 @@ def pack_skin_fwd(params, nc):
     out = torch.zeros(64, 18 * 64, device=W[0].device, dtype=HALF)
     blocks = [(W[0], 63, 0), (W[1], 64, 0), (W[2], 64, 0), (W[3], 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc),
               (Wf, 64, 0), (Wd, 64, 0), (Wr, 32, 0)]
+    pk = _Packer(out)
     for i, (w, cols, col0) in enumerate(blocks):
-        _pack(w, cols, col0, out, 128 * i, 64, 64, False, lo_col0=128 * i + 64)
-    return out
+        pk.add(w, cols, col0, 128 * i, 64, 64, False, lo_col0=128 * i + 64)
+    return pk.run()
 
 
 def pack_skin_bwd(params, nc):
@@ -209,9 +229,10 @@ def pack_skin_bwd(params, nc):
     out = torch.zeros(64, 9 * 64, device=W[0].device, dtype=HALF)
     blocks = [(Wr, 32, 0), (Wd, 64, 0), (Wf, 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc), (W[3], 64, 0), (W[2], 64, 0),
               (W[1], 64, 0), (W[0], 63, 0)]
+    pk = _Packer(out)
     for i, (w, cols, col0) in enumerate(blocks):
-        _pack(w, cols, col0, out, 64 * i, 64, 64, True)
-    return out
+        pk.add(w, cols, col0, 64 * i, 64, 64, True)
+    return pk.run()
 
 
 class SkinChainFn(torch.autograd.Function):

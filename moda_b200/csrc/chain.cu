@@ -100,6 +100,7 @@ struct Program {
   const float* xyz;
   // heads (nerf_coarse forward)
   const float* ws; const float* bs; const float* Wr; const float* br; float* raw;
+  int sigma_only;        // density-grid mode: the program ends at the sigma head and raw is (M) = sigma
   // rank-1 term (nerf_coarse adjoint): gsig (M), cvec (n), rscale (device scalar)
   const float* gsig; const float* cvec; const float* rscale;
   // load steps
@@ -220,7 +221,8 @@ struct EpiCtx {
 // sub-blocks {h, h + NH, ..} < 4 of every chunk.
 template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
-                                         uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1, float& hs2) {
+                                         uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1, float& hs2,
+                                         unsigned long long pm0, unsigned long long pm1) {
   constexpr int SPC = 4 / NH;                  // sub-blocks per chunk for this warp
   const int F = (CF >= 0) ? CF : Frt;   // CF >= 0: flavour known at compile time (straight-line hot paths)
   const bool MMA = !(F & (E_LOAD16 | E_LOAD32));
@@ -241,10 +243,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
   if (F & (E_MASK_IN | E_MASK_OUT)) {
     mp = reinterpret_cast<unsigned long long*>(pg.maskbits) +
          ((((size_t)st.mask_slot * cx.T + cx.tile) * NH + cx.h) * MW) * TILE_M + cx.trow;
-    if (F & E_MASK_IN) {
-      m0 = __ldg(mp);
-      if (MW == 2 && nsub > 4) m1 = __ldg(mp + TILE_M);
-    }
+    if (F & E_MASK_IN) { m0 = pm0; m1 = pm1; }   // fetched by the caller before it waited for the accumulator
   }
   float rvv = 0.f;
   if (F & E_RANK1) rvv = cx.live ? pg.gsig[cx.row] * cx.rscale : 0.f;
@@ -406,23 +405,24 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
 template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __forceinline__ void run_step(const int Frt, const Program& pg, const Maps& maps, const Step& st,
                                          const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1,
-                                         float& hs2) {
-  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+                                         float& hs2, unsigned long long pm0, unsigned long long pm1) {
+  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
 }
 // ... the run-time-flag version (a few steps per tile) out of line, so that it does not weigh on them
 template <int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __noinline__ void run_step_generic(const int Frt, const Program& pg, const Maps& maps, const Step& st,
                                               const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0,
-                                              float& hs1, float& hs2) {
-  run_step_body<-1, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+                                              float& hs1, float& hs2, unsigned long long pm0, unsigned long long pm1) {
+  run_step_body<-1, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
 }
 // the flavours that run once or twice per tile: straight-line too, but out of line, each with its own register
 // allocation (inlined next to the hot flavour they push it into spilling)
 template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
-                                           uint32_t acc_col, uint64_t* ready, float* hs) {
+                                           uint32_t acc_col, uint64_t* ready, float* hs, unsigned long long pm0,
+                                           unsigned long long pm1) {
   float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
-  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(CF, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(CF, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
   if (CF & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs[0] = hs0; hs[1] = hs1; hs[2] = hs2; }
 }
 
@@ -612,6 +612,16 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         const int flags = st.flags;
         if (ew == 0 && lane == 0) s_dbg[2] = it * 100 + s;
         int b = 0;
+        // the saved ReLU sign words of this step (adjoint programs) come from HBM: ask for them before waiting for
+        // the accumulator, so that their latency is off the step's critical path
+        unsigned long long pm0 = 0, pm1 = 0;
+        if (flags & E_MASK_IN) {
+          constexpr int MWc = (ACC_STRIDE / 16 / NH + 3) / 4;
+          const unsigned long long* mp = reinterpret_cast<const unsigned long long*>(pg.maskbits) +
+              ((((size_t)st.mask_slot * cx.T + cx.tile) * NH + cx.h) * MWc) * TILE_M + cx.trow;
+          asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(pm0) : "l"(mp));
+          if (MWc == 2 && (st.n >> 6) * (4 / NH) > 4) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(pm1) : "l"(mp + TILE_M));
+        }
         if (st.kc > 0) {
           b = mma_ctr & 1;
           wait_or_trap(&acc_full[b], (mma_ctr >> 1) & 1);
@@ -627,9 +637,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         constexpr int HOT_FWD = E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | LO;
         constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
 #define MODA_FLAVOUR(FL) \
-  if (flags == (FL)) run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2); else
+  if (flags == (FL)) run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
 #define MODA_COLD(FL) \
-  if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs); \
+  if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs, pm0, pm1); \
                        if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
 #ifndef MODA_CHAIN_DISPATCH
 #define MODA_CHAIN_DISPATCH 0
@@ -638,10 +648,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         // the flavour that makes up most of a pass inline, the rest through the inlined run-time-flag version
         if constexpr (PROG == P_FWD) {
           MODA_FLAVOUR(HOT_FWD)
-          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         } else {
           MODA_FLAVOUR(HOT_BWD)
-          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         }
 #else
         if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
@@ -649,25 +659,25 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           MODA_COLD(HOT_FWD | E_HEAD_SIGMA)
           MODA_COLD(E_BIAS | E_SMEM)                                   // xyz_encoding_final
           MODA_COLD(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM)             // dir layer + rgb head
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (PROG == P_FWD) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_COLD(E_BIAS | E_SMEM | E_LO)
           MODA_COLD(E_BIAS | E_OUT_F32)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (BOX_ROWS == 128) {
           MODA_FLAVOUR(HOT_BWD)
           MODA_COLD(E_SMEM)
           MODA_COLD(E_LOAD16 | E_SMEM)
           MODA_COLD(E_ADD_SX | E_SMEM)
           MODA_COLD(E_RANK1 | E_MASK_IN | E_SMEM)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         } else {
           MODA_FLAVOUR(HOT_BWD)
           MODA_COLD(E_SMEM)
           MODA_COLD(E_LOAD32 | E_SMEM)
           MODA_COLD(E_ADD_SX | E_SMEM)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         }
 #endif
 #undef MODA_COLD
@@ -685,7 +695,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             sig_keep = pg.bs[0];
 #pragma unroll
             for (int k = 0; k < NH; ++k) sig_keep += s_head[(k * 128 + trow) * 4 + 3];
+            if (pg.sigma_only && cx.live) pg.raw[cx.row] = sig_keep;
           }
+          if (pg.sigma_only) named_bar(4, EPI_THREADS);   // s_head is reused by the next tile's partials
         }
         if (flags & E_HEAD_RGB) {
           float* mine = s_head + (h * 128 + trow) * 4;
@@ -723,23 +735,39 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && lead;
         MODA_TR(tr, 30, 0, 0);
         if (lead) s_dbg[3] = it;
+        // this thread's PE_ROWS consecutive rows of xyz: fetched before the wait, so the global-load latency hides
+        // behind it
+        float xs[PE_ROWS][3];
+#pragma unroll
+        for (int rr = 0; rr < PE_ROWS; ++rr) {
+          const long long row = (long long)tile * TILE_M + (pw * 32 + lane) * PE_ROWS + rr;
+          const bool in = row < pg.M;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) xs[rr][c] = in ? __ldg(pg.xyz + row * 3 + c) : 0.f;
+        }
         wait_or_trap<0>(pe_free, (it & 1) ^ 1);   // the previous tile's last reader of the PE chunk(s) has completed
         MODA_TR(tr, 31, 0, 0);
 #pragma unroll 1
         for (int rr = 0; rr < PE_ROWS; ++rr) {
           const int trow = (pw * 32 + lane) * PE_ROWS + rr;
           const int sw = trow & 7;
-          const long long row = (long long)tile * TILE_M + trow;
-          float x[3] = {0.f, 0.f, 0.f};
-          if (row < pg.M) { x[0] = pg.xyz[row * 3]; x[1] = pg.xyz[row * 3 + 1]; x[2] = pg.xyz[row * 3 + 2]; }
+          float x[3] = {xs[0][0], xs[0][1], xs[0][2]};
+#pragma unroll
+          for (int j = 1; j < PE_ROWS; ++j)   // register select (the row loop stays rolled: code size)
+            if (rr == j) { x[0] = xs[j][0]; x[1] = xs[j][1]; x[2] = xs[j][2]; }
           const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
-          auto put = [&](const int idx, float v) {
-            const __half hv = __float2half_rn(v);
-            const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + (idx & 7) * 2);
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(hv)) : "memory");
-            if (BOX_ROWS == 64) {   // split precision: low half into the next chunk
-              const __half lv = __float2half_rn(v - __half2float(hv));
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + CHUNK_BYTES), "h"(__half_as_ushort(lv)) : "memory");
+          // channels come out in index order; two neighbours share one 32-bit store (idx is a compile-time constant
+          // after unrolling, so the parity test and the address arithmetic fold away)
+          float pend = 0.f;
+          auto put = [&](const int idx, const float v) {
+            if ((idx & 1) == 0) { pend = v; return; }
+            const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + ((idx & 7) - 1) * 2);
+            const __half2 hv = __floats2half2_rn(pend, v);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&hv)) : "memory");
+            if (BOX_ROWS == 64) {   // split precision: low halves into the next chunk
+              const float2 hf = __half22float2(hv);
+              const __half2 lv = __floats2half2_rn(pend - hf.x, v - hf.y);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + CHUNK_BYTES), "r"(*reinterpret_cast<const uint32_t*>(&lv)) : "memory");
             }
           };
           put(0, x[0]); put(1, x[1]); put(2, x[2]);
@@ -747,24 +775,23 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           for (int k = 0; k < 10; ++k) {
             const float f = (float)(1 << k);
             const float w = (k < pg.F) ? pg.win[k] : 0.f;
+            float sn[3], cs[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              float sn, cs;
-              if (BOX_ROWS == 128) {
-                // fp16-only consumer (2^-11 relative rounding): SFU sin/cos after a two-term Cody-Waite reduction
-                // to [-pi, pi] (absolute error ~1e-6 for |2^k x| <= 160 rad)
-                const float r = x[c] * f;
-                const float kk = rintf(r * 0.15915494309189535f);
-                float r2 = fmaf(kk, -6.2831854820251465f, r);
-                r2 = fmaf(kk, 1.7484555e-7f, r2);
-                sn = __sinf(r2);
-                cs = __cosf(r2);
-              } else {
-                sincosf(x[c] * f, &sn, &cs);   // split precision needs the full-accuracy path
-              }
-              put(3 + 6 * k + c, w * sn);
-              put(3 + 6 * k + 3 + c, w * cs);
+              // SFU sin/cos after an exact two-term Cody-Waite reduction to [-pi, pi]: absolute error below 1e-6
+              // for |2^k x| <= 160 rad, far inside the fp16 rounding of the plain path and at the level of the
+              // (hi, lo) pair's 2^-22 of the split-precision path
+              const float r = x[c] * f;
+              const float kk = rintf(r * 0.15915494309189535f);
+              float r2 = fmaf(kk, -6.2831854820251465f, r);
+              r2 = fmaf(kk, 1.7484555e-7f, r2);
+              sn[c] = w * __sinf(r2);
+              cs[c] = w * __cosf(r2);
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) put(3 + 6 * k + c, sn[c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) put(3 + 6 * k + 3 + c, cs[c]);
           }
           put(63, 0.f);
         }
@@ -1012,6 +1039,39 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     b.out(st, 0, 2);
   }
   return launch<128, 8, 1, 1, P_FWD>(b, wpack, 256, col * 64, stream);
+}
+
+// Density only (the grid query of mesh extraction, nnutils/train_utils.py:1377-1404 -> nerf.py:176-180 with
+// sigma_only=True): the first 30 weight chunks of the forward packing, layers 1-8 and the sigma head; nothing is
+// saved.  sigma (P) fp32.
+extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, const float* win, const void* wpack,
+                                      const float* const* biases, const float* ws, const float* bs, float* sigma,
+                                      cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(xyz && wpack && biases && ws && bs && sigma && F >= 0 && F <= 10, "chain_trunk_sigma: bad arguments");
+  MODA_REQUIRE(al16(wpack) && al16(ws), "chain_trunk_sigma: wpack and ws must be 16-byte aligned");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
+  pg.xyz = xyz; fill_win(pg, F, win);
+  pg.ws = ws; pg.bs = bs; pg.raw = sigma; pg.sigma_only = 1;
+  pg.vec0 = ws; pg.vec_len0 = 256;
+  const int PE = 4;
+  b.pe(PE, false, -1);
+  int col = 0;
+  for (int l = 0; l < 8; ++l) {
+    Step& st = b.add(256, E_RELU);
+    st.bias = biases[l];
+    if (l == 0) { b.k(st, PE, col); col += 1; }
+    else {
+      if (l == 4) { b.k(st, PE, col); col += 1; st.release_pe = 1; }
+      for (int i = 0; i < 4; ++i) b.k(st, i, col + i);
+      col += 4;
+    }
+    if (l == 7) st.flags |= E_HEAD_SIGMA;   // the last layer's activations only feed the head: not written back
+    else b.out(st, 0, 4);
+  }
+  return launch<128, 8, 1, 1, P_FWD>(b, wpack, 256, 38 * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the

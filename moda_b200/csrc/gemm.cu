@@ -373,7 +373,10 @@ extern "C" int moda_linear_wgrad(int M, int N, int nseg, const float* const* seg
   dim3 grid(cdiv(N, 64), cdiv(K, 64), splits);
   gemm_kernel<DenseT, ASrcT, EpiWgrad, 64, 64, false, false><<<grid, GEMM_THREADS, 0, stream>>>(p, a, ep, N, K, M, r_chunk);
   if (dbias) {
-    const int rpb = 2048;
+    // enough row blocks to cover the machine (the old fixed 2048 rows per block left a handful of CTAs walking
+    // thousands of rows each)
+    int rpb = cdiv(M, cdiv(148 * 4, cdiv(N, 64)));
+    if (rpb < 16) rpb = 16;
     dim3 g2(cdiv(N, 64), cdiv(M, rpb));
     colsum_kernel<<<g2, 64, 0, stream>>>(dY, ldy, dbias, M, N, rpb);
   }

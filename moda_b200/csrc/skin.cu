@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
   skin_point_bwd(ctx, B, px, py, pz, dl, win, gy, gsk, live, gp, a.gdskin ? a.gdskin + pi * a.ldd : nullptr,
                  a.gskin_in ? a.gskin_in + pi * B : nullptr, &gaux_pt, emit);
   if (a.gpts && live) { a.gpts[pi * 3] = gp[0]; a.gpts[pi * 3 + 1] = gp[1]; a.gpts[pi * 3 + 2] = gp[2]; }
+  if (a.gdskin && live)   // pad columns of a pitched row: always written, so callers need not pre-zero the buffer
+    for (int b2 = B; b2 < a.ldd; ++b2) a.gdskin[pi * a.ldd + b2] = 0.f;
   __syncthreads();
 
   // ---- per-bone epilogue ----
@@ -164,6 +166,262 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
     __shared__ float red[SKIN_THREADS / 32];
     const float t = warp_sum(gaux0);
     if (lane == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < SKIN_THREADS / 32; ++i) tot += red[i];
+      if (tot != 0.f) atomicAdd(a.gaux, tot);
+    }
+  }
+}
+
+// ---- fast path --------------------------------------------------------------------------------------------
+// The configuration of the training step and of the skinning microbenchmark: weights from the Gaussian logits
+// (+ MLP delta logits), B <= 32, warped point requested, no externally supplied weights, no weight output.
+// What differs from the general kernels above:
+//  * the delta-logit rows of a warp (32 rows x ld floats, contiguous in HBM) are staged through a per-warp
+//    shared-memory tile with fully coalesced 128-bit loads; a thread then walks its own row with conflict-free
+//    LDS (the general kernel's per-thread row walk costs 32 L1 sectors per instruction and is L1-bound);
+//  * the tile is rewritten in place: logits -> exp(l - max) -> d loss / d logit, so no pass recomputes the
+//    Gaussian logit, and the logit gradients leave through the same coalesced path (pad columns zeroed);
+//  * backward: the 20 per-bone accumulands of a warp's 32 samples are reduced by transposing them through
+//    shared memory (20 STS + 8 LDS.128 + 32 FADD per bone and lane) instead of 100 shuffles.
+constexpr int FAST_BONES = 32;
+constexpr int LT = 33;   // row pitch of the per-warp logit tile: column walks of 32 rows hit 32 banks
+constexpr int RT = 36;   // row pitch of the per-warp reduction tile: 16-byte aligned rows, conflict-free LDS.128
+
+__device__ __forceinline__ void stage_rows(const float* __restrict__ g, int nrows, int ld, int B, float* L, int lane) {
+  const int n = nrows * ld;
+  if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const int l4 = ld >> 2, n4 = n >> 2;
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = __ldg(g4 + i);
+      const int r = i / l4, c = (i - r * l4) * 4;
+      float* d = L + r * LT + c;
+      if (c < B) d[0] = v.x;
+      if (c + 1 < B) d[1] = v.y;
+      if (c + 2 < B) d[2] = v.z;
+      if (c + 3 < B) d[3] = v.w;
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const int r = i / ld, c = i - r * ld;
+      if (c < B) L[r * LT + c] = __ldg(g + i);
+    }
+  }
+}
+
+__device__ __forceinline__ void unstage_rows(float* __restrict__ g, int nrows, int ld, int B, const float* L, int lane) {
+  const int n = nrows * ld;
+  if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const int l4 = ld >> 2, n4 = n >> 2;
+    for (int i = lane; i < n4; i += 32) {
+      const int r = i / l4, c = (i - r * l4) * 4;
+      const float* d = L + r * LT + c;
+      float4 v;
+      v.x = (c < B) ? d[0] : 0.f;
+      v.y = (c + 1 < B) ? d[1] : 0.f;
+      v.z = (c + 2 < B) ? d[2] : 0.f;
+      v.w = (c + 3 < B) ? d[3] : 0.f;
+      g4[i] = v;
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const int r = i / ld, c = i - r * ld;
+      g[i] = (c < B) ? L[r * LT + c] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SKIN_THREADS) skin_warp_fwd_fast_kernel(SkinArgs a) {
+  __shared__ __align__(16) float ctx[FAST_BONES * CTX_STRIDE];
+  __shared__ float bone_s[FAST_BONES * 10];
+  __shared__ float Lt[SKIN_THREADS / 32][32 * LT];
+  const int ray = blockIdx.x, B = a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = blockIdx.y * SKIN_THREADS + warp * 32;
+  const int nrows = min(32, a.S - s0);
+  float* L = Lt[warp];
+  if (a.dskin && nrows > 0) stage_rows(a.dskin + ((size_t)ray * a.S + s0) * a.ldd, nrows, a.ldd, B, L, lane);
+  build_ctx(a, ray, ctx, bone_s);
+  __syncthreads();
+  if (lane >= nrows) return;
+  const size_t pi = (size_t)ray * a.S + s0 + lane;
+  const float px = __ldg(a.pts + pi * 3), py = __ldg(a.pts + pi * 3 + 1), pz = __ldg(a.pts + pi * 3 + 2);
+  float* Lr = L + lane * LT;
+  const bool has_dl = a.dskin != nullptr;
+  float mx = -INFINITY;
+  for (int b = 0; b < B; ++b) {
+    float l = bone_logit(ctx + b * CTX_STRIDE, px, py, pz);
+    if (has_dl) l += Lr[b];
+    Lr[b] = l;
+    mx = fmaxf(mx, l);
+  }
+  float sum = 0.f, bl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < B; ++b) {
+    const float e = expf(Lr[b] - mx);
+    sum += e;
+    const float4 c0 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 12);
+    const float4 c1 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 16);
+    bl[0] = fmaf(e, c0.x, bl[0]); bl[1] = fmaf(e, c0.y, bl[1]); bl[2] = fmaf(e, c0.z, bl[2]); bl[3] = fmaf(e, c0.w, bl[3]);
+    bl[4] = fmaf(e, c1.x, bl[4]); bl[5] = fmaf(e, c1.y, bl[5]); bl[6] = fmaf(e, c1.z, bl[6]); bl[7] = fmaf(e, c1.w, bl[7]);
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bl[i] *= inv;
+  const float inv_n = 1.0f / sqrtf(bl[0] * bl[0] + bl[1] * bl[1] + bl[2] * bl[2] + bl[3] * bl[3]);
+  float c[8], y[3];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i] = bl[i] * inv_n;
+  dq_apply(c, px, py, pz, y);
+  a.y[pi * 3] = y[0]; a.y[pi * 3 + 1] = y[1]; a.y[pi * 3 + 2] = y[2];
+}
+
+__global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinArgs a) {
+  __shared__ __align__(16) float ctx[FAST_BONES * CTX_STRIDE];
+  __shared__ float bone_s[FAST_BONES * 10];
+  __shared__ float acc[FAST_BONES * ACC_STRIDE];
+  __shared__ float Lt[SKIN_THREADS / 32][32 * LT];
+  __shared__ __align__(16) float Rt[SKIN_THREADS / 32][ACC_STRIDE * RT];
+  __shared__ float red[SKIN_THREADS / 32];
+  const int ray = blockIdx.x, B = a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = blockIdx.y * SKIN_THREADS + warp * 32;
+  const int nrows = max(0, min(32, a.S - s0));
+  float* L = Lt[warp];
+  float* R = Rt[warp];
+  if (a.dskin && nrows > 0) stage_rows(a.dskin + ((size_t)ray * a.S + s0) * a.ldd, nrows, a.ldd, B, L, lane);
+  build_ctx(a, ray, ctx, bone_s);
+  for (int i = threadIdx.x; i < B * ACC_STRIDE; i += SKIN_THREADS) acc[i] = 0.f;
+  __syncthreads();
+  const bool live = lane < nrows;
+  const size_t pi = (size_t)ray * a.S + (live ? s0 + lane : 0);
+  const float px = __ldg(a.pts + pi * 3), py = __ldg(a.pts + pi * 3 + 1), pz = __ldg(a.pts + pi * 3 + 2);
+  float g3[3] = {0.f, 0.f, 0.f};
+  if (live) { g3[0] = __ldg(a.gy + pi * 3); g3[1] = __ldg(a.gy + pi * 3 + 1); g3[2] = __ldg(a.gy + pi * 3 + 2); }
+  float* Lr = L + lane * LT;
+  const bool has_dl = a.dskin != nullptr;
+  // pass 1: logits, their maximum, and the arg-max bone's Gaussian logit (reference point of d/d skin_aux[0])
+  float mx = -INFINITY, gref = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float lg = bone_logit(ctx + b * CTX_STRIDE, px, py, pz);
+    const float l = (has_dl && live) ? lg + Lr[b] : lg;
+    Lr[b] = l;
+    if (l > mx) { mx = l; gref = lg; }
+  }
+  // pass 2: exp, sum, blend
+  float sum = 0.f, bl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < B; ++b) {
+    const float e = expf(Lr[b] - mx);
+    Lr[b] = e;
+    sum += e;
+    const float4 c0 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 12);
+    const float4 c1 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 16);
+    bl[0] = fmaf(e, c0.x, bl[0]); bl[1] = fmaf(e, c0.y, bl[1]); bl[2] = fmaf(e, c0.z, bl[2]); bl[3] = fmaf(e, c0.w, bl[3]);
+    bl[4] = fmaf(e, c1.x, bl[4]); bl[5] = fmaf(e, c1.y, bl[5]); bl[6] = fmaf(e, c1.z, bl[6]); bl[7] = fmaf(e, c1.w, bl[7]);
+  }
+  const float inv_sum = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bl[i] *= inv_sum;
+  float gp[3], gb[8];
+  {
+    const float n = sqrtf(bl[0] * bl[0] + bl[1] * bl[1] + bl[2] * bl[2] + bl[3] * bl[3]);
+    const float inv_n = live ? 1.0f / n : 0.f;
+    float c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = bl[i] * inv_n;
+    dq_apply_bwd(c, inv_n, px, py, pz, g3, gp, gb);
+  }
+  // pass 3: gs = sum_b W_b gW_b with gW_b = gb . dq_b
+  float gs = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float4 c0 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 12);
+    const float4 c1 = *reinterpret_cast<const float4*>(ctx + b * CTX_STRIDE + 16);
+    const float gw = gb[0] * c0.x + gb[1] * c0.y + gb[2] * c0.z + gb[3] * c0.w + gb[4] * c1.x + gb[5] * c1.y +
+                     gb[6] * c1.z + gb[7] * c1.w;
+    gs = fmaf(Lr[b] * inv_sum, gw, gs);
+  }
+  // pass 4: logit gradients and the per-ray / per-bone accumulands [gA(9) | gc(3) | gdq(8)]
+  float gaux = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* cb = ctx + b * CTX_STRIDE;
+    const float4 r0 = *reinterpret_cast<const float4*>(cb);
+    const float4 r1 = *reinterpret_cast<const float4*>(cb + 4);
+    const float4 r2 = *reinterpret_cast<const float4*>(cb + 8);
+    const float4 c0 = *reinterpret_cast<const float4*>(cb + 12);
+    const float4 c1 = *reinterpret_cast<const float4*>(cb + 16);
+    const float gw = gb[0] * c0.x + gb[1] * c0.y + gb[2] * c0.z + gb[3] * c0.w + gb[4] * c1.x + gb[5] * c1.y +
+                     gb[6] * c1.z + gb[7] * c1.w;
+    const float w = live ? Lr[b] * inv_sum : 0.f;
+    const float gl = w * (gw - gs);
+    Lr[b] = gl;
+    const bool any = (gl != 0.f) || (w != 0.f);
+    if (!__any_sync(0xffffffffu, any)) continue;   // exact zeros from every sample of the warp: nothing to add
+    const float dx = r0.w - px, dy = r1.w - py, dz = r2.w - pz;
+    const float u0 = r0.x * dx + r0.y * dy + r0.z * dz;
+    const float u1 = r1.x * dx + r1.y * dy + r1.z * dz;
+    const float u2 = r2.x * dx + r2.y * dy + r2.z * dz;
+    const float lgauss = -(u0 * u0 + u1 * u1 + u2 * u2);
+    gaux = fmaf(gl, lgauss - gref, gaux);
+    const float g0 = -2.f * gl * u0, g1 = -2.f * gl * u1, g2 = -2.f * gl * u2;
+    const float gdx = r0.x * g0 + r1.x * g1 + r2.x * g2;   // A^T gu
+    const float gdy = r0.y * g0 + r1.y * g1 + r2.y * g2;
+    const float gdz = r0.z * g0 + r1.z * g1 + r2.z * g2;
+    gp[0] -= gdx; gp[1] -= gdy; gp[2] -= gdz;
+    float* Rl = R + lane;
+    Rl[0 * RT] = g0 * dx; Rl[1 * RT] = g0 * dy; Rl[2 * RT] = g0 * dz;
+    Rl[3 * RT] = g1 * dx; Rl[4 * RT] = g1 * dy; Rl[5 * RT] = g1 * dz;
+    Rl[6 * RT] = g2 * dx; Rl[7 * RT] = g2 * dy; Rl[8 * RT] = g2 * dz;
+    Rl[9 * RT] = gdx; Rl[10 * RT] = gdy; Rl[11 * RT] = gdz;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Rl[(12 + i) * RT] = w * gb[i];
+    __syncwarp();
+    if (lane < ACC_STRIDE) {
+      const float4* row = reinterpret_cast<const float4*>(R + lane * RT);
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 x = row[k];
+        t0 += x.x; t1 += x.y; t2 += x.z; t3 += x.w;
+      }
+      const float t = (t0 + t1) + (t2 + t3);
+      if (t != 0.f) atomicAdd(&acc[b * ACC_STRIDE + lane], t);
+    }
+    __syncwarp();
+  }
+  if (live) { a.gpts[pi * 3] = gp[0]; a.gpts[pi * 3 + 1] = gp[1]; a.gpts[pi * 3 + 2] = gp[2]; }
+  if (a.gdskin && nrows > 0) {
+    __syncwarp();
+    unstage_rows(a.gdskin + ((size_t)ray * a.S + s0) * a.ldd, nrows, a.ldd, B, L, lane);
+  }
+  __syncthreads();
+
+  // ---- per-bone epilogue (as in the general kernel) ----
+  const int b = threadIdx.x;
+  if (b < B) {
+    const float kappa = 1000.0f * expf(a.skin_aux[0]);
+    const float* bone = a.bones + ((size_t)(a.bones_per_ray ? ray : 0) * B + b) * 10;
+    float bn[10], rr[8], gbone[10], grt[8];
+    for (int i = 0; i < 10; ++i) bn[i] = bone[i];
+    const float* r = a.rts + ((size_t)ray * B + b) * 8;
+    for (int i = 0; i < 8; ++i) rr[i] = r[i];
+    float unused = 0.f;
+    ray_bone_setup_bwd(bn, rr, a.deform, a.invert, kappa, bone_s + b * 10, acc + b * ACC_STRIDE, gbone, grt, &unused);
+    if (a.grts) {
+      float* o = a.grts + ((size_t)ray * B + b) * 8;
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, grt[i]);
+    }
+    if (a.gbones) {
+      float* o = a.gbones + ((size_t)(a.bones_per_ray ? ray : 0) * B + b) * 10;
+      for (int i = 0; i < 10; ++i)
+        if (gbone[i] != 0.f) atomicAdd(o + i, gbone[i]);
+    }
+  }
+  if (a.gaux) {
+    const float t = warp_sum(gaux);
+    if (lane == 0) red[warp] = t;
     __syncthreads();
     if (threadIdx.x == 0) {
       float tot = 0.f;
@@ -224,6 +482,10 @@ extern "C" int moda_skin_warp_fwd(const float* pts, const float* bones, const fl
   if (int e = skin_check(a)) return e;
   MODA_REQUIRE(!y || rts, "skin_warp_fwd: y requested without rts");
   if (R == 0) return 0;
+  if (B <= FAST_BONES && y && rts && !skin_in && !skin_out) {
+    skin_warp_fwd_fast_kernel<<<dim3(R, cdiv(S, SKIN_THREADS)), SKIN_THREADS, 0, stream>>>(a);
+    return check_launch("skin_warp_fwd");
+  }
   // grid.y is limited to 65535: fold rays beyond that into several launches
   for (int r0 = 0; r0 < R; r0 += 65535) {
     SkinArgs c = a;
@@ -254,6 +516,10 @@ extern "C" int moda_skin_warp_bwd(const float* pts, const float* bones, const fl
   a.gbones = gbones; a.gaux = gaux;
   if (int e = skin_check(a)) return e;
   if (R == 0) return 0;
+  if (B <= FAST_BONES && gy && rts && gpts && !skin_in && !gskin && !gskin_in) {
+    skin_warp_bwd_fast_kernel<<<dim3(R, cdiv(S, SKIN_THREADS)), SKIN_THREADS, 0, stream>>>(a);
+    return check_launch("skin_warp_bwd");
+  }
   for (int r0 = 0; r0 < R; r0 += 65535) {
     SkinArgs c = a;
     const int rc = (R - r0 < 65535) ? R - r0 : 65535;

@@ -103,6 +103,33 @@ __global__ void pack16_kernel(const float* __restrict__ in, int ld_in, int rows,
   if (out_lo) out_lo[o] = __float2half_rn(v - __half2float(h));
 }
 
+// several pack16 blocks of one packed-weight matrix in ONE launch (blockIdx.y = job): the per-step repacking of
+// a network's weights is a few dozen tiny blocks, which as separate launches cost more than the copies themselves
+constexpr int MAX_PACK_JOBS = 16;
+struct PackJob {
+  const float* in;
+  __half* out;
+  __half* out_lo;
+  int ld_in, rows, cols, col0, out_rows, width, transpose;
+};
+struct PackJobs {
+  PackJob j[MAX_PACK_JOBS];
+  int ld_out;
+};
+__global__ void pack16_multi_kernel(const __grid_constant__ PackJobs js) {
+  const PackJob& j = js.j[blockIdx.y];
+  const int total = j.out_rows * j.width;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int orow = t / j.width, ocol = t % j.width;
+    const int r = j.transpose ? ocol : orow, c = j.transpose ? orow : ocol;
+    const float v = (r < j.rows && c < j.cols) ? j.in[(size_t)r * j.ld_in + j.col0 + c] : 0.f;
+    const __half h = __float2half_rn(v);
+    const size_t o = (size_t)orow * js.ld_out + ocol;
+    j.out[o] = h;
+    if (j.out_lo) j.out_lo[o] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // fp32 (M, cols; row pitch ld_in) * (*scale) -> fp16 (hi, lo) pair of width `width` (zero padded), pitch ld_out
 __global__ void split16_kernel(const float* __restrict__ in, int ld_in, int cols, const float* scale_p,
                                __half* __restrict__ hi, __half* __restrict__ lo, int ld_out, int width, long long M) {
@@ -345,6 +372,34 @@ extern "C" int moda_pack16(const float* in, int ld_in, int rows, int cols, int c
       in, ld_in, rows, cols, col0, reinterpret_cast<__half*>(out16), reinterpret_cast<__half*>(out16_dup),
       reinterpret_cast<__half*>(out16_lo), ld_out, out_rows, width, transpose);
   return check_launch("pack16");
+}
+
+extern "C" int moda_pack16_multi(int n, const float* const* in, const int* ld_in, const int* rows, const int* cols,
+                                 const int* col0, void* const* out16, void* const* out16_lo, int ld_out,
+                                 const int* out_rows, const int* width, const int* transpose, cudaStream_t stream) {
+  MODA_REQUIRE(n >= 0 && in && ld_in && rows && cols && col0 && out16 && out16_lo && out_rows && width && transpose,
+               "pack16_multi: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += MAX_PACK_JOBS) {
+    PackJobs js;
+    memset(&js, 0, sizeof(js));
+    js.ld_out = ld_out;
+    const int m = (n - i0 < MAX_PACK_JOBS) ? n - i0 : MAX_PACK_JOBS;
+    int biggest = 0;
+    for (int k = 0; k < m; ++k) {
+      const int i = i0 + k;
+      MODA_REQUIRE(in[i] && out16[i] && rows[i] > 0 && cols[i] > 0 && ld_out >= width[i] && width[i] > 0 && out_rows[i] > 0,
+                   "pack16_multi: bad job %d", i);
+      MODA_REQUIRE(transpose[i] ? (width[i] >= rows[i] && out_rows[i] >= cols[i]) : (width[i] >= cols[i] && out_rows[i] >= rows[i]),
+                   "pack16_multi: output block of job %d too small", i);
+      PackJob& j = js.j[k];
+      j.in = in[i]; j.out = reinterpret_cast<__half*>(out16[i]); j.out_lo = reinterpret_cast<__half*>(out16_lo[i]);
+      j.ld_in = ld_in[i]; j.rows = rows[i]; j.cols = cols[i]; j.col0 = col0[i]; j.out_rows = out_rows[i];
+      j.width = width[i]; j.transpose = transpose[i];
+      if (out_rows[i] * width[i] > biggest) biggest = out_rows[i] * width[i];
+    }
+    pack16_multi_kernel<<<dim3(cdiv(biggest, 256), m), 256, 0, stream>>>(js);
+  }
+  return check_launch("pack16_multi");
 }
 
 extern "C" int moda_split16(const float* in, int ld_in, int cols, const float* scale, void* hi, void* lo, int ld_out,

@@ -388,12 +388,7 @@ class SkinWarpFn(torch.autograd.Function):
         gy = f32(gy) if gy is not None else None
         gskin = f32(gskin) if gskin is not None else None
         gpts = torch.empty_like(pts)
-        if dsk is None:
-            gdsk = None
-        elif ldd:
-            gdsk = torch.zeros_like(dsk)  # pitched: pad columns must stay zero
-        else:
-            gdsk = torch.empty_like(dsk)
+        gdsk = torch.empty_like(dsk) if dsk is not None else None  # the kernel zeroes the pad columns of pitched rows
         gsin = torch.empty_like(sin) if sin is not None else None
         grts = torch.zeros_like(rts_) if rts_ is not None else None
         gbones = torch.zeros_like(bones)
