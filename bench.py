@@ -276,6 +276,176 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Secondary workloads (BASELINE.json configs[3] and configs[4]); the default line stays the training step.
+
+def _event_ms(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_dqs(args):
+    """BASELINE configs[3]: 16.78 M points (131072 rays x 128) x 25 Gaussian bones, per-ray dual quaternions;
+    Gaussian skinning + backward warp, then skinning + forward warp (geom_utils.py:202-302, 372-517), forward and
+    backward timed separately, without and with streamed delta-logits (pitch 32 fp32)."""
+    from moda_b200 import synth, geom_utils as G, _lib
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
+    R, S, B = args.dqs_rays, SAMPLES, BONES
+    sp = synth.make_skin_problem(R, S, seed=0)
+    xyz = sp["xyz"].to(dev).requires_grad_(True)
+    bones = sp["bones_rst"].to(dev).requires_grad_(True)
+    aux = sp["skin_aux"].to(dev).requires_grad_(True)
+    rts = sp["bone_rts"].to(dev).requires_grad_(True)
+    P = R * S
+    peaks, src = _peaks()
+    out = {}
+    for tag, with_delta in (("no_delta", False), ("delta_streamed", True)):
+        d_bw = d_fw = None
+        if with_delta:
+            d_bw = (0.1 * torch.randn(R, S, 32, device=dev)).requires_grad_(True)
+            d_fw = (0.1 * torch.randn(R, S, 32, device=dev)).requires_grad_(True)
+            with torch.no_grad():
+                d_bw[..., B:] = 0
+                d_fw[..., B:] = 0
+        state = {}
+
+        def fwd():
+            can = G.warp_points(xyz, bones, rts, aux, d_bw, backward=True)
+            cyc = G.warp_points(can, bones, rts, aux, d_fw, backward=False)
+            state["y"] = (can, cyc)
+
+        g1, g2 = torch.randn(R, S, 3, device=dev), torch.randn(R, S, 3, device=dev)
+
+        def bwd():
+            can, cyc = state["y"]
+            leaves = [xyz, bones, aux, rts] + ([d_bw, d_fw] if with_delta else [])
+            torch.autograd.grad([can, cyc], leaves, [g1, g2], retain_graph=True)
+
+        ms_f = _event_ms(fwd, args.steps, max(args.warmup, 3))
+        ms_b = _event_ms(bwd, args.steps, max(args.warmup, 3))
+        # algorithmic bytes per point (SURVEY.md 8(d)): forward 12 in + 2 x 12 out + 1800/128 per-ray bone data
+        # [+ 2 x 25 x 4 delta]; backward: xyz, xyz_can, 2 gradients in, 1 out = 60 + 14 [+ 2 x 2 x 25 x 4 read+write]
+        bf = 50.1 + (200.0 if with_delta else 0.0)
+        bb = 74.0 + (400.0 if with_delta else 0.0)
+        out[tag] = {"fwd_ms": round(ms_f, 3), "bwd_ms": round(ms_b, 3),
+                    "fwd_gpts_s": round(P / ms_f / 1e6, 2), "bwd_gpts_s": round(P / ms_b / 1e6, 2),
+                    "fwd_hbm_frac": round(bf * P / (ms_f * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                    "bwd_hbm_frac": round(bb * P / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                    "alg_bytes_per_point": {"fwd": bf, "bwd": bb}}
+        del state, d_bw, d_fw
+    cpu = None
+    if not args.no_cpu:
+        from oracle import restated as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Rc = 2048
+        spc = synth.make_skin_problem(Rc, S, seed=0)
+        best = None
+        for i in range(3):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.skin_warp_roundtrip(spc["bones_rst"], spc["bone_rts"].reshape(Rc, B, 8), spc["skin_aux"], spc["xyz"])
+            dt = time.perf_counter() - t0
+            if i:
+                best = dt if best is None else min(best, dt)
+        cpu = {"value": round(Rc * S / best / 1e9, 5), "unit": "Gpts/s", "cores": cores, "kind": "port",
+               "sample": "%d points forward (both warps, no delta), best of 2 after 1 warm-up" % (Rc * S)}
+    a = out["delta_streamed"]
+    print(json.dumps({"metric": "DQ skinning Gpts/s (bw + fw warp, 25 Gaussian bones)", "value": out["no_delta"]["fwd_gpts_s"],
+                      "unit": "Gpts/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+                      "ms_per_step": out["no_delta"]["fwd_ms"], "higher_is_better": True, "scaling": "replicas only",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "DQ skinning microbench: %d points x %d bones, fw+bw warp" % (P, B),
+                                 "l2_policy": "working set (>0.6 GB) exceeds the 126 MB L2"},
+                      "variants": out,
+                      "roofline": {"bound": "hbm", "kernel": "skin_warp_fwd_kernel x2 with streamed delta logits",
+                                   "achieved": round(a["fwd_hbm_frac"] * peaks["hbm_gbs"], 1), "peak": peaks["hbm_gbs"],
+                                   "unit": "GB/s", "frac": a["fwd_hbm_frac"], "peak_source": src, "traffic": None},
+                      "cpu_baseline": cpu}))
+
+
+def run_grid(args):
+    """BASELINE configs[4]: canonical density on a G^3 lattice (train_utils.py:1377-1404), x-slabs per rank."""
+    import torch.distributed as dist
+    from moda_b200 import synth, models as MM, _lib
+    from moda_b200.extract import density_grid
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
+    Gs = args.grid
+    prob = synth.make_problem(8, seed=0)
+    models, emb, _ = MM.build_models(prob, dev, requires_grad=False)
+    lo, hi = rank * Gs // world, (rank + 1) * Gs // world
+    full = torch.empty(Gs, Gs, Gs, device=dev) if world > 1 else None
+
+    def step():
+        vol = density_grid(models["coarse"], Gs, (0.3, 0.3, 0.3), emb["xyz"], x_range=(lo, hi))
+        if world > 1:
+            dist.all_gather_into_tensor(full, vol)
+        return vol
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    if rank == 0:
+        peaks, src = _peaks()
+        pts = Gs ** 3
+        flop = pts * 491264 * 2.0
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * world
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import restated as O
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            Gc = 48
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.density_grid(prob["coarse"], Gc, (0.3, 0.3, 0.3))
+            dt = time.perf_counter() - t0
+            cpu = {"value": round(Gc ** 3 / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
+                   "sample": "%d^3 grid (%.2f s), one pass" % (Gc, dt)}
+        print(json.dumps({"metric": "density-grid Mpts/s (sigma_only nerf_coarse, %d^3)" % Gs, "value": round(pts / ms / 1e3, 1),
+                          "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+                          "config": {"workload": "mesh-extraction density query, %d^3 lattice, x-slabs over %d rank(s)" % (Gs, world)},
+                          "roofline": {"bound": "tensor", "kernel": "chain_kernel sigma-only program", "achieved": round(flop / (ms * 1e-3) / 1e12, 2),
+                                       "peak": peak, "unit": "TFLOP/s", "frac": round(flop / (ms * 1e-3) / 1e12 / peak, 4),
+                                       "peak_source": src + " bf16 sustained", "traffic": None},
+                          "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,7 +455,15 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--cpu-rays", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "dqs", "grid"],
+                    help="train: the headline training step (default); dqs / grid: BASELINE configs[3] / configs[4]")
+    ap.add_argument("--dqs-rays", type=int, default=131072)
+    ap.add_argument("--grid", type=int, default=256)
     args = ap.parse_args()
+    if args.workload == "dqs":
+        return run_dqs(args)
+    if args.workload == "grid":
+        return run_grid(args)
     if args.impl == "reference":
         args.steps = min(args.steps, 3)
         run_reference(args)

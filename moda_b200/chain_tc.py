@@ -116,6 +116,22 @@ def pack_trunk_bwd(params):
     return pk.run()
 
 
+def trunk_sigma(xyz, win, params):
+    """Density only, no gradient (the grid query of mesh extraction: nnutils/train_utils.py:1377-1404 ->
+    nerf.py:176-180 with sigma_only=True): xyz (P,3) -> sigma (P,1) through ``moda_chain_trunk_sigma``."""
+    xyz = f32(xyz).reshape(-1, 3)
+    P, dev = xyz.shape[0], xyz.device
+    params = [f32(p.detach()) for p in params]
+    Ws, bs = params[20], params[21]
+    wa, _ = _win_array(win)
+    wpack = pack_trunk_fwd(params)
+    biases = (ctypes.c_void_p * 8)(*[ptr(params[2 * i + 1]) for i in range(8)])
+    sigma = torch.empty(P, 1, device=dev, dtype=torch.float32)
+    call("moda_chain_trunk_sigma", ptr(xyz), P, len(win), wa, ptr(wpack), biases, ptr(_al16(Ws)), ptr(bs), ptr(sigma),
+         stream())
+    return sigma
+
+
 class TrunkChainFn(torch.autograd.Function):
     """apply(xyz (P,3), dir_embedded (R,cd), env_code (R,ce) | None, S, win, *params) -> raw (P,4) [rgb | sigma]."""
 

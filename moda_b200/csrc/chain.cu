@@ -168,7 +168,11 @@ __device__ __forceinline__ void trace_rec(long long* tr, int ev, int a, int b) {
     tr[region] = i + 1;
   }
 }
+#ifdef MODA_CHAIN_TRACE
 #define MODA_TR(on, ev, a, b) do { if (on) trace_rec(pg.trace, (ev), (a), (b)); } while (0)
+#else
+#define MODA_TR(on, ev, a, b) do { } while (0)   // product build: no trace code in the hot loops (tools/build_variant.sh trace -DMODA_CHAIN_TRACE)
+#endif
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -219,14 +223,14 @@ struct EpiCtx {
 // chunk-major with the TMEM load of the next sub-block in flight; after each completed 64-column chunk:
 // proxy fence, then the warp counts itself in on the chunk's mbarrier (no CTA-wide barrier: warps drift freely).  NH warps share a TMEM lane quarter: warp h owns the
 // sub-blocks {h, h + NH, ..} < 4 of every chunk.
-template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
+template <int CF, int CN, int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, const Maps& maps, const Step& st, const EpiCtx& cx,
                                          uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1, float& hs2,
                                          unsigned long long pm0, unsigned long long pm1) {
   constexpr int SPC = 4 / NH;                  // sub-blocks per chunk for this warp
   const int F = (CF >= 0) ? CF : Frt;   // CF >= 0: flavour known at compile time (straight-line hot paths)
   const bool MMA = !(F & (E_LOAD16 | E_LOAD32));
-  const int n = st.n;
+  const int n = (CN > 0) ? CN : st.n;   // CN > 0: width known at compile time -> the sub-block loop unrolls completely
   const int nch = n >> 6;
   const int nsub = nch * SPC;
   const uint32_t t_addr = cx.tmem_row + acc_col;
@@ -390,10 +394,20 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       }
     }
   };
+  if constexpr (CN > 0) {
+    // sub-block index, columns, chunk addresses and mask-word positions all fold to constants
+    constexpr int NSUB = (CN >> 6) * SPC;
+#pragma unroll
+    for (int i2 = 0; i2 < NSUB; i2 += 2) {
+      sub(i2, va, vb);
+      if (i2 + 1 < NSUB) sub(i2 + 1, vb, va);
+    }
+  } else {
 #pragma unroll 1
-  for (int i2 = 0; i2 < nsub; i2 += 2) {
-    sub(i2, va, vb);
-    if (i2 + 1 < nsub) sub(i2 + 1, vb, va);
+    for (int i2 = 0; i2 < nsub; i2 += 2) {
+      sub(i2, va, vb);
+      if (i2 + 1 < nsub) sub(i2 + 1, vb, va);
+    }
   }
   if (F & E_MASK_OUT) {
     *mp = m0;
@@ -402,18 +416,18 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
 }
 
 // hot flavours inline (straight-line code inside the kernel's register allocation) ...
-template <int CF, int NH, int ACC_STRIDE, int EPI_THREADS>
+template <int CF, int CN, int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __forceinline__ void run_step(const int Frt, const Program& pg, const Maps& maps, const Step& st,
                                          const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0, float& hs1,
                                          float& hs2, unsigned long long pm0, unsigned long long pm1) {
-  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+  run_step_body<CF, CN, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
 }
 // ... the run-time-flag version (a few steps per tile) out of line, so that it does not weigh on them
 template <int NH, int ACC_STRIDE, int EPI_THREADS>
 __device__ __noinline__ void run_step_generic(const int Frt, const Program& pg, const Maps& maps, const Step& st,
                                               const EpiCtx& cx, uint32_t acc_col, uint64_t* ready, float& hs0,
                                               float& hs1, float& hs2, unsigned long long pm0, unsigned long long pm1) {
-  run_step_body<-1, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+  run_step_body<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(Frt, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
 }
 // the flavours that run once or twice per tile: straight-line too, but out of line, each with its own register
 // allocation (inlined next to the hot flavour they push it into spilling)
@@ -422,7 +436,7 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
                                            uint32_t acc_col, uint64_t* ready, float* hs, unsigned long long pm0,
                                            unsigned long long pm1) {
   float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
-  run_step_body<CF, NH, ACC_STRIDE, EPI_THREADS>(CF, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+  run_step_body<CF, 0, NH, ACC_STRIDE, EPI_THREADS>(CF, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
   if (CF & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs[0] = hs0; hs[1] = hs1; hs[2] = hs2; }
 }
 
@@ -637,7 +651,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         constexpr int HOT_FWD = E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | LO;
         constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
 #define MODA_FLAVOUR(FL) \
-  if (flags == (FL)) run_step<(FL), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
+  if (flags == (FL) && st.n == ACC_STRIDE) run_step<(FL), ACC_STRIDE, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
 #define MODA_COLD(FL) \
   if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs, pm0, pm1); \
                        if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
@@ -648,10 +662,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         // the flavour that makes up most of a pass inline, the rest through the inlined run-time-flag version
         if constexpr (PROG == P_FWD) {
           MODA_FLAVOUR(HOT_FWD)
-          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         } else {
           MODA_FLAVOUR(HOT_BWD)
-          run_step<-1, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         }
 #else
         if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
@@ -822,6 +836,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             s_dbg[4] = it * 1000 + s * 10 + (d % 10); s_dbg[5] = 0;
             wait_or_trap<0>(&ready[c], gen & 1);
             s_dbg[5] = 1;
+            MODA_TR(pg.trace && blockIdx.x == 0 && it == 2, 20, s, c);
             if (pg.duty[d].map >= 0) {
               tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)(c * CHUNK_BYTES), (int)pg.duty[d].col * 64,
                                tile * TILE_M);
@@ -832,6 +847,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           }
           s_dbg[5] = 2;
           if (any) bulk_wait_read0();
+          MODA_TR(pg.trace && blockIdx.x == 0 && it == 2 && any, 21, s, 0);
           if (work) mbar_arrive(stores_done);
           s_dbg[5] = 3;
         }

@@ -88,6 +88,11 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
         fn = chain_tc.SkinChainFn if config.fused else skin_tc.SkinMlpTcFn
         out = fn.apply(pts2, inputs[1], nbins, win, *model.param_list()).reshape(Bn, nbins, 32)
         return out if _pitched else out[..., :model.out_channels]
+    # density-only grid query (mesh extraction): the sigma program of the chain kernel, inference only
+    if (config.precision == "fp16" and config.fused and sigma_only and len(segs) == 1 and segs[0][0] == SEG_PE and k == 3
+            and embed_xyz.N_freqs == 10 and trunk_tc.supported(model, model.in_channels_dir)
+            and not (torch.is_grad_enabled() and (pts2.requires_grad or any(p.requires_grad for p in model.parameters())))):
+        return chain_tc.trunk_sigma(pts2, win, model.param_list()).reshape(Bn, nbins, 1)
     xyz_segs, dir_segs = _split_segments(segs, cx)
     if len(xyz_segs) > 2 or len(dir_segs) > 2:
         raise NotImplementedError("more than two column segments per input group")

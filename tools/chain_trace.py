@@ -43,7 +43,7 @@ rec.sort(key=lambda r: r[3])
 t0 = rec[0][3]
 names = {0: "mma  wait acc_free", 1: "mma  step start", 2: "mma  A chunk ready", 3: "mma  W stage full", 4: "mma  step committed",
          10: "epi0 acc_full seen", 11: "epi0 chunk written", 12: "epi0 store-read waited", 13: "epi0 barrier passed",
-         20: "epiL acc_full seen", 21: "epiL chunk written", 22: "epiL -", 23: "epiL barrier passed",
+         20: "stor chunk ready seen", 21: "stor smem read done",
          30: "pe   computed", 31: "pe   chunk free"}
 for ev, a, bb, t in rec:
     if ev >= 40:
