@@ -65,6 +65,27 @@ def _small_linear(code, Wl, col0, bias, n):
     return rb
 
 
+def _grad_targets(refs, params):
+    """One accumulation buffer per parameter plus what backward() hands to autograd for it.  The weight-gradient
+    kernels all accumulate (atomic +=).  A parameter re-homed by ``parallel.FlatParams`` carries its gradient as a
+    view of the flat gradient buffer ("gradients are written into a flat fp32 buffer whose slices
+    are exposed as .grad views"): the kernels add straight into that view and autograd receives None, which saves a
+    zero fill and an AccumulateGrad add per parameter and step.  Any other parameter gets a fresh zero tensor that is
+    returned to autograd as usual."""
+    tg, ret = [], []
+    for r, q in zip(refs, params):
+        gr = r.grad if getattr(r, "_moda_grad_inplace", False) else None
+        if (gr is not None and gr.dtype == torch.float32 and gr.is_contiguous() and gr.device == q.device
+                and gr.shape == q.shape):
+            tg.append(gr)
+            ret.append(None)
+        else:
+            z = torch.zeros_like(q)
+            tg.append(z)
+            ret.append(z)
+    return tg, ret
+
+
 def _loss_scale(g):
     scale2 = torch.empty(2, device=g.device, dtype=torch.float32)
     work = torch.empty(1, device=g.device, dtype=torch.int32)
@@ -140,6 +161,7 @@ class TrunkChainFn(torch.autograd.Function):
         xyz_shape = xyz.shape
         xyz = f32(xyz).reshape(-1, 3)
         P, dev = xyz.shape[0], xyz.device
+        ctx.param_refs = params
         params = [f32(p) for p in params]
         need_bw = any(ctx.needs_input_grad)
         Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
@@ -179,7 +201,7 @@ class TrunkChainFn(torch.autograd.Function):
         P, dev = xyz.shape[0], xyz.device
         R, cc = code.shape
         Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
-        g = [torch.zeros_like(p) for p in params]
+        g, gret = _grad_targets(ctx.param_refs, params)
         graw = f32(graw).reshape(P, 4)
         sc, isc = _loss_scale(graw)
         # heads: d_dfe (scaled, masked by dfe > 0), gsig, and the head parameter gradients
@@ -218,7 +240,7 @@ class TrunkChainFn(torch.autograd.Function):
         ctx.act = None
         gdir = gcode[:, :cd].contiguous()
         genv = gcode[:, cd:].contiguous() if has_env else None
-        return (gxyz.reshape(xyz_shape), gdir, genv, None, None) + tuple(g)
+        return (gxyz.reshape(xyz_shape), gdir, genv, None, None) + tuple(gret)
 
 
 # -------------------------------------------------------------------------------------------------- nerf_skin
@@ -260,6 +282,7 @@ class SkinChainFn(torch.autograd.Function):
         pshape = pts.shape
         pts = f32(pts).reshape(-1, 3)
         P, dev = pts.shape[0], pts.device
+        ctx.param_refs = params
         params = [f32(p) for p in params]
         code = f32(code).reshape(-1, code.shape[-1])
         Rc, nc = code.shape
@@ -305,7 +328,7 @@ class SkinChainFn(torch.autograd.Function):
         P, dev = pts.shape[0], pts.device
         Rc, nc = code.shape
         W = [params[2 * i] for i in range(5)]
-        g = [torch.zeros_like(p) for p in params]
+        g, gret = _grad_targets(ctx.param_refs, params)
         gout = f32(gout).reshape(P, 32)
         sc, isc = _loss_scale(gout)
         wpackT = pack_skin_bwd(params, nc)
@@ -316,31 +339,34 @@ class SkinChainFn(torch.autograd.Function):
              ptr(dY), ptr(d_pe), stream())
         gcode = torch.zeros_like(code)
 
-        def code_part(dYl, Wl, gW, gb):
-            """hoisted pose-code columns of layers 1 / 5: everything happens at ray (or single-row) level in fp32"""
-            rbg = torch.zeros(Rc, 64, device=dev, dtype=torch.float32)
-            if Rc == 1:
-                call("moda_colsum16", ptr(dYl), WD, ptr(rbg), P, WD, ptr(isc), stream())
-            else:
+        def code_part(dYl, Wl, gW, gb, rbg=None):
+            """hoisted pose-code columns of layers 1 / 5: everything happens at ray (or single-row) level in fp32.
+            rbg: per-ray (or, for a single shared code row, whole-batch) sums of dYl; for the shared row they come
+            for free as the bias-gradient output of the layer's weight-gradient kernel."""
+            if rbg is None:
+                rbg = torch.empty(Rc, 64, device=dev, dtype=torch.float32)
                 call("moda_segsum16", ptr(dYl), WD, ptr(rbg), Rc, rep, 64, ptr(isc), 0, stream())
             call("moda_linear_dgrad", Rc, 64, nc, ptr(rbg), 64, ptr(Wl), Wl.shape[1], 63, None, 0, 1, ptr(gcode), nc,
                  stream())
             call("moda_linear_wgrad", Rc, 64, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(nc), _one(nc), _one(0), _one(1),
                  None, 0, ptr(rbg), 64, ptr(gW), Wl.shape[1], 63, ptr(gb), stream())
 
+        shared_row = Rc == 1
+        rb4 = torch.zeros(1, 64, device=dev, dtype=torch.float32) if shared_row else None
+        rb0 = torch.zeros(1, 64, device=dev, dtype=torch.float32) if shared_row else None
         _wgrad(G, WD, dfe, WD, P, g[16], 0, oc, 32, isc, dbias=g[17])
         _wgrad(d_dfe, WD, fin, WD, P, g[12], 0, 32, 64, isc, dbias=g[13])
         _wgrad(d_fin, WD, H[4], WD, P, g[10], 0, 64, 64, isc, dbias=g[11])
-        _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc)
+        _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc, dbias=rb4)
         _wgrad(dY[4], WD, H[3], WD, P, g[8], 63 + nc, 64, 64, isc)
-        code_part(dY[4], W[4], g[8], g[9])
+        code_part(dY[4], W[4], g[8], g[9], rb4)
         for i in (3, 2, 1):
             _wgrad(dY[i], WD, H[i - 1], WD, P, g[2 * i], 0, 64, 64, isc, dbias=g[2 * i + 1])
-        _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc)
-        code_part(dY[0], W[0], g[0], g[1])
+        _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc, dbias=rb0)
+        code_part(dY[0], W[0], g[0], g[1], rb0)
         gpts = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
         call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0, stream())
         ctx.act = None
-        g[14] = g[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
-        return (gpts.reshape(pshape), gcode, None, None) + tuple(g)
+        gret[14] = gret[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
+        return (gpts.reshape(pshape), gcode, None, None) + tuple(gret)

@@ -443,6 +443,18 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
+#ifndef MODA_TRUNK_EPI
+#define MODA_TRUNK_EPI 8   // epilogue warps of the 256-wide chains (8 or 16)
+#endif
+#ifndef MODA_SKIN_BWD_CTAS
+#define MODA_SKIN_BWD_CTAS 2   // resident CTAs per SM of the 64-wide adjoint chain (its 2 chunks leave room for 3)
+#endif
+#ifndef MODA_SKIN_BWD_STAGES
+#define MODA_SKIN_BWD_STAGES 8
+#endif
+#ifndef MODA_SKIN_EPI
+#define MODA_SKIN_EPI 4    // epilogue warps of the 64-wide chains (4 or 8)
+#endif
 constexpr int P_FWD = 0, P_BWD = 1;   // which set of straight-line epilogue flavours a kernel instance carries
 
 template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG>
@@ -655,20 +667,23 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 #define MODA_COLD(FL) \
   if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs, pm0, pm1); \
                        if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
-#ifndef MODA_CHAIN_DISPATCH
-#define MODA_CHAIN_DISPATCH 0
+        // Forward programs: the flavour that makes up most of a pass inline, the rest through the inlined
+        // run-time-flag version (measured: out-of-line cold flavours cost the forward 8 %).  Adjoint programs: every
+        // flavour straight-line, the rare ones out of line (trunk bwd 2.08 -> 2.01 ms, skin bwd 0.62 -> 0.54 ms).
+#ifndef MODA_CHAIN_DISPATCH_FWD
+#define MODA_CHAIN_DISPATCH_FWD 0
 #endif
-#if MODA_CHAIN_DISPATCH == 0
-        // the flavour that makes up most of a pass inline, the rest through the inlined run-time-flag version
-        if constexpr (PROG == P_FWD) {
+#ifndef MODA_CHAIN_DISPATCH_BWD
+#define MODA_CHAIN_DISPATCH_BWD 1
+#endif
+        if constexpr (PROG == P_FWD && !MODA_CHAIN_DISPATCH_FWD) {
           MODA_FLAVOUR(HOT_FWD)
+          MODA_FLAVOUR(HOT_FWD & ~E_MASK_OUT)                            // no sign bits wanted: inference, grid queries
           run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
-        } else {
+        } else if constexpr (PROG == P_BWD && !MODA_CHAIN_DISPATCH_BWD) {
           MODA_FLAVOUR(HOT_BWD)
           run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
-        }
-#else
-        if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
+        } else if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_COLD(HOT_FWD | E_HEAD_SIGMA)
           MODA_COLD(E_BIAS | E_SMEM)                                   // xyz_encoding_final
@@ -693,7 +708,6 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           MODA_COLD(E_ADD_SX | E_SMEM)
           run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         }
-#endif
 #undef MODA_COLD
 #undef MODA_FLAVOUR
         if (st.kc > 0) {
@@ -1054,7 +1068,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  return launch<128, 8, 1, 1, P_FWD>(b, wpack, 256, col * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD>(b, wpack, 256, col * 64, stream);
 }
 
 // Density only (the grid query of mesh extraction, nnutils/train_utils.py:1377-1404 -> nerf.py:176-180 with
@@ -1087,7 +1101,7 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
     if (l == 7) st.flags |= E_HEAD_SIGMA;   // the last layer's activations only feed the head: not written back
     else b.out(st, 0, 4);
   }
-  return launch<128, 8, 1, 1, P_FWD>(b, wpack, 256, 38 * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD>(b, wpack, 256, 38 * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -1147,7 +1161,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  return launch<128, 8, 1, 1, P_BWD>(b, wpackT, 256, col * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD>(b, wpackT, 256, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin
@@ -1187,7 +1201,7 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
   { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, 14);
     st.save_map = b.save(dfe, P, 64); b.out(st, AH, 1, AL); }
   { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, 16); }
-  return launch<64, 4, 1, 2, P_FWD>(b, wpack, 64, 18 * 64, stream);
+  return launch<64, MODA_SKIN_EPI, 1, 2, P_FWD>(b, wpack, 64, 18 * 64, stream);
 }
 
 // Adjoint chain of nerf_skin on plain fp16 operands.  wpackT: fp16 (64, 9*64), rows = input channel, cols = output:
@@ -1203,7 +1217,7 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
   MODA_REQUIRE(al16(gout) && al16(wpackT), "chain_skin_bwd: gout and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 2; pg.stages = 8;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 2; pg.stages = MODA_SKIN_BWD_STAGES;
   pg.maskbits = const_cast<unsigned int*>(maskbits);
   pg.load_src = gout; pg.load_ld = 32; pg.load_cols = 32; pg.load_scale = scale;
   const int A = 0, SX = 1;
@@ -1220,5 +1234,5 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
     b.out(st, A, 1);
   }
   { Step& st = b.add(64, E_ADD_SX); b.k(st, A, 8); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
-  return launch<64, 4, 1, 2, P_BWD>(b, wpackT, 64, 9 * 64, stream);
+  return launch<64, MODA_SKIN_EPI, 1, MODA_SKIN_BWD_CTAS, P_BWD>(b, wpackT, 64, 9 * 64, stream);
 }

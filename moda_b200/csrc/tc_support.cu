@@ -75,8 +75,14 @@ __global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __r
     float acc = get(c);
     for (int k = 0; k < F; ++k) {
       const float f = (float)(1 << k);
-      float sn, cs;
-      sincosf(x * f, &sn, &cs);
+      // same evaluation as the chain kernel's PE producers (chain.cu): exact two-term Cody-Waite reduction to
+      // [-pi, pi], then the SFU (absolute error < 1e-6 for |2^k x| <= 160 rad); the libm sincosf it replaces made
+      // this kernel instruction-bound at ~40 instructions per call
+      const float r = x * f;
+      const float kk = rintf(r * 0.15915494309189535f);
+      float r2 = fmaf(kk, -6.2831854820251465f, r);
+      r2 = fmaf(kk, 1.7484555e-7f, r2);
+      const float sn = __sinf(r2), cs = __cosf(r2);
       acc += win.w[k] * f * (cs * get(3 + 6 * k + c) - sn * get(3 + 6 * k + 3 + c));
     }
     acc *= is;
@@ -217,43 +223,59 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __half* __restrict_
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int j = 0; j < 4; ++j) a_wr[c][j] = 0.f;
-  for (long long p = warp0; p < P; p += nwarps) {
-    const float4 rw = *reinterpret_cast<const float4*>(raw + p * 4);
-    const float4 g = *reinterpret_cast<const float4*>(graw + p * 4);
-    const float g0 = g.x * rw.x * (1.f - rw.x), g1 = g.y * rw.y * (1.f - rw.y), g2 = g.z * rw.z * (1.f - rw.z);
-    const uint4 hv = *reinterpret_cast<const uint4*>(H8 + p * 256 + lane * 8);
-    const uint2 dv = *reinterpret_cast<const uint2*>(Dfe + p * 128 + lane * 4);
-    const __half2* hh = reinterpret_cast<const __half2*>(&hv);
-    const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+  // four consecutive rows per warp and trip, every load of the trip issued before the first use: one row per trip
+  // left ~800 bytes per warp in flight and the kernel at a quarter of the HBM rate
+  constexpr int U = 4;
+  for (long long p0 = warp0 * U; p0 < P; p0 += nwarps * U) {
+    float4 rwv[U], gv[U];
+    uint4 hvv[U];
+    uint2 dvv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(hh[j]);
-      a_ws[2 * j] = fmaf(g.w, f.x, a_ws[2 * j]);
-      a_ws[2 * j + 1] = fmaf(g.w, f.y, a_ws[2 * j + 1]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = (p0 + u < P) ? p0 + u : P - 1;
+      rwv[u] = __ldg(reinterpret_cast<const float4*>(raw + p * 4));
+      gv[u] = __ldg(reinterpret_cast<const float4*>(graw + p * 4));
+      hvv[u] = __ldg(reinterpret_cast<const uint4*>(H8 + p * 256 + lane * 8));
+      dvv[u] = __ldg(reinterpret_cast<const uint2*>(Dfe + p * 128 + lane * 4));
     }
-    float d[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float2 f = __half22float2(dh[j]);
-      d[2 * j] = f.x; d[2 * j + 1] = f.y;
-    }
-    uint2 ov;
-    __half2* oh = reinterpret_cast<__half2*>(&ov);
-    float o[4];
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u;
+      if (p >= P) break;
+      const float4 rw = rwv[u], g = gv[u];
+      const float g0 = g.x * rw.x * (1.f - rw.x), g1 = g.y * rw.y * (1.f - rw.y), g2 = g.z * rw.z * (1.f - rw.z);
+      const __half2* hh = reinterpret_cast<const __half2*>(&hvv[u]);
+      const __half2* dh = reinterpret_cast<const __half2*>(&dvv[u]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      a_wr[0][j] = fmaf(g0, d[j], a_wr[0][j]);
-      a_wr[1][j] = fmaf(g1, d[j], a_wr[1][j]);
-      a_wr[2][j] = fmaf(g2, d[j], a_wr[2][j]);
-      const float v = g0 * wrl[0][j] + g1 * wrl[1][j] + g2 * wrl[2][j];
-      o[j] = (d[j] > 0.f) ? v * scale : 0.f;
-    }
-    oh[0] = __floats2half2_rn(o[0], o[1]);
-    oh[1] = __floats2half2_rn(o[2], o[3]);
-    *reinterpret_cast<uint2*>(dDfe + p * 128 + lane * 4) = ov;
-    if (lane == 0) {
-      gsig[p] = g.w;
-      a_br[0] += g0; a_br[1] += g1; a_br[2] += g2; a_bs += g.w;
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hh[j]);
+        a_ws[2 * j] = fmaf(g.w, f.x, a_ws[2 * j]);
+        a_ws[2 * j + 1] = fmaf(g.w, f.y, a_ws[2 * j + 1]);
+      }
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 f = __half22float2(dh[j]);
+        d[2 * j] = f.x; d[2 * j + 1] = f.y;
+      }
+      uint2 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a_wr[0][j] = fmaf(g0, d[j], a_wr[0][j]);
+        a_wr[1][j] = fmaf(g1, d[j], a_wr[1][j]);
+        a_wr[2][j] = fmaf(g2, d[j], a_wr[2][j]);
+        const float v = g0 * wrl[0][j] + g1 * wrl[1][j] + g2 * wrl[2][j];
+        o[j] = (d[j] > 0.f) ? v * scale : 0.f;
+      }
+      oh[0] = __floats2half2_rn(o[0], o[1]);
+      oh[1] = __floats2half2_rn(o[2], o[3]);
+      *reinterpret_cast<uint2*>(dDfe + p * 128 + lane * 4) = ov;
+      if (lane == 0) {
+        gsig[p] = g.w;
+        a_br[0] += g0; a_br[1] += g1; a_br[2] += g2; a_bs += g.w;
+      }
     }
   }
   // block reduction through shared memory, then one atomic per value per block
@@ -426,7 +448,7 @@ extern "C" int moda_head_bwd(const void* H8, const void* Dfe, const float* raw, 
                              float* gbs, long long P, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(H8 && Dfe && raw && graw && Wr && dDfe && gsig && gWr && gbr && gws && gbs, "head_bwd: null pointer");
-  const int blocks = (int)min((long long)148 * 4, (P + 7) / 8);
+  const int blocks = (int)min((long long)148 * 4, (P + 31) / 32);
   head_bwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(H8), reinterpret_cast<const __half*>(Dfe),
                                              raw, graw, Wr, scale, reinterpret_cast<__half*>(dDfe), gsig, gWr, gbr,
                                              gws, gbs, P);

@@ -34,6 +34,9 @@ class FlatParams:
             self.flat[off:off + k].copy_(t.detach().reshape(-1))
             t.data = self.flat[off:off + k].view(t.shape)
             t.grad = self.grad[off:off + k].view(t.shape)
+            # the fused MLP backward (chain_tc._grad_targets) accumulates straight into this view instead of
+            # handing autograd a temporary; consequence: torch.autograd.grad() on a re-homed tensor sees None
+            t._moda_grad_inplace = True
         self.offsets = offs
         self.flat.requires_grad_(True)
         self.flat.grad = self.grad
