@@ -409,7 +409,11 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       if (i2 + 1 < nsub) sub(i2 + 1, vb, va);
     }
   }
+#ifndef MODA_EXP_NO_MASKW
   if (F & E_MASK_OUT) {
+#else
+  if (false) {
+#endif
     *mp = m0;
     if (MW == 2 && nsub > 4) mp[TILE_M] = m1;
   }
@@ -664,19 +668,51 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
 #define MODA_FLAVOUR(FL) \
   if (flags == (FL) && st.n == ACC_STRIDE) run_step<(FL), ACC_STRIDE, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
+#define MODA_FLAVOUR_N(FL, NN) \
+  if (flags == (FL) && st.n == (NN)) run_step<(FL), (NN), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
 #define MODA_COLD(FL) \
   if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs, pm0, pm1); \
                        if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
-        // Forward programs: the flavour that makes up most of a pass inline, the rest through the inlined
-        // run-time-flag version (measured: out-of-line cold flavours cost the forward 8 %).  Adjoint programs: every
-        // flavour straight-line, the rare ones out of line (trunk bwd 2.08 -> 2.01 ms, skin bwd 0.62 -> 0.54 ms).
+        // Dispatch modes (per direction): 2 = every flavour a program uses inline, unrolled over its compile-time
+        // width (default; measured on B200 against mode 0: trunk fwd 2.03 -> 1.65 ms, trunk bwd 2.08 -> 1.72 ms,
+        // skin fwd 0.80 -> 0.71 ms, skin bwd 0.62 -> 0.39 ms per pass); 1 = hot flavour inline, the others as
+        // out-of-line straight-line functions; 0 = hot flavour inline, the others through the run-time-flag version.
 #ifndef MODA_CHAIN_DISPATCH_FWD
-#define MODA_CHAIN_DISPATCH_FWD 0
+#define MODA_CHAIN_DISPATCH_FWD 2
 #endif
 #ifndef MODA_CHAIN_DISPATCH_BWD
-#define MODA_CHAIN_DISPATCH_BWD 1
+#define MODA_CHAIN_DISPATCH_BWD 2
 #endif
-        if constexpr (PROG == P_FWD && !MODA_CHAIN_DISPATCH_FWD) {
+        if constexpr (PROG == P_FWD && MODA_CHAIN_DISPATCH_FWD == 2) {
+          // every flavour of the forward programs inline and unrolled over its compile-time width
+          MODA_FLAVOUR(HOT_FWD)
+          MODA_FLAVOUR(HOT_FWD & ~E_MASK_OUT)
+          if constexpr (BOX_ROWS == 128) {
+            MODA_FLAVOUR(HOT_FWD | E_HEAD_SIGMA)
+            MODA_FLAVOUR(E_BIAS | E_RELU | E_HEAD_SIGMA)                 // sigma-only program: last layer feeds the head only
+            MODA_FLAVOUR(E_BIAS | E_SMEM)
+            MODA_FLAVOUR_N(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM, 128)
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          } else {
+            MODA_FLAVOUR(E_BIAS | E_SMEM | E_LO)
+            MODA_FLAVOUR(E_BIAS | E_OUT_F32)
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          }
+        } else if constexpr (PROG == P_BWD && MODA_CHAIN_DISPATCH_BWD == 2) {
+          MODA_FLAVOUR(HOT_BWD)
+          MODA_FLAVOUR(E_SMEM)
+          if constexpr (BOX_ROWS == 128) {
+            MODA_FLAVOUR(E_RANK1 | E_MASK_IN | E_SMEM)
+            MODA_FLAVOUR_N(E_LOAD16 | E_SMEM, 128)
+            MODA_FLAVOUR_N(E_SMEM, 64)
+            MODA_FLAVOUR_N(E_ADD_SX | E_SMEM, 64)
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          } else {
+            MODA_FLAVOUR(E_LOAD32 | E_SMEM)
+            MODA_FLAVOUR(E_ADD_SX | E_SMEM)
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          }
+        } else if constexpr (PROG == P_FWD && !MODA_CHAIN_DISPATCH_FWD) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_FLAVOUR(HOT_FWD & ~E_MASK_OUT)                            // no sign bits wanted: inference, grid queries
           run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
@@ -709,6 +745,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
         }
 #undef MODA_COLD
+#undef MODA_FLAVOUR_N
 #undef MODA_FLAVOUR
         if (st.kc > 0) {
           tc_fence_before();
@@ -851,9 +888,18 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             wait_or_trap<0>(&ready[c], gen & 1);
             s_dbg[5] = 1;
             MODA_TR(pg.trace && blockIdx.x == 0 && it == 2, 20, s, c);
+#ifdef MODA_EXP_NO_STORE
+            if (false) {
+#else
             if (pg.duty[d].map >= 0) {
+#endif
+#ifdef MODA_EXP_STORE_L2
+              const int trow0 = (tile & 63) * TILE_M;   // experiment: every store lands in the same L2-resident rows
+#else
+              const int trow0 = tile * TILE_M;
+#endif
               tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)(c * CHUNK_BYTES), (int)pg.duty[d].col * 64,
-                               tile * TILE_M);
+                               trow0);
               bulk_commit();
               any = true;
             }
