@@ -805,7 +805,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         float xs[PE_ROWS][3];
 #pragma unroll
         for (int rr = 0; rr < PE_ROWS; ++rr) {
-          const long long row = (long long)tile * TILE_M + (pw * 32 + lane) * PE_ROWS + rr;
+          const long long row = (long long)tile * TILE_M + pw * 32 * PE_ROWS + rr * 32 + lane;
           const bool in = row < pg.M;
 #pragma unroll
           for (int c = 0; c < 3; ++c) xs[rr][c] = in ? __ldg(pg.xyz + row * 3 + c) : 0.f;
@@ -814,25 +814,34 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         MODA_TR(tr, 31, 0, 0);
 #pragma unroll 1
         for (int rr = 0; rr < PE_ROWS; ++rr) {
-          const int trow = (pw * 32 + lane) * PE_ROWS + rr;
+          // lanes own consecutive rows: their swizzle phases differ, so the 128-bit stores below are conflict-free
+          // (the earlier lane -> 4 consecutive rows layout with 32-bit stores was a 16-way bank conflict, ~5k shared-
+          // memory wavefronts per tile taken from the tensor core's operand fetches)
+          const int trow = pw * 32 * PE_ROWS + rr * 32 + lane;
           const int sw = trow & 7;
           float x[3] = {xs[0][0], xs[0][1], xs[0][2]};
 #pragma unroll
           for (int j = 1; j < PE_ROWS; ++j)   // register select (the row loop stays rolled: code size)
             if (rr == j) { x[0] = xs[j][0]; x[1] = xs[j][1]; x[2] = xs[j][2]; }
           const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
-          // channels come out in index order; two neighbours share one 32-bit store (idx is a compile-time constant
-          // after unrolling, so the parity test and the address arithmetic fold away)
+          // channels come out in index order; eight neighbours (one 16-byte piece of the swizzled row) share one
+          // 128-bit store (idx is a compile-time constant after unrolling, so the tests and the address arithmetic
+          // fold away)
           float pend = 0.f;
+          uint32_t pk[4], pkl[4];
           auto put = [&](const int idx, const float v) {
             if ((idx & 1) == 0) { pend = v; return; }
-            const uint32_t a = hrow + (uint32_t)((((idx >> 3) ^ sw) << 4) + ((idx & 7) - 1) * 2);
             const __half2 hv = __floats2half2_rn(pend, v);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&hv)) : "memory");
+            pk[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
             if (BOX_ROWS == 64) {   // split precision: low halves into the next chunk
               const float2 hf = __half22float2(hv);
               const __half2 lv = __floats2half2_rn(pend - hf.x, v - hf.y);
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + CHUNK_BYTES), "r"(*reinterpret_cast<const uint32_t*>(&lv)) : "memory");
+              pkl[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&lv);
+            }
+            if ((idx & 7) == 7) {
+              const uint32_t a = hrow + (uint32_t)(((idx >> 3) ^ sw) << 4);
+              sts128(a, pk[0], pk[1], pk[2], pk[3]);
+              if (BOX_ROWS == 64) sts128(a + CHUNK_BYTES, pkl[0], pkl[1], pkl[2], pkl[3]);
             }
           };
           put(0, x[0]); put(1, x[1]); put(2, x[2]);
