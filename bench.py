@@ -10,6 +10,7 @@ backward -> one NCCL all-reduce of the flat gradient buffer (N>1) -> fused AdamW
 1 B200"); for N>1 every rank renders its own 8192-ray shard (weak scaling).
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -30,6 +31,7 @@ BONES = 25
 # the roofline numerator uses the conservative figure with per-ray-constant inputs hoisted (501.4 MFLOP/ray)
 FLOP_PER_RAY_FULL = 535.5e6
 FLOP_PER_RAY_HOISTED = 501.4e6
+TRUNK_MAC_PER_SAMPLE = 601600 - 91 * 128   # nerf_coarse, one pass, per-ray-constant dir/env columns hoisted
 
 
 def _peaks():
@@ -38,6 +40,19 @@ def _peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def _traffic(entries):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic); null when there is none."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    vals = [d["kernels"][k]["dram_bytes_per_launch"] for k in entries if k in d.get("kernels", {})]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), d.get("source")
 
 
 class ClockSampler:
@@ -104,7 +119,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a mismatched collective should fail within minutes, not hold the box for the default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
 
     R = args.rays
@@ -176,24 +192,43 @@ def run_ours(args):
 
     # per-kernel device time of one step (CUDA events around every C-ABI call on the launching stream)
     roof = None
+    # every rank runs these two steps (step() contains the gradient all-reduce: a collective issued by rank 0 alone
+    # would never complete); only rank 0 records events and summarises
     if rank == 0:
         _lib.PROFILE = {}
-        for _ in range(2):
-            step(rays)
+    for _ in range(2):
+        step(rays)
+    if rank == 0:
         summ = _lib.profile_summary()
         _lib.PROFILE = None
         peaks, src = _peaks()
-        lin_ms = sum(ms for k, (n, ms) in summ.items()
-                     if k.startswith(("moda_linear", "moda_tc", "moda_chain"))) / 2
-        tot_ms = sum(ms for _, ms in summ.values()) / 2
-        achieved = FLOP_PER_RAY_HOISTED * R / (lin_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        roof = {"bound": "tensor", "kernel": "linear layers of nerf_coarse + nerf_skin (fwd, dgrad, wgrad)",
+        per_entry = {k: (n / 2.0, ms / 2.0) for k, (n, ms) in summ.items()}   # launches and ms per step
+        tot_ms = sum(ms for _, ms in per_entry.values())
+        # dominant kernel: chain_kernel<128, 8, 1, 1, *> -- one persistent tcgen05 launch per pass of nerf_coarse
+        # (forward chain and adjoint chain are the same kernel template).  Algorithmic work of one launch: the hoisted
+        # layer MACs of the pass, 2 x 589952 FLOP per sample.
+        dom = ("moda_chain_trunk_fwd", "moda_chain_trunk_bwd")
+        dom_n = sum(per_entry[k][0] for k in dom if k in per_entry)
+        dom_ms = sum(per_entry[k][1] for k in dom if k in per_entry)
+        P = R * SAMPLES
+        flop_launch = 2.0 * TRUNK_MAC_PER_SAMPLE * P
+        achieved = flop_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        traffic, traffic_src = _traffic(dom)
+        lin_ms = sum(ms for k, (n, ms) in per_entry.items() if k.startswith(("moda_linear", "moda_tc", "moda_chain")))
+        agg = FLOP_PER_RAY_HOISTED * R / (lin_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "chain::chain_kernel<128,8,1,1,*> (moda_chain_trunk_fwd / moda_chain_trunk_bwd)",
                 "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-                "peak_source": src + " bf16 sustained", "traffic": None,
-                "kernel_ms_per_step": round(lin_ms, 3), "all_kernels_ms_per_step": round(tot_ms, 3),
-                "share_of_step": round(lin_ms / tot_ms, 4),
-                "per_entry_ms": {k: round(ms / 2, 3) for k, (n, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1])}}
+                "peak_source": src + " bf16 sustained (kernel timed inside the step)",
+                "flop_per_launch": flop_launch, "launches_per_step": dom_n, "ms_per_launch": round(dom_ms / max(dom_n, 1), 4),
+                "share_of_step": round(dom_ms / tot_ms, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "timing": "CUDA events around each C-ABI call on the launching stream, 2 steps after the timed region",
+                "step_aggregate": {"kernels": "all linear-layer kernels of nerf_coarse + nerf_skin (fwd, dgrad, wgrad)",
+                                   "flop_per_step": FLOP_PER_RAY_HOISTED * R, "ms_per_step": round(lin_ms, 3),
+                                   "achieved": round(agg, 3), "frac": round(agg / peak, 5),
+                                   "share_of_step": round(lin_ms / tot_ms, 4)},
+                "all_kernels_ms_per_step": round(tot_ms, 3),
+                "per_entry_ms": {k: round(ms, 3) for k, (n, ms) in sorted(per_entry.items(), key=lambda kv: -kv[1][1])}}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_rays=args.cpu_rays, repeats=2)

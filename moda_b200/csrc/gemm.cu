@@ -322,7 +322,11 @@ extern "C" int moda_linear_fwd(int M, int N, int nseg, const float* const* seg_p
   if (M == 0 || N == 0) return 0;
   Dense q{W, ldw, N, a.K};
   EpiFwd ep{Y, ldy, bias, act};
-  if (N > 32) {
+  if (N > 32 && cdiv(M, 128) * cdiv(N, 64) < 2 * 148) {
+    // per-ray-sized problems (the hoisted per-ray bias layers, M = rays): 128-row tiles leave most SMs idle
+    dim3 grid(cdiv(M, 32), cdiv(N, 64), 1);
+    gemm_kernel<ASrc, Dense, EpiFwd, 32, 64, true, true><<<grid, GEMM_THREADS, 0, stream>>>(a, q, ep, M, N, a.K, a.K);
+  } else if (N > 32) {
     dim3 grid(cdiv(M, 128), cdiv(N, 64), 1);
     gemm_kernel<ASrc, Dense, EpiFwd, 128, 64, true, true><<<grid, GEMM_THREADS, 0, stream>>>(a, q, ep, M, N, a.K, a.K);
   } else {
@@ -341,7 +345,10 @@ extern "C" int moda_linear_dgrad(int M, int N, int Kseg, const float* dY, int ld
   Dense p{dY, ldy, M, N};
   DenseT q{W + k0, ldw, Kseg, N};
   EpiDgrad ep{dA, lda, mask, ldm, accumulate};
-  if (Kseg > 32) {
+  if (Kseg > 32 && cdiv(M, 128) * cdiv(Kseg, 64) < 2 * 148) {
+    dim3 grid(cdiv(M, 32), cdiv(Kseg, 64), 1);
+    gemm_kernel<Dense, DenseT, EpiDgrad, 32, 64, true, false><<<grid, GEMM_THREADS, 0, stream>>>(p, q, ep, M, Kseg, N, N);
+  } else if (Kseg > 32) {
     dim3 grid(cdiv(M, 128), cdiv(Kseg, 64), 1);
     gemm_kernel<Dense, DenseT, EpiDgrad, 128, 64, true, false><<<grid, GEMM_THREADS, 0, stream>>>(p, q, ep, M, Kseg, N, N);
   } else {

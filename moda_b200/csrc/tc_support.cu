@@ -338,8 +338,25 @@ __global__ void segsum16_kernel(const __half* __restrict__ in, int ld, float* ou
 // amax over |g| -> power-of-two loss scale {S, 1/S} with S * amax ~ target
 __global__ void amax_kernel(const float* __restrict__ g, long long n, unsigned int* amax_bits) {
   float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(g[i]));
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    // 128-bit loads, two per trip in flight
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const long long n4 = n >> 2;
+    long long i = tid;
+    for (; i + nth < n4; i += 2 * nth) {
+      const float4 a = __ldg(g4 + i), b = __ldg(g4 + i + nth);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+    }
+    for (; i < n4; i += nth) {
+      const float4 a = __ldg(g4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (long long j = (n4 << 2) + tid; j < n; j += nth) m = fmaxf(m, fabsf(g[j]));
+  } else {
+    for (long long i = tid; i < n; i += nth) m = fmaxf(m, fabsf(g[i]));
+  }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
 }

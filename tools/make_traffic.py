@@ -1,0 +1,35 @@
+"""profiles/traffic.json: DRAM bytes (read + write) per launch of the main kernels, from `ncu --set full` captures:
+    python tools/make_traffic.py <tag> a.ncu-rep b.ncu-rep ...      (tag = the session the captures come from)"""
+import csv, json, os, re, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = [(r"chain_kernel<\(?i?n?t?\)?128.*\(?i?n?t?\)?0>\(", "moda_chain_trunk_fwd"), (r"chain_kernel<\(?i?n?t?\)?128.*\(?i?n?t?\)?1>\(", "moda_chain_trunk_bwd"),
+         (r"chain_kernel<\(?i?n?t?\)?64.*\(?i?n?t?\)?0>\(", "moda_chain_skin_fwd"), (r"chain_kernel<\(?i?n?t?\)?64.*\(?i?n?t?\)?1>\(", "moda_chain_skin_bwd"),
+         (r"tc_wgrad_kernel<\(?i?n?t?\)?256, \(?i?n?t?\)?256>", "moda_tc_wgrad<256,256>"),
+         (r"skin_warp_fwd", "moda_skin_warp_fwd"), (r"skin_warp_bwd", "moda_skin_warp_bwd")]
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+tag, reps = sys.argv[1], sys.argv[2:]
+acc = {}
+for rep in reps:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    u = dict(zip(h, units))
+    for r in rows[2:]:
+        d = dict(zip(h, r))
+        name = d.get("Kernel Name", "")
+        entry = next((e for pat, e in NAMES if re.search(pat, name)), None)
+        if entry is None:
+            continue
+        b = sum(float(d[m]) * SCALE[u[m]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        t = float(d["gpu__time_duration.sum"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u["gpu__time_duration.sum"], 1.0)
+        a = acc.setdefault(entry, {"kernel": name.split("(")[0], "bytes": [], "us": [], "report": os.path.basename(rep)})
+        a["bytes"].append(b)
+        a["us"].append(t)
+res = {"source": "ncu --set full --clock-control none, session %s (per launch, cold cache)" % tag, "kernels": {}}
+for e, a in acc.items():
+    res["kernels"][e] = {"kernel": a["kernel"], "dram_bytes_per_launch": sum(a["bytes"]) / len(a["bytes"]),
+                         "launches_captured": len(a["bytes"]), "us_per_launch_under_ncu": sum(a["us"]) / len(a["us"]),
+                         "report": a["report"]}
+json.dump(res, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print(json.dumps(res, indent=1))
