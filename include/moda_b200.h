@@ -88,11 +88,15 @@ int moda_skin_warp_fwd(const float* pts, const float* bones, const float* rts, c
                        int ld_dskin /* row pitch of dskin, 0 = B */, int bones_per_ray, int deform, int invert,
                        cudaStream_t stream);
 /* gy (R,S,3) / gskin (R,S,B): incoming gradients (either may be NULL).  gpts, gdskin, gskin_in overwritten;
- * grts (R,B,8), gbones, gaux (2) accumulated (zero them first). */
+ * grts (R,B,8), gbones, gaux accumulated (zero them first).  gcopies >= 1: with bones shared by every ray, gbones is
+ * (gcopies,B,10) and gaux (gcopies,2): ray r accumulates into copy r % gcopies and the caller sums the copies.  All rays
+ * adding into ONE (B,10) block (gcopies = 1) serialises in L2: same-address atomics retire at ~20 M/s per address on
+ * B200, which tripled this kernel's time at 8192 rays. */
 int moda_skin_warp_bwd(const float* pts, const float* bones, const float* rts, const float* skin_aux,
                        const float* dskin, const float* skin_in, const float* gy, const float* gskin, float* gpts,
                        float* gdskin, float* gskin_in, float* grts, float* gbones, float* gaux, int R, int S,
-                       int B, int ld_dskin, int bones_per_ray, int deform, int invert, cudaStream_t stream);
+                       int B, int ld_dskin, int bones_per_ray, int deform, int invert, int gcopies,
+                       cudaStream_t stream);
 
 /* ---- compositing: inference, nnutils/rendering.py:183-235 (+ frame_cyc_dis :341,:473) ------------------
  * rgb (P,3; row stride ld_rgb), sigma (P; stride ld_sigma), z (R,S), d (R,3), beta (1); noise (R,S) and

@@ -38,7 +38,7 @@ SIGNATURES = {
     "moda_bone_transform_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "moda_bone_transform_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "moda_skin_warp_fwd": [c_p] * 8 + [c_i] * 7 + [c_p],
-    "moda_skin_warp_bwd": [c_p] * 14 + [c_i] * 7 + [c_p],
+    "moda_skin_warp_bwd": [c_p] * 14 + [c_i] * 8 + [c_p],
     "moda_composite_fwd": [c_p, c_i, c_p, c_i] + [c_p] * 13 + [c_i, c_i, c_p],
     "moda_composite_bwd": [c_p, c_i, c_p, c_i] + [c_p] * 13 + [c_p, c_i, c_p, c_i] + [c_p] * 4 + [c_i, c_i, c_p],
     "moda_linear_fwd": [c_i, c_i, c_i, c_pp, c_ip, c_ip, c_ip, c_ip, c_fp, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p],

@@ -30,6 +30,7 @@ struct SkinArgs {
   int bones_per_ray;  // bones indexed by ray
   int deform;         // apply bone_transform(bones, rts) first (backward warp)
   int invert;         // blend with dq_inverse(rts) (backward warp)
+  int gcopies;        // backward: replicated (B,10) / (2) accumulators behind gbones / gaux (ray r adds into copy r % gcopies)
   // backward only
   const float* gy;     // (R,S,3) or null
   const float* gskin;  // (R,S,B) or null : gradient arriving on skin_out
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
       for (int i = 0; i < 8; ++i) atomicAdd(o + i, grt[i]);
     }
     if (a.gbones) {
-      float* o = a.gbones + ((size_t)(a.bones_per_ray ? ray : 0) * B + b) * 10;
+      float* o = a.gbones + ((size_t)(a.bones_per_ray ? ray : ray % a.gcopies) * B + b) * 10;
       for (int i = 0; i < 10; ++i)
         if (gbone[i] != 0.f) atomicAdd(o + i, gbone[i]);
     }
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_kernel(SkinArgs a)
     if (threadIdx.x == 0) {
       float tot = 0.f;
       for (int i = 0; i < SKIN_THREADS / 32; ++i) tot += red[i];
-      if (tot != 0.f) atomicAdd(a.gaux, tot);
+      if (tot != 0.f) atomicAdd(a.gaux + 2 * (ray % a.gcopies), tot);
     }
   }
 }
@@ -282,7 +283,10 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_fwd_fast_kernel(SkinAr
 __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinArgs a) {
   __shared__ __align__(16) float ctx[FAST_BONES * CTX_STRIDE];
   __shared__ float bone_s[FAST_BONES * 10];
-  __shared__ float acc[FAST_BONES * ACC_STRIDE];
+  // per-warp accumulators: a warp visits every bone once, so its 20 sums for bone b are a plain store (fp32 atomics
+  // on shared memory are a compare-and-swap spin loop; with dense skinning weights they were the kernel's bottleneck:
+  // the cycle warp's adjoint ran 2x slower than the backward warp's on the same instruction count)
+  __shared__ float accw[SKIN_THREADS / 32][FAST_BONES * ACC_STRIDE];
   __shared__ float Lt[SKIN_THREADS / 32][32 * LT];
   __shared__ __align__(16) float Rt[SKIN_THREADS / 32][ACC_STRIDE * RT];
   __shared__ float red[SKIN_THREADS / 32];
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinAr
   float* R = Rt[warp];
   if (a.dskin && nrows > 0) stage_rows(a.dskin + ((size_t)ray * a.S + s0) * a.ldd, nrows, a.ldd, B, L, lane);
   build_ctx(a, ray, ctx, bone_s);
-  for (int i = threadIdx.x; i < B * ACC_STRIDE; i += SKIN_THREADS) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < (SKIN_THREADS / 32) * FAST_BONES * ACC_STRIDE; i += SKIN_THREADS) (&accw[0][0])[i] = 0.f;
   __syncthreads();
   const bool live = lane < nrows;
   const size_t pi = (size_t)ray * a.S + (live ? s0 + lane : 0);
@@ -386,8 +390,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinAr
         const float4 x = row[k];
         t0 += x.x; t1 += x.y; t2 += x.z; t3 += x.w;
       }
-      const float t = (t0 + t1) + (t2 + t3);
-      if (t != 0.f) atomicAdd(&acc[b * ACC_STRIDE + lane], t);
+      accw[warp][b * ACC_STRIDE + lane] = (t0 + t1) + (t2 + t3);
     }
     __syncwarp();
   }
@@ -408,13 +411,21 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinAr
     const float* r = a.rts + ((size_t)ray * B + b) * 8;
     for (int i = 0; i < 8; ++i) rr[i] = r[i];
     float unused = 0.f;
-    ray_bone_setup_bwd(bn, rr, a.deform, a.invert, kappa, bone_s + b * 10, acc + b * ACC_STRIDE, gbone, grt, &unused);
+    float accb[ACC_STRIDE];
+#pragma unroll
+    for (int i = 0; i < ACC_STRIDE; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < SKIN_THREADS / 32; ++w) t += accw[w][b * ACC_STRIDE + i];
+      accb[i] = t;
+    }
+    ray_bone_setup_bwd(bn, rr, a.deform, a.invert, kappa, bone_s + b * 10, accb, gbone, grt, &unused);
     if (a.grts) {
       float* o = a.grts + ((size_t)ray * B + b) * 8;
       for (int i = 0; i < 8; ++i) atomicAdd(o + i, grt[i]);
     }
     if (a.gbones) {
-      float* o = a.gbones + ((size_t)(a.bones_per_ray ? ray : 0) * B + b) * 10;
+      float* o = a.gbones + ((size_t)(a.bones_per_ray ? ray : ray % a.gcopies) * B + b) * 10;
       for (int i = 0; i < 10; ++i)
         if (gbone[i] != 0.f) atomicAdd(o + i, gbone[i]);
     }
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_warp_bwd_fast_kernel(SkinAr
     if (threadIdx.x == 0) {
       float tot = 0.f;
       for (int i = 0; i < SKIN_THREADS / 32; ++i) tot += red[i];
-      if (tot != 0.f) atomicAdd(a.gaux, tot);
+      if (tot != 0.f) atomicAdd(a.gaux + 2 * (ray % a.gcopies), tot);
     }
   }
 }
@@ -507,8 +518,9 @@ extern "C" int moda_skin_warp_bwd(const float* pts, const float* bones, const fl
                                   const float* gy, const float* gskin, float* gpts, float* gdskin,
                                   float* gskin_in, float* grts, float* gbones, float* gaux, int R, int S,
                                   int B, int ld_dskin, int bones_per_ray, int deform, int invert,
-                                  cudaStream_t stream) {
+                                  int gcopies, cudaStream_t stream) {
   SkinArgs a = {};
+  a.gcopies = gcopies > 0 ? gcopies : 1;
   a.ldd = ld_dskin > 0 ? ld_dskin : B;
   a.pts = pts; a.bones = bones; a.rts = rts; a.skin_aux = skin_aux; a.dskin = dskin; a.skin_in = skin_in;
   a.R = R; a.S = S; a.B = B; a.bones_per_ray = bones_per_ray; a.deform = deform; a.invert = invert;

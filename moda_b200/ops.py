@@ -340,6 +340,9 @@ class BoneTransformFn(torch.autograd.Function):
         return gb.reshape(bshape), gr.reshape(rshape)
 
 
+GCOPIES = 64  # replicated bone-gradient accumulators of the skin-warp adjoint
+
+
 class SkinWarpFn(torch.autograd.Function):
     """Gaussian skinning weights and/or dual-quaternion blend skinning of (R,S,3) points.
 
@@ -391,11 +394,18 @@ class SkinWarpFn(torch.autograd.Function):
         gdsk = torch.empty_like(dsk) if dsk is not None else None  # the kernel zeroes the pad columns of pitched rows
         gsin = torch.empty_like(sin) if sin is not None else None
         grts = torch.zeros_like(rts_) if rts_ is not None else None
-        gbones = torch.zeros_like(bones)
-        gaux = torch.zeros(2, device=pts.device, dtype=torch.float32)
+        # bones shared by every ray: the rays' contributions go to GCOPIES replicated accumulators that are summed
+        # afterwards (same-address L2 atomics from 8192 CTAs serialise: see include/moda_b200.h)
+        copies = 1 if per_ray else max(1, min(R, GCOPIES))
+        gbones = torch.zeros_like(bones) if per_ray else torch.zeros((copies,) + tuple(bones.shape), device=pts.device,
+                                                                      dtype=torch.float32)
+        gaux = torch.zeros(copies, 2, device=pts.device, dtype=torch.float32)
         call("moda_skin_warp_bwd", ptr(pts), ptr(bones), ptr(rts_), ptr(aux), ptr(dsk), ptr(sin), ptr(gy),
              ptr(gskin), ptr(gpts), ptr(gdsk), ptr(gsin), ptr(grts), ptr(gbones), ptr(gaux), R, S, B, ldd, per_ray,
-             deform, invert, stream())
+             deform, invert, copies, stream())
+        if not per_ray:
+            gbones = gbones.sum(0)
+        gaux = gaux.sum(0)
         return (gpts, gbones, grts.reshape(rshape) if grts is not None else None, gaux if has_aux else None,
                 gdsk, gsin, None, None, None, None)
 
