@@ -168,7 +168,7 @@ class TrunkChainFn(torch.autograd.Function):
         code = f32(dir_emb) if env is None else torch.cat([f32(dir_emb), f32(env)], -1)
         R, cc = code.shape
         assert R * S == P and Wd.shape[1] == 256 + cc
-        T = (P + TILE - 1) // TILE
+        T = ((P + TILE - 1) // TILE + 1) & ~1   # even: the CTA-pair kernels run tiles two at a time
         wa, _ = _win_array(win)
         rb = _small_linear(code, Wd, 256, bd, 128)
         wpack = pack_trunk_fwd(params)
@@ -293,7 +293,7 @@ class SkinChainFn(torch.autograd.Function):
         b = [params[2 * i + 1] for i in range(5)]
         bf, bd, br = params[11], params[13], params[17]
         oc = br.shape[0]
-        T = (P + TILE - 1) // TILE
+        T = ((P + TILE - 1) // TILE + 1) & ~1   # even: the CTA-pair kernels run tiles two at a time
         wa, _ = _win_array(win)
         rb1 = _small_linear(code, W[0], 63, b[0], 64)
         rb5 = _small_linear(code, W[4], 63, b[4], 64)

@@ -129,19 +129,34 @@ __device__ __forceinline__ int* dbg_words() {
 #define s_dbg (dbg_words())
 
 // spin on an mbarrier phase; a wait that lasts seconds means a protocol bug: trap instead of hanging the GPU
-template <int SLEEP_NS = 0>
+// CLUSTER: the arrivals come from the peer CTA of a pair too (acquire at cluster scope)
+template <int SLEEP_NS = 0, int CLUSTER = 0>
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (CLUSTER)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   if (ok) return;
   const long long t0 = clock64();
   do {
-    asm volatile(
+    if (CLUSTER)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    else
+      asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
@@ -217,6 +232,7 @@ struct EpiCtx {
   bool live, lane0;
   float rscale, lscale;
   int tr;               // trace event base (0: off)
+  uint32_t ready2_remote;   // CTA pairs: cluster address of the leader's ready2[0] (0: single-CTA kernel)
 };
 
 // One step's epilogue for this warp (flavour F = st.flags).  Sub-blocks of 16 columns are processed
@@ -385,12 +401,18 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
     if ((F & E_SMEM) && last_of_chunk) {
       // this warp's part of the chunk is complete: make the generic-proxy writes visible to the async proxy
       // (tensor core, TMA) and count the warp in; the MMA thread and the store warp wait on the chunk barrier
+#ifndef MODA_EXP_NO_FENCE
       fence_async_smem();
+#endif
       __syncwarp();
       if (cx.lane0) {
         MODA_TR(cx.tr, cx.tr + 1, c64, 0);
         mbar_arrive(&ready[chunk]);
         if (F & E_LO) mbar_arrive(&ready[st.out_lo_chunk + c64]);
+        if (cx.ready2_remote) {   // CTA pair: the leader's MMA thread counts both CTAs' writers
+          mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)chunk);
+          if (F & E_LO) mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)(st.out_lo_chunk + c64));
+        }
       }
     }
   };
@@ -447,6 +469,12 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
+#ifndef MODA_TRUNK_PAIR
+#define MODA_TRUNK_PAIR 0   // 1: the 256-wide chains run as CTA pairs (tcgen05 cta_group::2)
+#endif
+#ifndef MODA_TRUNK_STAGES
+#define MODA_TRUNK_STAGES (MODA_TRUNK_PAIR ? 8 : 4)   // weight ring depth (16 KB stages for pairs, 32 KB otherwise)
+#endif
 #ifndef MODA_TRUNK_EPI
 #define MODA_TRUNK_EPI 8   // epilogue warps of the 256-wide chains (8 or 16)
 #endif
@@ -461,13 +489,23 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
 #endif
 constexpr int P_FWD = 0, P_BWD = 1;   // which set of straight-line epilogue flavours a kernel instance carries
 
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG>
+// PAIR = 1 (256-wide chains only): launched as clusters of two CTAs.  Each CTA runs the whole protocol on its own tile
+// (own A chunks, epilogue, PE producers, store warp), but every layer step is ONE tcgen05.mma.cta_group::2 stream issued
+// by the leader CTA (cluster rank 0): M = 256 = both tiles, and each CTA stages and feeds only HALF of every weight
+// chunk (N/2 rows of B).  That halves the weight traffic through each SM's shared memory (TMA writes + UMMA reads:
+// 256 KB -> 128 KB of the 448 KB a layer step moves), which is what bounds these kernels.
+// Cross-CTA signalling: the peer's TMA loads count their bytes on the leader's w_full; writers of both CTAs arrive on
+// the leader's ready2 / acc_free2 / stores_done2 (remote mbarrier arrives); tcgen05.commit multicasts acc_full,
+// w_empty and pe_free to both CTAs.
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR>
 __global__ void __launch_bounds__((3 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
 chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
+  static_assert(!PAIR || BOX_ROWS == 128, "CTA pairs: 256-wide chains only");
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;       // TMEM columns per accumulator
   constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   constexpr int BOX_BYTES = BOX_ROWS * 128;
-  constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_BYTES : BOX_BYTES;
+  constexpr int STAGE_BYTES = PAIR ? BOX_BYTES : ((BOX_ROWS == 128) ? 2 * BOX_BYTES : BOX_BYTES);
+  constexpr int PB_ROWS = 32;                                    // PAIR: rows of one weight TMA box (4 KB)
   constexpr int NH = EPI_WARPS / 4;                              // warps sharing one TMEM lane quarter
   constexpr int EPI_THREADS = EPI_WARPS * 32;
   constexpr int PE_THREADS = PE_WARPS * 32;
@@ -488,7 +526,14 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   uint64_t* acc_free = acc_full + 2;             // [2]
   uint64_t* pe_free = acc_free + 2;              // [1]
   uint64_t* stores_done = pe_free + 1;           // [1] one phase per step: its TMA stores have read their chunks
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done + 1);
+  // CTA pairs, used in the leader CTA only: the same three conditions counted over both CTAs
+  uint64_t* ready2 = stores_done + 1;            // [MAX_CHUNKS]
+  uint64_t* acc_free2 = ready2 + MAX_CHUNKS;     // [2]
+  uint64_t* stores_done2 = acc_free2 + 2;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done2 + 1);
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  (void)leader;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = pg.num_tiles;
@@ -499,6 +544,11 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     mbar_init(stores_done, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS); }
     mbar_init(pe_free, 1);
+    if (PAIR) {
+      for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready2[i], 2 * (pg.from_pe[i] ? PE_WARPS : EPI_WARPS));
+      for (int i = 0; i < 2; ++i) mbar_init(&acc_free2[i], 2 * EPI_WARPS);
+      mbar_init(stores_done2, 2);
+    }
     fence_barrier_init();
   }
   // biases of every step, staged once (step s reads row bias_row[s])
@@ -511,9 +561,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     for (int i = threadIdx.x; i < pg.vec_len0; i += blockDim.x) s_bias[pg.vec_row * ACC_STRIDE + i] = pg.vec0[i];
   if (pg.vec_row1 >= 0)
     for (int i = threadIdx.x; i < pg.vec_len1; i += blockDim.x) s_bias[pg.vec_row1 * ACC_STRIDE + i] = pg.vec1[i];
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -530,18 +581,30 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           s_dbg[0] = s;
           for (int kc = 0; kc < st.kc; ++kc) {
             wait_or_trap<0>(&w_empty[stage], phase ^ 1);
-            mbar_expect_tx(&w_full[stage], (uint32_t)(boxes * BOX_BYTES));
-            for (int bx = 0; bx < boxes; ++bx)
-              tma_load_2d(sB + (size_t)stage * STAGE_BYTES + bx * BOX_BYTES, &maps.w, &w_full[stage],
-                          (int)st.b_col[kc] * 64, bx * BOX_ROWS);
+            if (PAIR) {
+              // this CTA's half of the chunk: rows [crank n/2, (crank + 1) n/2) of the packed weights, in 32-row
+              // boxes; the bytes of both halves are counted on the leader's barrier
+              const int half = st.n >> 1;
+              if (leader) mbar_expect_tx(&w_full[stage], (uint32_t)(st.n * 128));
+              const uint32_t bar = mapa_u32(smem_u32(&w_full[stage]), 0);
+              const uint32_t dst = smem_u32(sB + (size_t)stage * STAGE_BYTES);
+              for (int bx = 0; bx * PB_ROWS < half; ++bx)
+                tma_load_2d_pair(dst + (uint32_t)(bx * PB_ROWS * 128), &maps.w, bar, (int)st.b_col[kc] * 64,
+                                 (int)crank * half + bx * PB_ROWS);
+            } else {
+              mbar_expect_tx(&w_full[stage], (uint32_t)(boxes * BOX_BYTES));
+              for (int bx = 0; bx < boxes; ++bx)
+                tma_load_2d(sB + (size_t)stage * STAGE_BYTES + bx * BOX_BYTES, &maps.w, &w_full[stage],
+                            (int)st.b_col[kc] * 64, bx * BOX_ROWS);
+            }
             if (++stage == pg.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+    // ================================================================== MMA issuer (CTA pairs: the leader's only)
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0, mma_ctr = 0, gstep = 0;
       int it = 0;
@@ -555,21 +618,23 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           // has seen chunks written by an epilogue that was itself released by this thread.
           const uint32_t sd_need = (uint32_t)it * (uint32_t)pg.sd_per_tile + (uint32_t)st.sd_wait;
           if (st.kc == 0) {
-            if (sd_need > 0) wait_or_trap(stores_done, (sd_need - 1) & 1);
+            if (sd_need > 0) { if (PAIR) wait_or_trap<0, 1>(stores_done2, (sd_need - 1) & 1); else wait_or_trap(stores_done, (sd_need - 1) & 1); }
             continue;
           }
           const int b = mma_ctr & 1;
           const bool tr = pg.trace && blockIdx.x == 0 && it == 2;
           MODA_TR(tr, 0, s, 0);
-          wait_or_trap(&acc_free[b], ((mma_ctr >> 1) & 1) ^ 1);   // epilogue of two MMA steps ago has drained it
+          // epilogue of two MMA steps ago has drained it
+          if (PAIR) wait_or_trap<0, 1>(&acc_free2[b], ((mma_ctr >> 1) & 1) ^ 1);
+          else wait_or_trap(&acc_free[b], ((mma_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
           MODA_TR(tr, 1, s, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
-          const uint32_t idesc = make_idesc(TILE_M, st.n, 0, 0);
+          const uint32_t idesc = make_idesc(PAIR ? 2 * TILE_M : TILE_M, st.n, 0, 0);
           for (int kc = 0; kc < st.kc; ++kc) {
             const int c = st.a_chunk[kc];
             const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + st.a_gen[kc];
-            wait_or_trap(&ready[c], gen & 1);
+            if (PAIR) wait_or_trap<0, 1>(&ready2[c], gen & 1); else wait_or_trap(&ready[c], gen & 1);
             MODA_TR(tr, 2, s, kc);
             wait_or_trap(&w_full[stage], phase);
             tc_fence_after();
@@ -580,16 +645,17 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             for (int k = 0; k < 4; ++k) {
               const uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
               const uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
-              umma_f16(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
+              if (PAIR) umma_f16_pair(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
+              else umma_f16(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
             }
-            umma_commit(&w_empty[stage]);
+            if (PAIR) umma_commit_pair(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
             if (++stage == pg.stages) { stage = 0; phase ^= 1; }
           }
           // In-place rewrite guarantee: the epilogue of THIS step overwrites chunks that TMA stores of earlier steps
           // read; it starts on acc_full, so that is only signalled once those stores have read their source.
-          if (sd_need > 0) wait_or_trap(stores_done, (sd_need - 1) & 1);
-          umma_commit(&acc_full[b]);
-          if (st.release_pe) umma_commit(pe_free);
+          if (sd_need > 0) { if (PAIR) wait_or_trap<0, 1>(stores_done2, (sd_need - 1) & 1); else wait_or_trap(stores_done, (sd_need - 1) & 1); }
+          if (PAIR) umma_commit_pair(&acc_full[b], 3); else umma_commit(&acc_full[b]);
+          if (st.release_pe) { if (PAIR) umma_commit_pair(pe_free, 3); else umma_commit(pe_free); }
           MODA_TR(tr, 4, s, 0);
           ++mma_ctr;
         }
@@ -615,6 +681,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     cx.rscale = pg.rscale ? *pg.rscale : 1.0f;
     cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
     cx.T = T;
+    cx.ready2_remote = PAIR ? mapa_u32(smem_u32(&ready2[0]), 0) : 0u;
+    const uint32_t acc_free2_remote = PAIR ? mapa_u32(smem_u32(&acc_free2[0]), 0) : 0u;
+    (void)acc_free2_remote;
     const int h = cx.h, trow = cx.trow;
     uint32_t mma_ctr = 0;
     float sig_keep = 0.f;
@@ -629,7 +698,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         // per tile and then read like any bias.  First barrier: every warp is done with the previous tile's rows.
         named_bar(5, EPI_THREADS);
         const int et = threadIdx.x - 64;
-        const size_t ray = (size_t)(((long long)tile * TILE_M) / pg.rep);
+        long long row0 = (long long)tile * TILE_M;
+        if (row0 >= pg.M) row0 = pg.M - 1;   // dead tile of an odd tile count (CTA pairs): any valid ray
+        const size_t ray = (size_t)(row0 / pg.rep);
         for (int s = 0; s < pg.nsteps; ++s) {
           const Step& st = pg.st[s];
           if (st.tile_bias)
@@ -750,7 +821,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         if (st.kc > 0) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_free[b]);
+          if (lane == 0) { if (PAIR) mbar_arrive_remote(acc_free2_remote + 8u * (uint32_t)b); else mbar_arrive(&acc_free[b]); }
           ++mma_ctr;
         }
         if (flags & E_HEAD_SIGMA) {
@@ -874,6 +945,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         if (lane == 0) {
           mbar_arrive(&ready[pg.pe_chunk]);
           if (pg.pe_lo) mbar_arrive(&ready[pg.pe_chunk + 1]);
+          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&ready2[pg.pe_chunk]), 0));
         }
       }
     }
@@ -917,7 +989,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           s_dbg[5] = 2;
           if (any) bulk_wait_read0();
           MODA_TR(pg.trace && blockIdx.x == 0 && it == 2 && any, 21, s, 0);
-          if (work) mbar_arrive(stores_done);
+          if (work) { if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(stores_done2), 0)); else mbar_arrive(stores_done); }
           s_dbg[5] = 3;
         }
       }
@@ -926,10 +998,12 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA of the pair exits while the other may still signal it or use its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (PAIR) cluster_sync_all();
 }
 
 }  // namespace chain
@@ -1034,28 +1108,40 @@ struct Builder {
   }
 };
 
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG>
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR = 0>
 int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
   if (b.err) return b.err;
   b.finish((BOX_ROWS == 128) ? 256 : 64);
   b.pg.trace = g_trace;
-  if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, BOX_ROWS)) return e;
-  constexpr int STAGE_BYTES = (BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128;
+  if (PAIR) b.pg.num_tiles = (b.pg.num_tiles + 1) & ~1;   // both CTAs of a pair run the same number of tiles
+  if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, PAIR ? 32 : BOX_ROWS)) return e;
+  constexpr int STAGE_BYTES = PAIR ? BOX_ROWS * 128 : ((BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128);
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;
   constexpr int THREADS = (3 + EPI_WARPS + PE_WARPS) * 32;
   const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + head_smem(EPI_WARPS / 4) +
                       (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512 + 32;
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
   MODA_REQUIRE(smem <= cap, "chain: needs %zu B of shared memory (limit %zu)", smem, cap);
-  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS, PROG>;
+  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS, PROG, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     attr_set = true;
   }
-  const int slots = sm_count() * MIN_CTAS;
+  const int slots = PAIR ? ((sm_count() * MIN_CTAS) & ~1) : sm_count() * MIN_CTAS;
   const int grid = b.pg.num_tiles < slots ? b.pg.num_tiles : slots;
-  kern<<<grid, THREADS, smem, stream>>>(b.pg, b.maps);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b.pg, b.maps);
+    MODA_REQUIRE(e == cudaSuccess, "chain: cluster launch failed: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, THREADS, smem, stream>>>(b.pg, b.maps);
+  }
   return check_launch("chain");
 }
 
@@ -1086,7 +1172,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
   MODA_REQUIRE(al16(rowbias) && al16(raw) && al16(wpack), "chain_trunk_fwd: rowbias, raw and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = 4;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
   pg.vec0 = ws; pg.vec_len0 = 256; pg.vec1 = Wr; pg.vec_len1 = 3 * 128;
@@ -1123,7 +1209,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD>(b, wpack, 256, col * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, MODA_TRUNK_PAIR>(b, wpack, 256, col * 64, stream);
 }
 
 // Density only (the grid query of mesh extraction, nnutils/train_utils.py:1377-1404 -> nerf.py:176-180 with
@@ -1137,7 +1223,7 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
   MODA_REQUIRE(al16(wpack) && al16(ws), "chain_trunk_sigma: wpack and ws must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.raw = sigma; pg.sigma_only = 1;
   pg.vec0 = ws; pg.vec_len0 = 256;
@@ -1156,7 +1242,7 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
     if (l == 7) st.flags |= E_HEAD_SIGMA;   // the last layer's activations only feed the head: not written back
     else b.out(st, 0, 4);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD>(b, wpack, 256, 38 * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, MODA_TRUNK_PAIR>(b, wpack, 256, 38 * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -1175,7 +1261,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
   MODA_REQUIRE(al16(d_dfe) && al16(wpackT), "chain_trunk_bwd: d_dfe and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = 4;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
   pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
   pg.vec0 = ws; pg.vec_len0 = 256;
   pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
@@ -1216,7 +1302,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD>(b, wpackT, 256, col * 64, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, MODA_TRUNK_PAIR>(b, wpackT, 256, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin
