@@ -73,7 +73,11 @@ __global__ void pe16_bwd_kernel(const float* __restrict__ xyz, const __half* __r
   for (int c = 0; c < 3; ++c) {
     const float x = xyz[p * 3 + c];
     float acc = get(c);
-    for (int k = 0; k < F; ++k) {
+    // unrolled over the maximum frequency count with a guard: the gradient row then stays in registers (a run-time
+    // trip count turned `buf` into a local-memory array and the kernel into a stack-traffic benchmark)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (k >= F) break;
       const float f = (float)(1 << k);
       // same evaluation as the chain kernel's PE producers (chain.cu): exact two-term Cody-Waite reduction to
       // [-pi, pi], then the SFU (absolute error < 1e-6 for |2^k x| <= 160 rad); the libm sincosf it replaces made

@@ -3,9 +3,16 @@
 import csv, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = [(r"chain_kernel<\(?i?n?t?\)?128.*\(?i?n?t?\)?0>\(", "moda_chain_trunk_fwd"), (r"chain_kernel<\(?i?n?t?\)?128.*\(?i?n?t?\)?1>\(", "moda_chain_trunk_bwd"),
-         (r"chain_kernel<\(?i?n?t?\)?64.*\(?i?n?t?\)?0>\(", "moda_chain_skin_fwd"), (r"chain_kernel<\(?i?n?t?\)?64.*\(?i?n?t?\)?1>\(", "moda_chain_skin_bwd"),
-         (r"tc_wgrad_kernel<\(?i?n?t?\)?256, \(?i?n?t?\)?256>", "moda_tc_wgrad<256,256>"),
+_T = r"\(?(?:int)?\)?"   # ncu prints template arguments as (int)128
+
+
+def _chain(width, prog):
+    return r"chain_kernel<%s%d, %s\d+, %s\d+, %s\d+, %s%d[,>]" % (_T, width, _T, _T, _T, _T, prog)
+
+
+NAMES = [(_chain(128, 0), "moda_chain_trunk_fwd"), (_chain(128, 1), "moda_chain_trunk_bwd"),
+         (_chain(64, 0), "moda_chain_skin_fwd"), (_chain(64, 1), "moda_chain_skin_bwd"),
+         (r"tc_wgrad_kernel<%s256, %s256>" % (_T, _T), "moda_tc_wgrad<256,256>"),
          (r"skin_warp_fwd", "moda_skin_warp_fwd"), (r"skin_warp_bwd", "moda_skin_warp_bwd")]
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tag, reps = sys.argv[1], sys.argv[2:]
