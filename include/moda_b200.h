@@ -206,7 +206,7 @@ int moda_chain_trunk_fwd(const float* xyz, long long P, int rep /* samples per r
                          const float* rowbias /* (P/rep,128) per-ray part of the dir layer */, const float* ws,
                          const float* bs, const float* Wr, const float* br, void* A0 /* (P,64) fp16 PE */,
                          void* H /* (8,P,256) */, void* fin /* (P,256) */, void* dfe /* (P,128) */,
-                         unsigned int* maskbits /* (8,tiles,8,128) ReLU sign bits */, float* raw /* Density-only pass of nerf_coarse for grid queries (extract_mesh, nnutils/train_utils.py:1377-1404 with
+                         unsigned int* maskbits /* (8,tiles2,8,128) ReLU sign bits, tiles2 = ceil(P/128) rounded up to even */, float* raw /* Density-only pass of nerf_coarse for grid queries (extract_mesh, nnutils/train_utils.py:1377-1404 with
  * nerf.py:176-180 sigma_only=True): layers 1-8 + sigma head on tensor cores, nothing saved.  wpack as for
  * moda_chain_trunk_fwd; sigma (P) fp32. */
 int moda_chain_trunk_sigma(const float* xyz, long long P, int F, const float* win, const void* wpack,
@@ -221,11 +221,16 @@ int moda_chain_trunk_bwd(const void* d_dfe /* (P,128) fp16 */, const float* gsig
 int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const float* win,
                         const void* wpack /* fp16 (64, 18*64): [Whi | Wlo] per layer */,
                         const float* const* biases /* rb1, b2, b3, b4, rb5, bfinal, bdir64, brgb64 */, void* A0,
-                        void* H /* (5,P,64) */, void* fin, void* dfe, unsigned int* maskbits /* (6,tiles,2,128) */,
+                        void* H /* (5,P,64) */, void* fin, void* dfe, unsigned int* maskbits /* (6,tiles2,4,128), tiles2 as above */,
                         float* y32 /* (P,32) delta skinning logits */, cudaStream_t stream);
 /* debug: device buffer (>= 16004 int64, zeroed) that subsequent chain launches fill with an event timeline of
  * block 0's third tile (tools/chain_trace.py); NULL switches tracing off */
 int moda_chain_set_trace(long long* buf);
+/* on != 0: the 256-wide chains (moda_chain_trunk_fwd / _sigma / _bwd) are launched as clusters of two CTAs that share
+ * one tcgen05.mma.cta_group::2 stream (M = 256 = two tiles; each CTA stages half of every weight chunk).  Results are
+ * bit-identical to the single-CTA kernels; measured at parity on B200, off by default.  The sign-bit
+ * buffers must be sized for an EVEN tile count in either mode. */
+int moda_chain_set_pair(int on);
 int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);

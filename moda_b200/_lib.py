@@ -68,6 +68,7 @@ SIGNATURES = {
     "moda_chain_skin_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 7,
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,
     "moda_chain_set_trace": [c_p],
+    "moda_chain_set_pair": [c_i],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 
@@ -87,6 +88,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = ctypes.c_int
+    if os.environ.get("MODA_B200_TRUNK_PAIR", "0") != "0":   # config.trunk_pair: CTA-pair launch mode of the trunk chains
+        L.moda_chain_set_pair(1)
     _lib = L
     return L
 

@@ -19,3 +19,16 @@ def set_precision(p):
     if p not in ("fp16", "fp32"):
         raise ValueError("precision must be 'fp16' or 'fp32'")
     precision = p
+
+
+# trunk_pair: run the 256-wide chain kernels as CTA pairs (tcgen05 cta_group::2; csrc/chain.cu, PAIR = 1).  Results
+# are bit-identical; measured at parity with the single-CTA kernels on B200, so the default is off.
+trunk_pair = os.environ.get("MODA_B200_TRUNK_PAIR", "0") != "0"
+
+
+def set_trunk_pair(on):
+    """Switches the CTA-pair launch mode of the nerf_coarse chains (takes effect at the next call)."""
+    global trunk_pair
+    from . import _lib
+    trunk_pair = bool(on)
+    _lib.call("moda_chain_set_pair", int(trunk_pair))

@@ -80,6 +80,7 @@ struct Step {
 
 struct Program {
   int nsteps, num_tiles, rep, nchunks, stages, nbias;
+  int mask_tiles;        // tile stride of the sign-bit buffer: the tile count rounded up to even (same in both launch modes)
   int has_tile_bias;     // some step has tile_bias set
   // head vectors staged behind the biases in shared memory: vec0 (ws, or cvec of the adjoint) from row vec_row,
   // vec1 (Wr, (3, n)) from row vec_row1; -1: none
@@ -469,12 +470,6 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
-#ifndef MODA_TRUNK_PAIR
-#define MODA_TRUNK_PAIR 0   // 1: the 256-wide chains run as CTA pairs (tcgen05 cta_group::2)
-#endif
-#ifndef MODA_TRUNK_STAGES
-#define MODA_TRUNK_STAGES (MODA_TRUNK_PAIR ? 8 : 4)   // weight ring depth (16 KB stages for pairs, 32 KB otherwise)
-#endif
 #ifndef MODA_TRUNK_EPI
 #define MODA_TRUNK_EPI 8   // epilogue warps of the 256-wide chains (8 or 16)
 #endif
@@ -680,7 +675,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     cx.lane0 = lane == 0;
     cx.rscale = pg.rscale ? *pg.rscale : 1.0f;
     cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
-    cx.T = T;
+    cx.T = pg.mask_tiles;
     cx.ready2_remote = PAIR ? mapa_u32(smem_u32(&ready2[0]), 0) : 0u;
     const uint32_t acc_free2_remote = PAIR ? mapa_u32(smem_u32(&acc_free2[0]), 0) : 0u;
     (void)acc_free2_remote;
@@ -1016,6 +1011,12 @@ using namespace moda;
 using namespace moda::chain;
 
 static long long* g_trace = nullptr;
+#ifndef MODA_TRUNK_PAIR
+#define MODA_TRUNK_PAIR 0   // default of the run-time switch below
+#endif
+// 1: the 256-wide chains (nerf_coarse forward, density-only, adjoint) run as CTA pairs (tcgen05 cta_group::2)
+static int g_pair = MODA_TRUNK_PAIR;
+extern "C" int moda_chain_set_pair(int on) { g_pair = on ? 1 : 0; return 0; }
 // debug: device buffer of >= 4 + 4 * 4000 int64 (zeroed by the caller) that the next chain launches fill with a timeline
 extern "C" int moda_chain_set_trace(long long* buf) { g_trace = buf; return 0; }
 
@@ -1113,6 +1114,7 @@ int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t str
   if (b.err) return b.err;
   b.finish((BOX_ROWS == 128) ? 256 : 64);
   b.pg.trace = g_trace;
+  b.pg.mask_tiles = (b.pg.num_tiles + 1) & ~1;
   if (PAIR) b.pg.num_tiles = (b.pg.num_tiles + 1) & ~1;   // both CTAs of a pair run the same number of tiles
   if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, PAIR ? 32 : BOX_ROWS)) return e;
   constexpr int STAGE_BYTES = PAIR ? BOX_ROWS * 128 : ((BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128);
@@ -1172,7 +1174,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
   MODA_REQUIRE(al16(rowbias) && al16(raw) && al16(wpack), "chain_trunk_fwd: rowbias, raw and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
   pg.vec0 = ws; pg.vec_len0 = 256; pg.vec1 = Wr; pg.vec_len1 = 3 * 128;
@@ -1209,7 +1211,8 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, MODA_TRUNK_PAIR>(b, wpack, 256, col * 64, stream);
+  return g_pair ? launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 1>(b, wpack, 256, col * 64, stream)
+                : launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 0>(b, wpack, 256, col * 64, stream);
 }
 
 // Density only (the grid query of mesh extraction, nnutils/train_utils.py:1377-1404 -> nerf.py:176-180 with
@@ -1223,7 +1226,7 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
   MODA_REQUIRE(al16(wpack) && al16(ws), "chain_trunk_sigma: wpack and ws must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.raw = sigma; pg.sigma_only = 1;
   pg.vec0 = ws; pg.vec_len0 = 256;
@@ -1242,7 +1245,8 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
     if (l == 7) st.flags |= E_HEAD_SIGMA;   // the last layer's activations only feed the head: not written back
     else b.out(st, 0, 4);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, MODA_TRUNK_PAIR>(b, wpack, 256, 38 * 64, stream);
+  return g_pair ? launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 1>(b, wpack, 256, 38 * 64, stream)
+                : launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 0>(b, wpack, 256, 38 * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -1261,7 +1265,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
   MODA_REQUIRE(al16(d_dfe) && al16(wpackT), "chain_trunk_bwd: d_dfe and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = MODA_TRUNK_STAGES;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
   pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
   pg.vec0 = ws; pg.vec_len0 = 256;
   pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
@@ -1302,7 +1306,8 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, MODA_TRUNK_PAIR>(b, wpackT, 256, col * 64, stream);
+  return g_pair ? launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, 1>(b, wpackT, 256, col * 64, stream)
+                : launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, 0>(b, wpackT, 256, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin

@@ -434,6 +434,52 @@ def test_fused_chains_match_layer_by_layer_kernels():
         config.fused = True
 
 
+def test_trunk_chains_as_cta_pairs_match_single_cta_kernels():
+    """The CTA-pair launch mode of the 256-wide chains (tcgen05 cta_group::2, csrc/chain.cu PAIR = 1) performs the
+    same arithmetic in the same order as the single-CTA kernels: outputs and the data gradients are bit-identical,
+    the weight gradients (atomic accumulation order) agree to rounding.  Sizes: an odd tile count (the pair's dead
+    tile), a ragged last tile, and more tile pairs than CTAs."""
+    from moda_b200 import config, geom_utils as G, synth, models as MM
+    from moda_b200.extract import density_grid
+    config.set_precision("fp16")
+    prob = synth.make_problem(8, seed=0)
+    models, emb, _ = MM.build_models(prob, DEV)
+    model = models["coarse"]
+    nrel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
+
+    def run(R, S):
+        gen = torch.Generator().manual_seed(11)
+        pts = (torch.rand(R, S, 3, generator=gen) * 0.6 - 0.3).to(DEV).requires_grad_(True)
+        de = torch.randn(R, 27, generator=gen).to(DEV).requires_grad_(True)
+        env = (0.1 * torch.randn(R, 64, generator=gen)).to(DEV).requires_grad_(True)
+        gout = torch.randn(R, S, 4, generator=gen).to(DEV) * 1e-3
+        model.zero_grad()
+        out = G.evaluate_mlp(model, pts, embed_xyz=emb["xyz"], dir_embedded=de, code=env)
+        (out * gout).sum().backward()
+        data = {"pts": pts.grad.clone(), "dir": de.grad.clone(), "env": env.grad.clone()}
+        par = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        with torch.no_grad():
+            vol = density_grid(model, 24, (0.3, 0.3, 0.3), emb["xyz"])
+        return out.detach().clone(), data, par, vol
+
+    try:
+        for R, S in ((3, 128), (37, 64), (700, 128)):
+            config.set_trunk_pair(False)
+            a = run(R, S)
+            config.set_trunk_pair(True)
+            b = run(R, S)
+            assert torch.equal(a[0], b[0]), (R, S, max_abs(a[0], b[0]))
+            assert torch.equal(a[3], b[3]), (R, S, "density grid")
+            for k in ("pts",):
+                assert torch.equal(a[1][k], b[1][k]), (R, S, k, max_abs(a[1][k], b[1][k]))
+            for k in ("dir", "env"):
+                assert nrel(b[1][k], a[1][k]) < 1e-5, (R, S, k)
+            worst = max((nrel(b[2][k], a[2][k]), k) for k in a[2])
+            assert worst[0] < 1e-4, (R, S, worst)
+    finally:
+        config.set_trunk_pair(False)
+
+
 def test_training_step_on_flat_parameter_buffer():
     """bench.py / the data-parallel path re-home every parameter into one flat buffer (moda_b200.parallel.FlatParams):
     the kernels must accept those views (128-bit loads need the 16-byte alignment FlatParams guarantees) and give
