@@ -629,11 +629,13 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           for (int kc = 0; kc < st.kc; ++kc) {
             const int c = st.a_chunk[kc];
             const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + st.a_gen[kc];
-            if (PAIR) wait_or_trap<0, 1>(&ready2[c], gen & 1); else wait_or_trap(&ready[c], gen & 1);
-            MODA_TR(tr, 2, s, kc);
+            // weights first: the producer runs far ahead, so this check completes while the epilogue is still writing
+            // the A chunk, and nothing but the descriptors stands between the chunk's arrival and the MMA issue
             wait_or_trap(&w_full[stage], phase);
-            tc_fence_after();
             MODA_TR(tr, 3, s, kc);
+            if (PAIR) wait_or_trap<0, 1>(&ready2[c], gen & 1); else wait_or_trap(&ready[c], gen & 1);
+            tc_fence_after();
+            MODA_TR(tr, 2, s, kc);
             const uint32_t a_addr = smem_u32(sA + (size_t)c * CHUNK_BYTES);
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * STAGE_BYTES);
 #pragma unroll
