@@ -197,15 +197,40 @@ def run_ours(args):
         optim.step()
         return loss
 
+    # end-to-end input pipeline: two device buffer sets; while step i computes, the host->device copy of step i+1's
+    # rays runs on a copy stream from pinned memory (every step's inputs are copied inside the timed region, one copy
+    # set per step), and the step's loss is read back to pinned host memory
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{k: torch.empty_like(rays[k]) for k in ray_keys} for _ in range(2)]
+    ready_ev = [torch.cuda.Event() for _ in range(2)]
+    free_ev = [torch.cuda.Event() for _ in range(2)]
+    pipe = {"i": 0, "primed": False}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free_ev[slot])      # the step that last read this buffer set has finished
+            for k in ray_keys:
+                bufs[slot][k].copy_(host[k], non_blocking=True)
+            ready_ev[slot].record(copy_stream)
+
     def step_e2e():
+        slot = pipe["i"] & 1
+        if not pipe["primed"]:
+            issue_copy(slot)
+            pipe["primed"] = True
+        issue_copy(slot ^ 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready_ev[slot])
         rd = {"xys": rays["xys"]}
         for k in ray_keys:
-            t = host[k].to(dev, non_blocking=True)
+            t = bufs[slot][k].detach()
             if k in ("bone_rts", "time_embedded", "env_code", "rays_o", "rays_d"):
                 t.requires_grad_(True)
             rd[k] = t
         loss = step(rd)
+        free_ev[slot].record(cur)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        pipe["i"] += 1
         return loss
 
     def barrier():
@@ -291,7 +316,8 @@ def run_ours(args):
                           "rays_per_gpu": R, "samples_per_ray": SAMPLES, "bones": BONES, "parallelism": "dp%d" % world,
                           "l2_policy": "inputs+activations per step (>10 GB) exceed the 126 MB L2"},
                "e2e": {"value": round(R * world / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
-                       "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3)},
+                       "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
+                       "input_pipeline": "pinned host rays -> double-buffered H2D prefetch on a copy stream, one copy set per step"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(out))
     if world > 1:
