@@ -267,6 +267,11 @@ def run_ours(args):
     roof = None
     # every rank runs these two steps (step() contains the gradient all-reduce: a collective issued by rank 0 alone
     # would never complete); only rank 0 records events and summarises
+    # (single-stream launches for these two steps: with the weight-gradient kernels alternating over two streams the
+    # per-call event intervals overlap and would be counted twice)
+    from moda_b200 import config as _cfg
+    side_was = _cfg.side_stream
+    _cfg.side_stream = False
     if rank == 0:
         _lib.PROFILE = {}
     for _ in range(2):
@@ -274,6 +279,7 @@ def run_ours(args):
     if rank == 0:
         summ = _lib.profile_summary()
         _lib.PROFILE = None
+    _cfg.side_stream = side_was
         peaks, src = _peaks()
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         per_entry = {k: (n / 2.0, ms / 2.0) for k, (n, ms) in summ.items()}   # launches and ms per step

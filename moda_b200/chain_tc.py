@@ -12,6 +12,7 @@ import ctypes
 
 import torch
 
+from . import config
 from ._lib import call, ptr, stream, f32
 from .ops import _win_array
 
@@ -63,6 +64,48 @@ def _small_linear(code, Wl, col0, bias, n):
     call("moda_linear_fwd", R, n, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(nc), _one(nc), _one(0), _one(1), None, 0,
          ptr(Wl) + 4 * col0, Wl.shape[1], ptr(bias), 0, ptr(rb), n, stream())
     return rb
+
+
+_SIDE = {}
+
+
+class _Alternate:
+    """Issues independent kernels alternately on the current stream and on a per-device side stream, so that the tail
+    of one persistent weight-gradient kernel (CTAs draining their atomics) overlaps the ramp-up of the next instead
+    of serialising behind it.  Everything issued before `with _Alternate(dev) as alt:` is visible to both streams,
+    and the current stream waits for the side stream on exit (so buffers may be released by the caller afterwards).
+    MODA_B200_SIDE_STREAM=0 keeps everything on the current stream."""
+
+    def __init__(self, dev):
+        self.dev, self.i = dev, 0
+        self.on = config.side_stream
+
+    def __enter__(self):
+        if self.on:
+            self.main = torch.cuda.current_stream(self.dev)
+            key = (self.dev.index, self.main.cuda_stream)
+            if key not in _SIDE:
+                _SIDE[key] = torch.cuda.Stream(device=self.dev)
+            self.side = _SIDE[key]
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+        return self
+
+    def run(self, fn, *a, **k):
+        self.i += 1
+        if self.on and (self.i & 1) == 0:
+            with torch.cuda.stream(self.side):
+                fn(*a, **k)
+        else:
+            fn(*a, **k)
+
+    def __exit__(self, *exc):
+        if self.on:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+        return False
 
 
 def _grad_targets(refs, params):
@@ -225,18 +268,20 @@ class TrunkChainFn(torch.autograd.Function):
         call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(_al16(Ws.reshape(-1))), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
              ptr(d_fin), ptr(dY), ptr(d_pe), stream())
         # weight gradients (bias gradients ride along as column sums of the dY operand)
-        _wgrad(d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
-        _wgrad(d_fin, 256, H[7], 256, P, g[16], 0, 256, 256, isc, dbias=g[17])
-        for i in range(7, 0, -1):
-            if i == 4:
-                _wgrad(dY[4], 256, A0, 64, P, g[8], 0, 256, 63, isc)
-                _wgrad(dY[4], 256, H[3], 256, P, g[8], 63, 256, 256, isc, dbias=g[9])
-            else:
-                _wgrad(dY[i], 256, H[i - 1], 256, P, g[2 * i], 0, 256, 256, isc, dbias=g[2 * i + 1])
-        _wgrad(dY[0], 256, A0, 64, P, g[0], 0, 256, 63, isc, dbias=g[1])
         gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
-        call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
+        with _Alternate(dev) as alt:   # the launches below are independent of each other
+            alt.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+            alt.run(_wgrad, d_fin, 256, H[7], 256, P, g[16], 0, 256, 256, isc, dbias=g[17])
+            for i in range(7, 0, -1):
+                if i == 4:
+                    alt.run(_wgrad, dY[4], 256, A0, 64, P, g[8], 0, 256, 63, isc)
+                    alt.run(_wgrad, dY[4], 256, H[3], 256, P, g[8], 63, 256, 256, isc, dbias=g[9])
+                else:
+                    alt.run(_wgrad, dY[i], 256, H[i - 1], 256, P, g[2 * i], 0, 256, 256, isc, dbias=g[2 * i + 1])
+            alt.run(_wgrad, dY[0], 256, A0, 64, P, g[0], 0, 256, 63, isc, dbias=g[1])
+            alt.run(lambda: call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0,
+                                 stream()))
         ctx.act = None
         gdir = gcode[:, :cd].contiguous()
         genv = gcode[:, cd:].contiguous() if has_env else None
@@ -354,19 +399,21 @@ class SkinChainFn(torch.autograd.Function):
         shared_row = Rc == 1
         rb4 = torch.zeros(1, 64, device=dev, dtype=torch.float32) if shared_row else None
         rb0 = torch.zeros(1, 64, device=dev, dtype=torch.float32) if shared_row else None
-        _wgrad(G, WD, dfe, WD, P, g[16], 0, oc, 32, isc, dbias=g[17])
-        _wgrad(d_dfe, WD, fin, WD, P, g[12], 0, 32, 64, isc, dbias=g[13])
-        _wgrad(d_fin, WD, H[4], WD, P, g[10], 0, 64, 64, isc, dbias=g[11])
-        _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc, dbias=rb4)
-        _wgrad(dY[4], WD, H[3], WD, P, g[8], 63 + nc, 64, 64, isc)
-        code_part(dY[4], W[4], g[8], g[9], rb4)
-        for i in (3, 2, 1):
-            _wgrad(dY[i], WD, H[i - 1], WD, P, g[2 * i], 0, 64, 64, isc, dbias=g[2 * i + 1])
-        _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc, dbias=rb0)
-        code_part(dY[0], W[0], g[0], g[1], rb0)
         gpts = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
-        call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0, stream())
+        with _Alternate(dev) as alt:   # independent launches; the two that feed code_part stay on the current stream
+            _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc, dbias=rb4)
+            _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc, dbias=rb0)
+            alt.run(_wgrad, G, WD, dfe, WD, P, g[16], 0, oc, 32, isc, dbias=g[17])
+            alt.run(_wgrad, d_dfe, WD, fin, WD, P, g[12], 0, 32, 64, isc, dbias=g[13])
+            alt.run(_wgrad, d_fin, WD, H[4], WD, P, g[10], 0, 64, 64, isc, dbias=g[11])
+            alt.run(_wgrad, dY[4], WD, H[3], WD, P, g[8], 63 + nc, 64, 64, isc)
+            for i in (3, 2, 1):
+                alt.run(_wgrad, dY[i], WD, H[i - 1], WD, P, g[2 * i], 0, 64, 64, isc, dbias=g[2 * i + 1])
+            alt.run(lambda: call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0,
+                                 stream()))
+            code_part(dY[4], W[4], g[8], g[9], rb4)
+            code_part(dY[0], W[0], g[0], g[1], rb0)
         ctx.act = None
         gret[14] = gret[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
         return (gpts.reshape(pshape), gcode, None, None) + tuple(gret)

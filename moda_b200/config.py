@@ -21,6 +21,10 @@ def set_precision(p):
     precision = p
 
 
+# side_stream: the independent weight-gradient launches of a backward pass alternate between the current stream and a
+# side stream (tail/ramp-up overlap of the persistent kernels); "0" keeps everything on the current stream.
+side_stream = os.environ.get("MODA_B200_SIDE_STREAM", "1") != "0"
+
 # trunk_pair: run the 256-wide chain kernels as CTA pairs (tcgen05 cta_group::2; csrc/chain.cu, PAIR = 1).  Results
 # are bit-identical; measured at parity with the single-CTA kernels on B200, so the default is off.
 trunk_pair = os.environ.get("MODA_B200_TRUNK_PAIR", "0") != "0"

@@ -3,7 +3,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from moda_b200 import synth, models as MM, _lib
+from moda_b200 import synth, models as MM, _lib, config
+config.side_stream = False   # one stream: per-call intervals do not overlap
 from moda_b200.parallel import FlatParams
 from moda_b200.rendering import render_rays
 
