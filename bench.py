@@ -276,10 +276,10 @@ def run_ours(args):
         _lib.PROFILE = {}
     for _ in range(2):
         step(rays)
+    _cfg.side_stream = side_was
     if rank == 0:
         summ = _lib.profile_summary()
         _lib.PROFILE = None
-    _cfg.side_stream = side_was
         peaks, src = _peaks()
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         per_entry = {k: (n / 2.0, ms / 2.0) for k, (n, ms) in summ.items()}   # launches and ms per step
