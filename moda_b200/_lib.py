@@ -88,8 +88,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = ctypes.c_int
-    if os.environ.get("MODA_B200_TRUNK_PAIR", "0") != "0":   # config.trunk_pair: CTA-pair launch mode of the trunk chains
-        L.moda_chain_set_pair(1)
+    # config.trunk_pair: CTA-pair launch mode of the trunk chains (library default: on)
+    L.moda_chain_set_pair(0 if os.environ.get("MODA_B200_TRUNK_PAIR", "1") == "0" else 1)
     _lib = L
     return L
 

@@ -462,6 +462,7 @@ def test_trunk_chains_as_cta_pairs_match_single_cta_kernels():
             vol = density_grid(model, 24, (0.3, 0.3, 0.3), emb["xyz"])
         return out.detach().clone(), data, par, vol
 
+    was = config.trunk_pair
     try:
         for R, S in ((3, 128), (37, 64), (700, 128)):
             config.set_trunk_pair(False)
@@ -477,7 +478,7 @@ def test_trunk_chains_as_cta_pairs_match_single_cta_kernels():
             worst = max((nrel(b[2][k], a[2][k]), k) for k in a[2])
             assert worst[0] < 1e-4, (R, S, worst)
     finally:
-        config.set_trunk_pair(False)
+        config.set_trunk_pair(was)
 
 
 def test_training_step_on_flat_parameter_buffer():
