@@ -232,6 +232,7 @@ int moda_chain_set_trace(long long* buf);
  * On by default; if the cluster cannot be launched the library falls back to the single-CTA kernels for good.  The sign-bit
  * buffers must be sized for an EVEN tile count in either mode. */
 int moda_chain_set_pair(int on);
+int moda_chain_get_pair(void); /* the mode in effect: 1 = CTA pairs, 0 = single-CTA kernels (requested, or after a fallback) */
 int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);

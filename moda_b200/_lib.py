@@ -69,6 +69,7 @@ SIGNATURES = {
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,
     "moda_chain_set_trace": [c_p],
     "moda_chain_set_pair": [c_i],
+    "moda_chain_get_pair": [],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 

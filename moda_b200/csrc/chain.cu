@@ -1020,6 +1020,7 @@ static long long* g_trace = nullptr;
 static int g_pair = MODA_TRUNK_PAIR;
 constexpr int PAIR_UNAVAILABLE = -77;   // launch<..., PAIR = 1> could not place the cluster: the caller relaunches single-CTA
 extern "C" int moda_chain_set_pair(int on) { g_pair = on ? 1 : 0; return 0; }
+extern "C" int moda_chain_get_pair(void) { return g_pair; }   // 0 after a fallback, whatever was requested
 // debug: device buffer of >= 4 + 4 * 4000 int64 (zeroed by the caller) that the next chain launches fill with a timeline
 extern "C" int moda_chain_set_trace(long long* buf) { g_trace = buf; return 0; }
 
