@@ -45,6 +45,29 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly ONE line, the JSON result: until _emit() everything written to file descriptor 1 (NCCL
+    prints its "NCCL version ..." banner there at the first collective, whatever NCCL_DEBUG_FILE says) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+        os.close(_REAL_STDOUT)
+        _REAL_STDOUT = None
+    print(json.dumps(obj), flush=True)
+
+
 def _traffic(entries):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` capture
     (profiles/traffic.json, written by tools/ncu_summary.py --traffic); null when there is none."""
@@ -327,7 +350,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
                        "input_pipeline": "pinned host rays -> double-buffered H2D prefetch on a copy stream, one copy set per step"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -383,7 +406,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = round(R / dt, 2)
     sample = "%d rays x %d samples per step (bounded sample of the %d-ray workload)" % (R, SAMPLES, RAYS_PER_GPU)
-    print(json.dumps({"impl": "reference", "metric": "train rays/s (128 samp/ray)", "value": v, "unit": "rays/s",
+    _emit(({"impl": "reference", "metric": "train rays/s (128 samp/ray)", "value": v, "unit": "rays/s",
                       "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": min(args.warmup, 1),
                       "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -478,7 +501,7 @@ def run_dqs(args):
         cpu = {"value": round(Rc * S / best / 1e9, 5), "unit": "Gpts/s", "cores": cores, "kind": "port",
                "sample": "%d points forward (both warps, no delta), best of 2 after 1 warm-up" % (Rc * S)}
     a = out["delta_streamed"]
-    print(json.dumps({"metric": "DQ skinning Gpts/s (bw + fw warp, 25 Gaussian bones)", "value": out["no_delta"]["fwd_gpts_s"],
+    _emit(({"metric": "DQ skinning Gpts/s (bw + fw warp, 25 Gaussian bones)", "value": out["no_delta"]["fwd_gpts_s"],
                       "unit": "Gpts/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
                       "ms_per_step": out["no_delta"]["fwd_ms"], "higher_is_better": True, "scaling": "replicas only",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -550,7 +573,7 @@ def run_grid(args):
             dt = time.perf_counter() - t0
             cpu = {"value": round(Gc ** 3 / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
                    "sample": "%d^3 grid (%.2f s), one pass" % (Gc, dt)}
-        print(json.dumps({"metric": "density-grid Mpts/s (sigma_only nerf_coarse, %d^3)" % Gs, "value": round(pts / ms / 1e3, 1),
+        _emit(({"metric": "density-grid Mpts/s (sigma_only nerf_coarse, %d^3)" % Gs, "value": round(pts / ms / 1e3, 1),
                           "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                           "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
@@ -577,6 +600,7 @@ def main():
     ap.add_argument("--dqs-rays", type=int, default=131072)
     ap.add_argument("--grid", type=int, default=256)
     args = ap.parse_args()
+    _quiet_stdout()
     if args.workload == "dqs":
         return run_dqs(args)
     if args.workload == "grid":
