@@ -602,6 +602,8 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0, mma_ctr = 0, gstep = 0;
+      const uint64_t desc_hi = make_desc(0, 16, 1024);   // everything but the start address
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       int it = 0;
       for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
         for (int s = 0; s < pg.nsteps; ++s, ++gstep) {
@@ -636,14 +638,21 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             if (PAIR) wait_or_trap<0, 1>(&ready2[c], gen & 1); else wait_or_trap(&ready[c], gen & 1);
             tc_fence_after();
             MODA_TR(tr, 2, s, kc);
-            const uint32_t a_addr = smem_u32(sA + (size_t)c * CHUNK_BYTES);
-            const uint32_t b_addr = smem_u32(sB + (size_t)stage * STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
-              if (PAIR) umma_f16_pair(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
-              else umma_f16(d_tmem, ad, bd, idesc, (kc | k) ? 1u : 0u);
+            // This thread is the serial resource of the kernel (tools/microbench/mma_latency.cu: the tensor pipe answers
+            // within ~200 cycles, a K chunk of N = 256 takes 512): the descriptors of a chunk are built once and the
+            // three K = 16 advances are plain additions (32 bytes = 2 units of the 16-byte address field).
+            const uint64_t ad0 = desc_hi | (uint64_t)(((sA_u + (uint32_t)c * CHUNK_BYTES) & 0x3FFFF) >> 4);
+            const uint64_t bd0 = desc_hi | (uint64_t)(((sB_u + (uint32_t)stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+            if (PAIR) {
+              umma_f16_pair(d_tmem, ad0, bd0, idesc, kc ? 1u : 0u);
+              umma_f16_pair(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
+              umma_f16_pair(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
+              umma_f16_pair(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, ad0, bd0, idesc, kc ? 1u : 0u);
+              umma_f16(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
+              umma_f16(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
+              umma_f16(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
             }
             if (PAIR) umma_commit_pair(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
             if (++stage == pg.stages) { stage = 0; phase ^= 1; }
