@@ -197,16 +197,18 @@ def trunk_sigma(xyz, win, params):
 
 
 class TrunkChainFn(torch.autograd.Function):
-    """apply(xyz (P,3), dir_embedded (R,cd), env_code (R,ce) | None, S, win, *params) -> raw (P,4) [rgb | sigma]."""
+    """apply(xyz (P,3), dir_embedded (R,cd), env_code (R,ce) | None, S, win, save, *params) -> raw (P,4) [rgb | sigma].
+    ``save``: the caller's ``torch.is_grad_enabled()`` (always False inside Function.forward, and needs_input_grad
+    only reflects requires_grad): without it nothing is kept for a backward pass and the kernel stores nothing."""
 
     @staticmethod
-    def forward(ctx, xyz, dir_emb, env, S, win, *params):
+    def forward(ctx, xyz, dir_emb, env, S, win, save, *params):
         xyz_shape = xyz.shape
         xyz = f32(xyz).reshape(-1, 3)
         P, dev = xyz.shape[0], xyz.device
         ctx.param_refs = params
         params = [f32(p) for p in params]
-        need_bw = any(ctx.needs_input_grad)
+        need_bw = bool(save) and any(ctx.needs_input_grad)
         Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
         code = f32(dir_emb) if env is None else torch.cat([f32(dir_emb), f32(env)], -1)
         R, cc = code.shape
@@ -285,7 +287,7 @@ class TrunkChainFn(torch.autograd.Function):
         ctx.act = None
         gdir = gcode[:, :cd].contiguous()
         genv = gcode[:, cd:].contiguous() if has_env else None
-        return (gxyz.reshape(xyz_shape), gdir, genv, None, None) + tuple(gret)
+        return (gxyz.reshape(xyz_shape), gdir, genv, None, None, None) + tuple(gret)
 
 
 # -------------------------------------------------------------------------------------------------- nerf_skin
@@ -319,11 +321,11 @@ def pack_skin_bwd(params, nc):
 
 
 class SkinChainFn(torch.autograd.Function):
-    """apply(pts (..,3), code (Rc,nc) with Rc in {rays, 1}, S, win, *params) -> (P, 32) fp32 delta logits,
-    columns >= out_channels are zero (a row pitch the skinning kernels accept directly)."""
+    """apply(pts (..,3), code (Rc,nc) with Rc in {rays, 1}, S, win, save, *params) -> (P, 32) fp32 delta logits,
+    columns >= out_channels are zero (a row pitch the skinning kernels accept directly).  ``save`` as in TrunkChainFn."""
 
     @staticmethod
-    def forward(ctx, pts, code, S, win, *params):
+    def forward(ctx, pts, code, S, win, save, *params):
         pshape = pts.shape
         pts = f32(pts).reshape(-1, 3)
         P, dev = pts.shape[0], pts.device
@@ -333,7 +335,7 @@ class SkinChainFn(torch.autograd.Function):
         Rc, nc = code.shape
         rep = S if Rc * S == P else P
         assert Rc * rep == P, "pose code rows do not match the points"
-        need_bw = any(ctx.needs_input_grad)
+        need_bw = bool(save) and any(ctx.needs_input_grad)
         W = [params[2 * i] for i in range(5)]
         b = [params[2 * i + 1] for i in range(5)]
         bf, bd, br = params[11], params[13], params[17]
@@ -416,4 +418,4 @@ class SkinChainFn(torch.autograd.Function):
             code_part(dY[0], W[0], g[0], g[1], rb0)
         ctx.act = None
         gret[14] = gret[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
-        return (gpts.reshape(pshape), gcode, None, None) + tuple(gret)
+        return (gpts.reshape(pshape), gcode, None, None, None) + tuple(gret)

@@ -78,15 +78,20 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
             and all(sg[0] == SEG_BCAST and sg[3] == nbins for sg in segs[1:])
             and trunk_tc.supported(model, sum(sg[2] for sg in segs[1:])) and embed_xyz.N_freqs == 10 and k == 3):
         env = inputs[2] if len(segs) == 3 else None
-        fn = chain_tc.TrunkChainFn if config.fused else trunk_tc.TrunkTcFn
-        out = fn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
+        if config.fused:
+            out = chain_tc.TrunkChainFn.apply(pts2, inputs[1], env, nbins, win, torch.is_grad_enabled(), *model.param_list())
+        else:
+            out = trunk_tc.TrunkTcFn.apply(pts2, inputs[1], env, nbins, win, *model.param_list())
         return out.reshape(Bn, nbins, 4)
     # tensor-core (split-precision) path for the reference's nerf_skin on [PE(xyz) | pose code]
     if (config.precision == "fp16" and not sigma_only and len(segs) == 2 and segs[0][0] == SEG_PE
             and segs[1][0] == SEG_BCAST and segs[1][3] in (nbins, M) and k == 3 and embed_xyz.N_freqs == 10
             and skin_tc.supported(model, segs[1][2])):
-        fn = chain_tc.SkinChainFn if config.fused else skin_tc.SkinMlpTcFn
-        out = fn.apply(pts2, inputs[1], nbins, win, *model.param_list()).reshape(Bn, nbins, 32)
+        if config.fused:
+            out = chain_tc.SkinChainFn.apply(pts2, inputs[1], nbins, win, torch.is_grad_enabled(), *model.param_list())
+        else:
+            out = skin_tc.SkinMlpTcFn.apply(pts2, inputs[1], nbins, win, *model.param_list())
+        out = out.reshape(Bn, nbins, 32)
         return out if _pitched else out[..., :model.out_channels]
     # density-only grid query (mesh extraction): the sigma program of the chain kernel, inference only
     if (config.precision == "fp16" and config.fused and sigma_only and len(segs) == 1 and segs[0][0] == SEG_PE and k == 3

@@ -119,3 +119,88 @@ def default_opts():
     return types.SimpleNamespace(neudbs=True, lbs=False, dist_corresp=False, use_corresp=False,
                                  use_corr=False, use_ot=False, symm_shape=False, scale_rgb=1.3,
                                  rgb_filter=False, s3im_loss=False)
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+# the full default-flag step of MoDA: nerf_feat / nerf_vis, a paired target frame with its
+# own camera and bone transforms, per-ray observations.  Same conventions as above: plain CPU fp32 tensors.
+IMG_SIZE = 512
+NUM_FEAT = 16
+OBJ_BOUND = (0.18, 0.2, 0.22)
+
+
+def _small_rotation(gen, n, scale):
+    """(n,3,3) rotation matrices from a small random quaternion perturbation of the identity."""
+    q = torch.tensor([1.0, 0, 0, 0], dtype=F32) + scale * torch.randn(n, 4, generator=gen, dtype=F32)
+    q = q / q.norm(dim=-1, keepdim=True)
+    r, i, j, k = q.unbind(-1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(n, 3, 3)
+
+
+def _random_dq(gen, n, num_bones, rs=0.2, ts=0.05):
+    r = torch.tensor([1.0, 0, 0, 0], dtype=F32) + rs * torch.randn(n, num_bones, 4, generator=gen, dtype=F32)
+    r = r / r.norm(dim=-1, keepdim=True)
+    t = ts * torch.randn(n, num_bones, 3, generator=gen, dtype=F32)
+    tq = torch.cat([torch.zeros(n, num_bones, 1, dtype=F32), t], -1)
+    return torch.cat([r, 0.5 * q_mul_np(tq, r)], -1).reshape(n, num_bones * 8)
+
+
+def make_full_problem(n_rays, seed=0, num_bones=NUM_BONES):
+    """``make_problem`` + everything the default-flag training step reads (nnutils/moda.py:344-348, 447-449,
+    1215-1327; geom_utils.py:746-794): ``nerf_feat`` (5x128 -> 16), ``nerf_vis`` (5x64 -> 1), rays cast from two
+    cameras (the first half of the rays belongs to frame 0 and targets frame 1, the second half the reverse),
+    ``rtk_vec`` / ``rtk_vec_target`` (N,21) = [R | T | Kinv], ``bone_rts_target`` and the per-ray observations."""
+    p = make_problem(n_rays, seed=seed, num_bones=num_bones)
+    gen = torch.Generator().manual_seed(seed + 7919)
+    p["nerf_feat"] = nerf_state(gen, D=5, W=128, in_channels_xyz=PE_XYZ, in_channels_dir=0, out_channels=NUM_FEAT,
+                                init_beta=1.0)
+    p["nerf_vis"] = nerf_state(gen, D=5, W=64, in_channels_xyz=PE_XYZ, in_channels_dir=0, out_channels=1,
+                               init_beta=0.01)
+    # keep the visibility logits off the 0.5 decision threshold of rendering.py:215 (a random-init net outputs ~0)
+    p["nerf_vis"]["rgb.0.weight"] = p["nerf_vis"]["rgb.0.weight"] * 8.0
+    N = n_rays
+    h = N // 2
+    Rm = _small_rotation(gen, 2, 0.05)
+    Tm = torch.tensor([[0.0, 0.0, 0.3]], dtype=F32) + 0.02 * torch.randn(2, 3, generator=gen, dtype=F32)
+    K = torch.tensor([[600.0, 600.0, 256.0, 256.0], [620.0, 610.0, 250.0, 260.0]], dtype=F32)
+    Kinv = torch.zeros(2, 3, 3, dtype=F32)
+    Kinv[:, 0, 0] = 1 / K[:, 0]
+    Kinv[:, 1, 1] = 1 / K[:, 1]
+    Kinv[:, 0, 2] = -K[:, 2] / K[:, 0]
+    Kinv[:, 1, 2] = -K[:, 3] / K[:, 1]
+    Kinv[:, 2, 2] = 1
+    frame = torch.cat([torch.zeros(h, dtype=torch.long), torch.ones(N - h, dtype=torch.long)])
+    xys = torch.rand(N, 2, generator=gen, dtype=F32) * (IMG_SIZE - 1)
+    xy1 = torch.cat([xys, torch.ones(N, 1, dtype=F32)], -1)
+    xyz3d = torch.einsum("nj,nij->ni", xy1, Kinv[frame])            # xy1s.matmul(Kinv^T), geom_utils.py:764
+    rays_d = torch.einsum("ni,nij->nj", xyz3d, Rm[frame])           # .matmul(Rmat), :765
+    rays_o = -torch.einsum("ni,nij->nj", Tm[frame], Rm[frame])      # :766
+    rtk = torch.cat([Rm.reshape(2, 9), Tm, Kinv.reshape(2, 9)], -1)
+    rays = p["rays"]
+    rays["rays_o"], rays["rays_d"], rays["xys"] = rays_o, rays_d, xys
+    rays["rtk_vec"] = rtk[frame]
+    rays["rtk_vec_target"] = rtk[1 - frame]
+    rays["bone_rts_target"] = _random_dq(gen, N, num_bones)
+    rays["feats_at_samp"] = torch.randn(N, NUM_FEAT, generator=gen, dtype=F32)
+    rays["img_at_samp"] = torch.rand(N, 3, generator=gen, dtype=F32)
+    rays["sil_at_samp"] = (torch.rand(N, 1, generator=gen, dtype=F32) < 0.6).float()
+    rays["vis_at_samp"] = (torch.rand(N, 1, generator=gen, dtype=F32) < 0.9).float()
+    rays["flo_at_samp"] = 0.05 * torch.randn(N, 2, generator=gen, dtype=F32)
+    cfd = torch.rand(N, 1, generator=gen, dtype=F32)
+    rays["cfd_at_samp"] = torch.where(cfd < 0.2, torch.zeros_like(cfd), cfd)
+    p["obj_bound"] = torch.tensor(OBJ_BOUND, dtype=F32)
+    p["img_size"] = IMG_SIZE
+    return p
+
+
+def full_opts(**kw):
+    """``default_opts`` with the reference's default flag values for the full step (nnutils/moda.py:149-170)."""
+    o = default_opts()
+    o.dist_corresp, o.use_corresp, o.use_ot, o.use_corr = True, True, True, False
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
