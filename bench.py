@@ -344,7 +344,8 @@ def run_ours(args):
                                       "8x256 nerf_coarse + 5x64 nerf_skin, AdamW step, grad all-reduce" % (R, SAMPLES, BONES),
                           "rays_per_gpu": R, "samples_per_ray": SAMPLES, "bones": BONES, "parallelism": "dp%d" % world,
                           "l2_policy": "inputs+activations per step (>10 GB) exceed the 126 MB L2",
-                          "launch_modes": {"trunk_chains_as_cta_pairs": bool(_lib.lib().moda_chain_get_pair()),
+                          "launch_modes": {"trunk_chains_as_cta_pairs": bool(_cfg.trunk_pair and _lib.lib().moda_chain_pair_available()),
+                                           "trunk_tiles_in_flight_per_cta": _cfg.trunk_slots if _cfg.trunk_pair else 1,
                                            "wgrad_side_stream": bool(_cfg.side_stream)}},
                "e2e": {"value": round(R * world / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),

@@ -12,7 +12,8 @@
  *   - "ld*" arguments are row strides in elements, so column slices of wider matrices can be passed;
  *   - return value 0 = success; >0 = cudaError_t of the launch; <0 = argument check failed;
  *     moda_last_error() returns the thread-local message; nothing synchronises the device;
- *   - re-entrant: no global mutable state; work is issued only on the stream argument;
+ *   - re-entrant: no mutable state except two atomics (a sticky "cluster launch unavailable" flag and the debug trace
+ *     hook moda_chain_set_trace); per-device attributes are set on every launch; work is issued only on the stream argument;
  *   - optional pointers may be NULL where stated.
  */
 #ifndef MODA_B200_H
@@ -206,18 +207,18 @@ int moda_chain_trunk_fwd(const float* xyz, long long P, int rep /* samples per r
                          const float* rowbias /* (P/rep,128) per-ray part of the dir layer */, const float* ws,
                          const float* bs, const float* Wr, const float* br, void* A0 /* (P,64) fp16 PE */,
                          void* H /* (8,P,256) */, void* fin /* (P,256) */, void* dfe /* (P,128) */,
-                         unsigned int* maskbits /* (8,tiles2,8,128) ReLU sign bits, tiles2 = ceil(P/128) rounded up to even */, float* raw /* Density-only pass of nerf_coarse for grid queries (extract_mesh, nnutils/train_utils.py:1377-1404 with
+                         unsigned int* maskbits /* (8,tiles2,8,128) ReLU sign bits, tiles2 = ceil(P/128) rounded up to even */,
+                         float* raw /* (P,4) */, int mode /* MODA_CHAIN_* bits */, cudaStream_t stream);
+/* Density-only pass of nerf_coarse for grid queries (extract_mesh, nnutils/train_utils.py:1377-1404 with
  * nerf.py:176-180 sigma_only=True): layers 1-8 + sigma head on tensor cores, nothing saved.  wpack as for
  * moda_chain_trunk_fwd; sigma (P) fp32. */
 int moda_chain_trunk_sigma(const float* xyz, long long P, int F, const float* win, const void* wpack,
-                           const float* const* biases, const float* ws, const float* bs, float* sigma,
+                           const float* const* biases, const float* ws, const float* bs, float* sigma, int mode,
                            cudaStream_t stream);
-/* (P,4) */,
-                         cudaStream_t stream);
 int moda_chain_trunk_bwd(const void* d_dfe /* (P,128) fp16 */, const float* gsig /* (P) */, const float* ws,
                          const float* rscale, const void* wpackT /* fp16 (256, 42*64) */,
                          const unsigned int* maskbits, long long P, void* d_fin /* (P,256) */,
-                         void* dY /* (8,P,256) */, void* d_pe /* (P,64) */, cudaStream_t stream);
+                         void* dY /* (8,P,256) */, void* d_pe /* (P,64) */, int mode, cudaStream_t stream);
 int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const float* win,
                         const void* wpack /* fp16 (64, 18*64): [Whi | Wlo] per layer */,
                         const float* const* biases /* rb1, b2, b3, b4, rb5, bfinal, bdir64, brgb64 */, void* A0,
@@ -226,13 +227,17 @@ int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const flo
 /* debug: device buffer (>= 16004 int64, zeroed) that subsequent chain launches fill with an event timeline of
  * block 0's third tile (tools/chain_trace.py); NULL switches tracing off */
 int moda_chain_set_trace(long long* buf);
-/* on != 0: the 256-wide chains (moda_chain_trunk_fwd / _sigma / _bwd) are launched as clusters of two CTAs that share
- * one tcgen05.mma.cta_group::2 stream (M = 256 = two tiles; each CTA stages half of every weight chunk).  Results are
- * bit-identical to the single-CTA kernels; +1.7 % on the training step, +5.5 % on the density grid.
- * On by default; if the cluster cannot be launched the library falls back to the single-CTA kernels for good.  The sign-bit
- * buffers must be sized for an EVEN tile count in either mode. */
-int moda_chain_set_pair(int on);
-int moda_chain_get_pair(void); /* the mode in effect: 1 = CTA pairs, 0 = single-CTA kernels (requested, or after a fallback) */
+/* `mode` of the 256-wide chains (moda_chain_trunk_fwd / _sigma / _bwd), a per-call argument:
+ *   MODA_CHAIN_PAIR       launched as clusters of two CTAs sharing one tcgen05.mma.cta_group::2 stream (M = 256 = two
+ *                         tiles; each CTA stages half of every weight chunk);
+ *   MODA_CHAIN_TWO_SLOTS  (with MODA_CHAIN_PAIR) two tiles in flight per CTA: the tensor core works on one tile's layer
+ *                         while the other tile's epilogue drains its accumulator (used when every CTA gets >= 2 tiles).
+ * Results are bit-identical in every mode.  If a cluster cannot be launched the library falls back to the single-CTA
+ * kernels for the rest of the process (moda_chain_pair_available() then returns 0).  The sign-bit buffers must be
+ * sized for an EVEN tile count in every mode. */
+#define MODA_CHAIN_PAIR 1
+#define MODA_CHAIN_TWO_SLOTS 2
+int moda_chain_pair_available(void);
 int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);

@@ -62,14 +62,13 @@ SIGNATURES = {
     "moda_colsum16": [c_p, c_i, c_p, c_ll, c_i, c_p, c_p],
     "moda_segsum16": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
     "moda_loss_scale": [c_p, c_ll, c_f, c_p, c_p, c_p],
-    "moda_chain_trunk_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 12,
-    "moda_chain_trunk_sigma": [c_p, c_ll, c_i, c_fp, c_p, c_pp, c_p, c_p, c_p, c_p],
-    "moda_chain_trunk_bwd": [c_p] * 6 + [c_ll] + [c_p] * 4,
+    "moda_chain_trunk_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 11 + [c_i, c_p],
+    "moda_chain_trunk_sigma": [c_p, c_ll, c_i, c_fp, c_p, c_pp, c_p, c_p, c_p, c_i, c_p],
+    "moda_chain_trunk_bwd": [c_p] * 6 + [c_ll] + [c_p] * 3 + [c_i, c_p],
     "moda_chain_skin_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 7,
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,
     "moda_chain_set_trace": [c_p],
-    "moda_chain_set_pair": [c_i],
-    "moda_chain_get_pair": [],
+    "moda_chain_pair_available": [],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 
@@ -89,8 +88,7 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = ctypes.c_int
-    # config.trunk_pair: CTA-pair launch mode of the trunk chains (library default: on)
-    L.moda_chain_set_pair(0 if os.environ.get("MODA_B200_TRUNK_PAIR", "1") == "0" else 1)
+    L.moda_chain_pair_available.restype = ctypes.c_int   # a query, not a status code
     _lib = L
     return L
 

@@ -192,7 +192,7 @@ def trunk_sigma(xyz, win, params):
     biases = (ctypes.c_void_p * 8)(*[ptr(params[2 * i + 1]) for i in range(8)])
     sigma = torch.empty(P, 1, device=dev, dtype=torch.float32)
     call("moda_chain_trunk_sigma", ptr(xyz), P, len(win), wa, ptr(wpack), biases, ptr(_al16(Ws)), ptr(bs), ptr(sigma),
-         stream())
+         config.chain_mode(), stream())
     return sigma
 
 
@@ -230,7 +230,7 @@ class TrunkChainFn(torch.autograd.Function):
         call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(_al16(Ws)), ptr(bs),
              ptr(_al16(Wr)),
              ptr(br), ptr(A0), ptr(H), ptr(fin), ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(raw),
-             stream())
+             config.chain_mode(), stream())
         if need_bw:
             ctx.save_for_backward(xyz, code, raw, *params)
             ctx.act = (A0, H, fin, dfe, bits)
@@ -268,7 +268,7 @@ class TrunkChainFn(torch.autograd.Function):
         dY = torch.empty(8, P, 256, device=dev, dtype=HALF)
         d_pe = torch.empty(P, 64, device=dev, dtype=HALF)
         call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(_al16(Ws.reshape(-1))), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
-             ptr(d_fin), ptr(dY), ptr(d_pe), stream())
+             ptr(d_fin), ptr(dY), ptr(d_pe), config.chain_mode(), stream())
         # weight gradients (bias gradients ride along as column sums of the dY operand)
         gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)

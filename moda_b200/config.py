@@ -25,15 +25,29 @@ def set_precision(p):
 # side stream (tail/ramp-up overlap of the persistent kernels); "0" keeps everything on the current stream.
 side_stream = os.environ.get("MODA_B200_SIDE_STREAM", "1") != "0"
 
-# trunk_pair: run the 256-wide chain kernels as CTA pairs (tcgen05 cta_group::2; csrc/chain.cu, PAIR = 1).  Results
-# are bit-identical; +1.7 % on the training step and +5.5 % on the density grid, so the default is on (the library
-# falls back to the single-CTA kernels by itself if a cluster launch fails).  MODA_B200_TRUNK_PAIR=0 switches it off.
+# Launch mode of the 256-wide chains (csrc/chain.cu), passed to the library with every call (no library-side state):
+# trunk_pair:  CTA pairs (tcgen05 cta_group::2, each CTA stages half of every weight chunk).  MODA_B200_TRUNK_PAIR=0: off.
+# trunk_slots: two tiles in flight per CTA (needs trunk_pair): the tensor core works on one tile's layer while the other
+#              tile's epilogue drains its accumulator.  MODA_B200_TRUNK_SLOTS=1 selects one tile per CTA.
+# Results are bit-identical in every mode; the library falls back to single-CTA kernels if a cluster cannot be placed.
 trunk_pair = os.environ.get("MODA_B200_TRUNK_PAIR", "1") != "0"
+trunk_slots = 1 if os.environ.get("MODA_B200_TRUNK_SLOTS", "2") == "1" else 2
 
 
 def set_trunk_pair(on):
     """Switches the CTA-pair launch mode of the nerf_coarse chains (takes effect at the next call)."""
     global trunk_pair
-    from . import _lib
     trunk_pair = bool(on)
-    _lib.call("moda_chain_set_pair", int(trunk_pair))
+
+
+def set_trunk_slots(n):
+    """1 or 2 tiles in flight per CTA for the nerf_coarse chains (2 needs the CTA-pair mode)."""
+    global trunk_slots
+    if n not in (1, 2):
+        raise ValueError("trunk_slots must be 1 or 2")
+    trunk_slots = n
+
+
+def chain_mode():
+    """The `mode` argument of moda_chain_trunk_*: bit 0 = CTA pairs, bit 1 = two tile slots."""
+    return (1 if trunk_pair else 0) | (2 if (trunk_pair and trunk_slots == 2) else 0)

@@ -39,7 +39,7 @@ constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_SAVE_MAPS = 14;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_DUTY = 48;
-constexpr int head_smem(int nh) { return nh * 128 * 4 * 4; }   // [warp-of-quarter][row][4] floats
+constexpr int head_smem(int nh) { return (nh > 1 ? nh - 1 : 1) * 128 * 4 * 4; }   // [warp-of-quarter - 1][row][4] floats (per tile slot)
 
 // Epilogue flavour bits (tested at run time: every branch is uniform across the CTA).
 enum : int {
@@ -68,23 +68,26 @@ struct Step {
   int save_map;        // TMA-store descriptor for the fp16 result, -1: not saved
   int mask_slot;
   int release_pe;      // last step of the tile that reads the PE chunks
-  int bias_row;        // row of the shared-memory bias table holding `bias`
+  int bias_off;        // float offset of `bias` (or of the staged per-tile rowbias, one copy per tile slot) in the bias table
   int sd_wait;         // stores_done phases (steps with store-warp work) of this tile that precede this step
-  int tile_bias;       // rowbias is constant over a tile (rep % 128 == 0): staged into bias_row at every tile start
+  int tile_bias;       // rowbias is constant over a tile (rep % 128 == 0): staged at bias_off (+ slot * n) at every tile start
   const float* bias;     // (n) or null
   const float* rowbias;  // (M / rep, n) or null
-  unsigned char a_chunk[MAX_KC];   // shared-memory chunk feeding K chunk kc
-  unsigned char a_gen[MAX_KC];     // which write of that chunk within the tile it must see
+  // per K chunk, packed (one constant-bank read on the MMA thread): bits 0-7 shared-memory chunk feeding it, bits 8-15
+  // which write of that chunk within the tile it must see, bit 16: that write was made by the epilogue of an earlier
+  // MMA step of the tile (with a single-buffered accumulator, i.e. two tile slots, the acc_free wait already covers it)
+  unsigned int a_info[MAX_KC];
   unsigned short b_col[MAX_KC];    // chunk index (64-column block) in the packed weights
 };
 
 struct Program {
-  int nsteps, num_tiles, rep, nchunks, stages, nbias;
+  int nsteps, num_tiles, rep, nchunks, stages;
+  int bias_floats;       // size of the shared-memory bias / head-vector table
   int mask_tiles;        // tile stride of the sign-bit buffer: the tile count rounded up to even (same in both launch modes)
   int has_tile_bias;     // some step has tile_bias set
-  // head vectors staged behind the biases in shared memory: vec0 (ws, or cvec of the adjoint) from row vec_row,
-  // vec1 (Wr, (3, n)) from row vec_row1; -1: none
-  int vec_row, vec_row1, vec_len0, vec_len1;
+  // head vectors staged behind the biases in shared memory: vec0 (ws, or cvec of the adjoint) at float offset vec_off0,
+  // vec1 (Wr, (3, n)) at vec_off1; -1: none
+  int vec_off0, vec_off1, vec_len0, vec_len1;
   const float* vec0; const float* vec1;
   long long M;
   int wpt[MAX_CHUNKS];   // writes per tile of each chunk (ready-barrier phases per tile)
@@ -175,17 +178,18 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
 
 // debug timeline: every traced thread appends records of 4 x int64 (event, a, b, SM clock) to its own region
 // (region = event / 10 < 32, 1000 records each; tr[region] counts them).  Plain stores: the trace costs a few cycles.
-__device__ __forceinline__ void trace_rec(long long* tr, int ev, int a, int b) {
+// The record count of a region lives in a register of the (single) thread that writes it (`tr_n` in the caller's
+// scope): nothing is read back from memory, so an event costs a handful of store instructions.
+__device__ __forceinline__ void trace_rec(long long* tr, int ev, int a, int b, int& n) {
   const int region = ev / 10;
-  const long long i = tr[region];
-  if (i < 1000) {
-    long long* r = tr + 32 + 4 * (region * 1000 + i);
+  if (n < 1000) {
+    long long* r = tr + 32 + 4 * (region * 1000 + n);
     r[0] = ev; r[1] = a; r[2] = b; r[3] = clock64();
-    tr[region] = i + 1;
+    tr[region] = ++n;
   }
 }
 #ifdef MODA_CHAIN_TRACE
-#define MODA_TR(on, ev, a, b) do { if (on) trace_rec(pg.trace, (ev), (a), (b)); } while (0)
+#define MODA_TR(on, ev, a, b) do { if (on) trace_rec(pg.trace, (ev), (a), (b), tr_n); } while (0)
 #else
 #define MODA_TR(on, ev, a, b) do { } while (0)   // product build: no trace code in the hot loops (tools/build_variant.sh trace -DMODA_CHAIN_TRACE)
 #endif
@@ -233,7 +237,9 @@ struct EpiCtx {
   bool live, lane0;
   float rscale, lscale;
   int tr;               // trace event base (0: off)
-  uint32_t ready2_remote;   // CTA pairs: cluster address of the leader's ready2[0] (0: single-CTA kernel)
+  int slot;             // tile slot of this epilogue group (two tiles in flight per CTA: 0 / 1)
+  mutable int trn;      // trace records written by this thread
+  uint32_t ready2_remote;   // CTA pairs: cluster address of the leader's ready2[slot][0] (0: single-CTA kernel)
 };
 
 // One step's epilogue for this warp (flavour F = st.flags).  Sub-blocks of 16 columns are processed
@@ -246,6 +252,8 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
                                          unsigned long long pm0, unsigned long long pm1) {
   constexpr int SPC = 4 / NH;                  // sub-blocks per chunk for this warp
   const int F = (CF >= 0) ? CF : Frt;   // CF >= 0: flavour known at compile time (straight-line hot paths)
+  int& tr_n = cx.trn;
+  (void)tr_n;
   const bool MMA = !(F & (E_LOAD16 | E_LOAD32));
   const int n = (CN > 0) ? CN : st.n;   // CN > 0: width known at compile time -> the sub-block loop unrolls completely
   const int nch = n >> 6;
@@ -253,7 +261,19 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
   const uint32_t t_addr = cx.tmem_row + acc_col;
   auto col_of = [&](int i) { return (i / SPC) * 64 + (cx.h + NH * (i % SPC)) * 16; };
   float va[16], vb[16];
-  if (MMA) tmem_ld16_issue(t_addr + (uint32_t)col_of(0), va);
+#ifdef MODA_EXP_NO_TMEMLD   // timing experiment: the epilogue does not read the accumulator
+#define MODA_TMEM_LD_ISSUE(addr, v) do { for (int j_ = 0; j_ < 16; ++j_) (v)[j_] = __uint_as_float((addr) + j_); } while (0)
+#define MODA_TMEM_LD_WAIT() do { } while (0)
+#else
+#define MODA_TMEM_LD_ISSUE(addr, v) tmem_ld16_issue((addr), (v))
+#define MODA_TMEM_LD_WAIT() tmem_ld_wait()
+#endif
+#ifdef MODA_EXP_NO_STS      // timing experiment: the epilogue does not write the A chunks
+#define MODA_STS128(...) do { } while (0)
+#else
+#define MODA_STS128(...) sts128(__VA_ARGS__)
+#endif
+  if (MMA) MODA_TMEM_LD_ISSUE(t_addr + (uint32_t)col_of(0), va);
   // ReLU sign bits: 16 per sub-block (column j <-> bit 15 - j, set = pre-activation >= 0); this thread's sub-blocks
   // of the step are packed four to a 64-bit word (at most two words) -> at most two global accesses per thread
   // and step instead of one per sub-block
@@ -270,7 +290,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
   if (F & E_RANK1) rvv = cx.live ? pg.gsig[cx.row] * cx.rscale : 0.f;
   const float* rb = nullptr;
   if (F & E_ROWBIAS) rb = st.rowbias + (size_t)((cx.live ? cx.row : 0) / pg.rep) * n;
-  const uint32_t sb = cx.s_bias + (uint32_t)(st.bias_row * ACC_STRIDE * 4);
+  const uint32_t sb = cx.s_bias + (uint32_t)((st.bias_off + (st.tile_bias ? cx.slot * st.n : 0)) * 4);
   auto sub = [&](const int i, float* __restrict__ v, float* __restrict__ vn) {
     const int cc = col_of(i);                // first of this thread's 16 columns
     const int c64 = cc >> 6;                 // chunk within the result
@@ -298,8 +318,8 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
           v[4 * j + 2] = f.z * cx.lscale; v[4 * j + 3] = f.w * cx.lscale;
         }
       } else {
-        tmem_ld_wait();
-        if (i + 1 < nsub) tmem_ld16_issue(t_addr + (uint32_t)col_of(i + 1), vn);
+        MODA_TMEM_LD_WAIT();
+        if (i + 1 < nsub) MODA_TMEM_LD_ISSUE(t_addr + (uint32_t)col_of(i + 1), vn);
       }
       if (F & E_BIAS) {
 #pragma unroll
@@ -387,8 +407,8 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
       if (F & E_SMEM) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          sts128(crow + (((p0 + j) ^ cx.sw) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                 pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          MODA_STS128(crow + (((p0 + j) ^ cx.sw) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                      pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
         if (F & E_LO) {
           const uint32_t crow_lo = cx.sA + (uint32_t)((st.out_lo_chunk + c64) * CHUNK_BYTES + cx.trow * 128);
 #pragma unroll
@@ -407,7 +427,6 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
 #endif
       __syncwarp();
       if (cx.lane0) {
-        MODA_TR(cx.tr, cx.tr + 1, c64, 0);
         mbar_arrive(&ready[chunk]);
         if (F & E_LO) mbar_arrive(&ready[st.out_lo_chunk + c64]);
         if (cx.ready2_remote) {   // CTA pair: the leader's MMA thread counts both CTAs' writers
@@ -492,10 +511,20 @@ constexpr int P_FWD = 0, P_BWD = 1;   // which set of straight-line epilogue fla
 // Cross-CTA signalling: the peer's TMA loads count their bytes on the leader's w_full; writers of both CTAs arrive on
 // the leader's ready2 / acc_free2 / stores_done2 (remote mbarrier arrives); tcgen05.commit multicasts acc_full,
 // w_empty and pe_free to both CTAs.
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR>
-__global__ void __launch_bounds__((3 + EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
+//
+// SLOTS = 2 (CTA pairs only): TWO tiles in flight per CTA.  Each tile slot has its own A chunks, its own TMEM
+// accumulator (256 columns), its own group of EPI_WARPS epilogue warps and its own barriers; the MMA thread alternates
+// between the slots step by step, so the tensor core works on one tile's layer while the other tile's epilogue drains
+// its accumulator and rewrites its A chunks: the accumulator-full -> epilogue -> chunk-ready -> MMA round trip of a
+// tile (which left the tensor pipe idle for ~2/3 of every step with one tile per CTA) is hidden
+// behind the other tile's MMAs.  A slot's accumulator is single-buffered: the next step's MMAs start when the
+// epilogue has drained it completely.  Per-tile arithmetic is unchanged, so results are bit-identical.
+// Tiles of CTA b: b, b + G, b + 2G, ... (G = grid); the j-th of them runs in slot j % SLOTS as that slot's tile j / SLOTS.
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR, int SLOTS>
+__global__ void __launch_bounds__((3 + SLOTS * EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
 chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
   static_assert(!PAIR || BOX_ROWS == 128, "CTA pairs: 256-wide chains only");
+  static_assert(SLOTS == 1 || (SLOTS == 2 && PAIR == 1 && PE_WARPS == 1), "two tile slots: CTA-pair kernels only");
   constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;       // TMEM columns per accumulator
   constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   constexpr int BOX_BYTES = BOX_ROWS * 128;
@@ -509,53 +538,72 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                            // nchunks x 16 KB
-  uint8_t* sB = sA + (size_t)pg.nchunks * CHUNK_BYTES;           // stages x STAGE_BYTES
-  float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);
-  float* s_bias = s_head + head_smem(NH) / 4;                    // nbias x ACC_STRIDE floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.nbias * ACC_STRIDE);
+  uint8_t* sA = smem;                                            // SLOTS x nchunks x 16 KB
+  uint8_t* sB = sA + (size_t)SLOTS * pg.nchunks * CHUNK_BYTES;   // stages x STAGE_BYTES
+  float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);   // SLOTS x head_smem
+  float* s_bias = s_head + SLOTS * head_smem(NH) / 4;            // bias_floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.bias_floats);
   uint64_t* w_full = bars;                       // [MAX_STAGES]
   uint64_t* w_empty = w_full + MAX_STAGES;       // [MAX_STAGES]
-  uint64_t* ready = w_empty + MAX_STAGES;        // [MAX_CHUNKS] chunk (re)written and visible to the tensor core
-  uint64_t* acc_full = ready + MAX_CHUNKS;       // [2]
+  uint64_t* ready = w_empty + MAX_STAGES;        // [2][MAX_CHUNKS] chunk (re)written and visible to the tensor core (per slot)
+  uint64_t* acc_full = ready + 2 * MAX_CHUNKS;   // [2] per accumulator
   uint64_t* acc_free = acc_full + 2;             // [2]
-  uint64_t* pe_free = acc_free + 2;              // [1]
-  uint64_t* stores_done = pe_free + 1;           // [1] one phase per step: its TMA stores have read their chunks
+  uint64_t* pe_free = acc_free + 2;              // [2] per slot
+  uint64_t* stores_done = pe_free + 2;           // [2] per slot, one phase per step: its TMA stores have read their chunks
   // CTA pairs, used in the leader CTA only: the same three conditions counted over both CTAs
-  uint64_t* ready2 = stores_done + 1;            // [MAX_CHUNKS]
-  uint64_t* acc_free2 = ready2 + MAX_CHUNKS;     // [2]
-  uint64_t* stores_done2 = acc_free2 + 2;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done2 + 1);
+  uint64_t* ready2 = stores_done + 2;            // [2][MAX_CHUNKS]
+  uint64_t* acc_free2 = ready2 + 2 * MAX_CHUNKS; // [2]
+  uint64_t* stores_done2 = acc_free2 + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done2 + 2);
+  constexpr int SLOT_CHUNK_BYTES_MAX = MAX_CHUNKS * CHUNK_BYTES;
+  (void)SLOT_CHUNK_BYTES_MAX;
+  const uint32_t slot_bytes = (uint32_t)pg.nchunks * CHUNK_BYTES;   // A chunks of one tile slot
+  // accumulator of (slot, n-th MMA step of that slot) and the phase its barriers are in: one tile per CTA ping-pongs
+  // over both accumulators step by step, two tile slots own one accumulator each
+  auto acc_of = [](int slot, uint32_t ctr) { return SLOTS == 2 ? slot : (int)(ctr & 1); };
+  auto acc_phase = [](uint32_t ctr) { return SLOTS == 2 ? (ctr & 1) : ((ctr >> 1) & 1); };
+  // Scope of the MMA thread's waits on barriers that the PEER CTA's warps arrive on.  What those arrivals order is the
+  // peer's shared memory, already visible to the peer's async proxy (fence.proxy.async before the arrive) and read only
+  // by the peer's tensor core / TMA once this thread issues the MMA; this thread reads none of it.  A cluster-scope
+  // acquire makes ptxas add an L1 invalidation (CCTL.IVALL) after every wait, on the kernel's serial thread.
+#ifdef MODA_MMA_WAIT_CLUSTER
+  constexpr int MMA_WAIT_CLUSTER = PAIR;
+#else
+  constexpr int MMA_WAIT_CLUSTER = 0;
+#endif
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = crank == 0;
   (void)leader;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = pg.num_tiles;
+  const int ntile = (T - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA (grid <= T)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[i], pg.from_pe[i] ? PE_WARPS : EPI_WARPS);
-    mbar_init(stores_done, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS); }
-    mbar_init(pe_free, 1);
-    if (PAIR) {
-      for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready2[i], 2 * (pg.from_pe[i] ? PE_WARPS : EPI_WARPS));
-      for (int i = 0; i < 2; ++i) mbar_init(&acc_free2[i], 2 * EPI_WARPS);
-      mbar_init(stores_done2, 2);
+    for (int k = 0; k < 2; ++k) {
+      for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[k * MAX_CHUNKS + i], pg.from_pe[i] ? PE_WARPS : EPI_WARPS);
+      mbar_init(&stores_done[k], 1);
+      mbar_init(&acc_full[k], 1); mbar_init(&acc_free[k], EPI_WARPS);
+      mbar_init(&pe_free[k], 1);
+      if (PAIR) {
+        for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready2[k * MAX_CHUNKS + i], 2 * (pg.from_pe[i] ? PE_WARPS : EPI_WARPS));
+        mbar_init(&acc_free2[k], 2 * EPI_WARPS);
+        mbar_init(&stores_done2[k], 2);
+      }
     }
     fence_barrier_init();
   }
-  // biases of every step, staged once (step s reads row bias_row[s])
+  // biases of every step, staged once (step s reads the bias_off[s] region of the table)
   for (int s = 0; s < pg.nsteps; ++s) {
     const Step& st = pg.st[s];
     if (st.bias)
-      for (int i = threadIdx.x; i < st.n; i += blockDim.x) s_bias[st.bias_row * ACC_STRIDE + i] = st.bias[i];
+      for (int i = threadIdx.x; i < st.n; i += blockDim.x) s_bias[st.bias_off + i] = st.bias[i];
   }
-  if (pg.vec_row >= 0)
-    for (int i = threadIdx.x; i < pg.vec_len0; i += blockDim.x) s_bias[pg.vec_row * ACC_STRIDE + i] = pg.vec0[i];
-  if (pg.vec_row1 >= 0)
-    for (int i = threadIdx.x; i < pg.vec_len1; i += blockDim.x) s_bias[pg.vec_row1 * ACC_STRIDE + i] = pg.vec1[i];
+  if (pg.vec_off0 >= 0)
+    for (int i = threadIdx.x; i < pg.vec_len0; i += blockDim.x) s_bias[pg.vec_off0 + i] = pg.vec0[i];
+  if (pg.vec_off1 >= 0)
+    for (int i = threadIdx.x; i < pg.vec_len1; i += blockDim.x) s_bias[pg.vec_off1 + i] = pg.vec1[i];
   if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
@@ -569,11 +617,14 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
       prefetch_tmap(&maps.w);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+      // same order as the MMA thread consumes: tile iteration, step, slot (active slots of the iteration), K chunk
+      for (int it = 0; it * SLOTS < ntile; ++it) {
+        const int nact = (ntile - it * SLOTS < SLOTS) ? ntile - it * SLOTS : SLOTS;
         for (int s = 0; s < pg.nsteps; ++s) {
           const Step& st = pg.st[s];
           const int boxes = st.n > BOX_ROWS ? st.n / BOX_ROWS : 1;
           s_dbg[0] = s;
+          for (int slot = 0; slot < nact; ++slot)
           for (int kc = 0; kc < st.kc; ++kc) {
             wait_or_trap<0>(&w_empty[stage], phase ^ 1);
             if (PAIR) {
@@ -599,86 +650,130 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (CTA pairs: the leader's only)
-    if (lane == 0 && leader) {
+    // The WHOLE warp runs the loop converged (every lane polls the barriers) and one elected lane issues the tensor
+    // core instructions: the loop state is then warp-uniform and ptxas keeps descriptors, barrier addresses and counters
+    // in uniform registers.  Run by a single diverged lane, every tcgen05.mma cost an ELECT plus seven R2UR moves and
+    // the ~100 dependent instructions per K chunk, arbitrated against four busy epilogue warps on the same scheduler,
+    // took ~900 cycles against the 512 tensor cycles of the chunk (profiles/r02_*: tensor pipe 37 % active whatever
+    // the epilogue did): this thread, not the tensor core or the epilogue, bounded the kernel.
+    if (leader) {
       int stage = 0;
-      uint32_t phase = 0, mma_ctr = 0, gstep = 0;
-      const uint64_t desc_hi = make_desc(0, 16, 1024);   // everything but the start address
+      uint32_t phase = 0, gstep = 0;
+      uint32_t mma_ctr0 = 0, mma_ctr1 = 0;               // MMA steps issued so far, per slot
+      int tr_n = 0;
+      (void)tr_n;
+      const uint32_t dhi = (uint32_t)(make_desc(0, 16, 1024) >> 32);   // everything but the start address
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
-        for (int s = 0; s < pg.nsteps; ++s, ++gstep) {
+      const uint32_t w_full_u = smem_u32(w_full), w_empty_u = smem_u32(w_empty), acc_full_u = smem_u32(acc_full),
+                     pe_free_u = smem_u32(pe_free);
+      for (int it = 0; it * SLOTS < ntile; ++it) {
+        const int nact = (ntile - it * SLOTS < SLOTS) ? ntile - it * SLOTS : SLOTS;
+        for (int s = 0; s < pg.nsteps; ++s) {
           const Step& st = pg.st[s];
-          s_dbg[1] = (int)gstep;
+          const int nkc = st.kc, n = st.n, rel_pe = st.release_pe;
           // stores_done completes one phase per step that has store-warp work; `sd_need` of them precede this
           // step.  It grows by at most one per step and is waited for at every step, so no phase is skipped
           // (parity waits must observe each one), and the store warp cannot run ahead: it only arrives after it
           // has seen chunks written by an epilogue that was itself released by this thread.
           const uint32_t sd_need = (uint32_t)it * (uint32_t)pg.sd_per_tile + (uint32_t)st.sd_wait;
-          if (st.kc == 0) {
-            if (sd_need > 0) { if (PAIR) wait_or_trap<0, 1>(stores_done2, (sd_need - 1) & 1); else wait_or_trap(stores_done, (sd_need - 1) & 1); }
-            continue;
-          }
-          const int b = mma_ctr & 1;
-          const bool tr = pg.trace && blockIdx.x == 0 && it == 2;
-          MODA_TR(tr, 0, s, 0);
-          // epilogue of two MMA steps ago has drained it
-          if (PAIR) wait_or_trap<0, 1>(&acc_free2[b], ((mma_ctr >> 1) & 1) ^ 1);
-          else wait_or_trap(&acc_free[b], ((mma_ctr >> 1) & 1) ^ 1);
-          tc_fence_after();
-          MODA_TR(tr, 1, s, 0);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
-          const uint32_t idesc = make_idesc(PAIR ? 2 * TILE_M : TILE_M, st.n, 0, 0);
-          for (int kc = 0; kc < st.kc; ++kc) {
-            const int c = st.a_chunk[kc];
-            const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + st.a_gen[kc];
-            // weights first: the producer runs far ahead, so this check completes while the epilogue is still writing
-            // the A chunk, and nothing but the descriptors stands between the chunk's arrival and the MMA issue
-            wait_or_trap(&w_full[stage], phase);
-            MODA_TR(tr, 3, s, kc);
-            if (PAIR) wait_or_trap<0, 1>(&ready2[c], gen & 1); else wait_or_trap(&ready[c], gen & 1);
-            tc_fence_after();
-            MODA_TR(tr, 2, s, kc);
-            // This thread is the serial resource of the kernel (tools/microbench/mma_latency.cu: the tensor pipe answers
-            // within ~200 cycles, a K chunk of N = 256 takes 512): the descriptors of a chunk are built once and the
-            // three K = 16 advances are plain additions (32 bytes = 2 units of the 16-byte address field).
-            const uint64_t ad0 = desc_hi | (uint64_t)(((sA_u + (uint32_t)c * CHUNK_BYTES) & 0x3FFFF) >> 4);
-            const uint64_t bd0 = desc_hi | (uint64_t)(((sB_u + (uint32_t)stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-            if (PAIR) {
-              umma_f16_pair(d_tmem, ad0, bd0, idesc, kc ? 1u : 0u);
-              umma_f16_pair(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
-              umma_f16_pair(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
-              umma_f16_pair(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
-            } else {
-              umma_f16(d_tmem, ad0, bd0, idesc, kc ? 1u : 0u);
-              umma_f16(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
-              umma_f16(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
-              umma_f16(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
+          const uint32_t idesc = make_idesc(PAIR ? 2 * TILE_M : TILE_M, n, 0, 0);
+#pragma unroll 1
+          for (int slot = 0; slot < nact; ++slot, ++gstep) {
+            if (lane == 0) s_dbg[1] = (int)gstep;
+            uint64_t* const sd_bar = PAIR ? &stores_done2[slot] : &stores_done[slot];
+            if (nkc == 0) {
+              if (sd_need > 0) wait_or_trap<0, MMA_WAIT_CLUSTER>(sd_bar, (sd_need - 1) & 1);
+              continue;
             }
-            if (PAIR) umma_commit_pair(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
-            if (++stage == pg.stages) { stage = 0; phase ^= 1; }
+            const uint32_t ctr = slot ? mma_ctr1 : mma_ctr0;
+            const int b = acc_of(slot, ctr);
+            const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && lane == 0;
+            (void)tr;
+            MODA_TR(tr, 0, s, slot);
+            // the epilogue that last read this accumulator has drained it
+            wait_or_trap<0, MMA_WAIT_CLUSTER>(PAIR ? &acc_free2[b] : &acc_free[b], acc_phase(ctr) ^ 1);
+            tc_fence_after();
+            MODA_TR(tr, 1, s, slot);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
+            const uint32_t sA_slot = sA_u + (uint32_t)slot * slot_bytes;
+            uint64_t* const rdy = (PAIR ? ready2 : ready) + slot * MAX_CHUNKS;
+#pragma unroll 1
+            for (int kc = 0; kc < nkc; ++kc) {
+              const uint32_t info = st.a_info[kc];
+              const int c = (int)(info & 0xFF);
+              // weights first: the producer runs far ahead, so this check completes while the epilogue is still writing
+              // the A chunk, and nothing but the descriptors stands between the chunk's arrival and the MMA issue
+              wait_or_trap(&w_full[stage], phase);
+              // two tile slots: chunks written by this tile's earlier MMA-step epilogues are complete once the
+              // accumulator has been handed back (their warps arrived on the chunk barriers before acc_free)
+              if (!(SLOTS == 2 && (info & 0x10000))) {
+                const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + ((info >> 8) & 0xFF);
+                wait_or_trap<0, MMA_WAIT_CLUSTER>(&rdy[c], gen & 1);
+              }
+              tc_fence_after();
+              // the descriptors of a chunk are built once; the three K = 16 advances are plain additions (32 bytes = 2
+              // units of the 16-byte address field, which cannot carry out of its 14 bits within a 16 KB chunk)
+              const uint32_t alo = ((sA_slot + (uint32_t)c * CHUNK_BYTES) & 0x3FFFF) >> 4;
+              const uint32_t blo = ((sB_u + (uint32_t)stage * STAGE_BYTES) & 0x3FFFF) >> 4;
+              if (elect_one()) {
+                if (PAIR) {
+                  umma_f16_pair_lohi(d_tmem, alo, blo, dhi, idesc, kc ? 1u : 0u);
+                  umma_f16_pair_lohi(d_tmem, alo + 2, blo + 2, dhi, idesc, 1u);
+                  umma_f16_pair_lohi(d_tmem, alo + 4, blo + 4, dhi, idesc, 1u);
+                  umma_f16_pair_lohi(d_tmem, alo + 6, blo + 6, dhi, idesc, 1u);
+                  umma_commit_pair_u32(w_empty_u + 8u * (uint32_t)stage, 3);
+                } else {
+                  umma_f16_lohi(d_tmem, alo, blo, dhi, idesc, kc ? 1u : 0u);
+                  umma_f16_lohi(d_tmem, alo + 2, blo + 2, dhi, idesc, 1u);
+                  umma_f16_lohi(d_tmem, alo + 4, blo + 4, dhi, idesc, 1u);
+                  umma_f16_lohi(d_tmem, alo + 6, blo + 6, dhi, idesc, 1u);
+                  umma_commit_u32(w_empty_u + 8u * (uint32_t)stage);
+                }
+              }
+              __syncwarp();
+              if (++stage == pg.stages) { stage = 0; phase ^= 1; }
+            }
+            MODA_TR(tr, 2, s, slot);
+            // In-place rewrite guarantee: the epilogue of THIS step overwrites chunks that TMA stores of earlier steps
+            // read; it starts on acc_full, so that is only signalled once those stores have read their source.
+            if (sd_need > 0) wait_or_trap<0, MMA_WAIT_CLUSTER>(sd_bar, (sd_need - 1) & 1);
+            if (elect_one()) {
+              if (PAIR) {
+                umma_commit_pair_u32(acc_full_u + 8u * (uint32_t)b, 3);
+                if (rel_pe) umma_commit_pair_u32(pe_free_u + 8u * (uint32_t)slot, 3);
+              } else {
+                umma_commit_u32(acc_full_u + 8u * (uint32_t)b);
+                if (rel_pe) umma_commit_u32(pe_free_u + 8u * (uint32_t)slot);
+              }
+            }
+            __syncwarp();
+            MODA_TR(tr, 4, s, slot);
+            if (slot) mma_ctr1 = ctr + 1; else mma_ctr0 = ctr + 1;
           }
-          // In-place rewrite guarantee: the epilogue of THIS step overwrites chunks that TMA stores of earlier steps
-          // read; it starts on acc_full, so that is only signalled once those stores have read their source.
-          if (sd_need > 0) { if (PAIR) wait_or_trap<0, 1>(stores_done2, (sd_need - 1) & 1); else wait_or_trap(stores_done, (sd_need - 1) & 1); }
-          if (PAIR) umma_commit_pair(&acc_full[b], 3); else umma_commit(&acc_full[b]);
-          if (st.release_pe) { if (PAIR) umma_commit_pair(pe_free, 3); else umma_commit(pe_free); }
-          MODA_TR(tr, 4, s, 0);
-          ++mma_ctr;
         }
       }
+      (void)w_full_u;
     }
-  } else if (warp < 2 + EPI_WARPS) {
-    // ================================================================== epilogue
+  } else if (warp < 2 + SLOTS * EPI_WARPS) {
+    // ================================================================== epilogue (one group of EPI_WARPS per tile slot)
     // Column assignment is chunk-major: for every 64-column chunk of the result, warp (q, h) owns the 32-column
     // sub-blocks {h, h + NH, ..} < 2 of lane quarter q.  All warps therefore finish chunk 0 first, and the next
     // step's MMAs start on it while chunks 1.. are still being drained.
-    const int ew = warp - 2;
+    const int slot = (warp - 2) / EPI_WARPS;
+    const int ew = (warp - 2) - slot * EPI_WARPS;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    float* const s_head_slot = s_head + slot * (head_smem(NH) / 4);
+    uint64_t* const ready_slot = ready + slot * MAX_CHUNKS;
+    const int bar_id = 4 + 2 * slot;        // named barriers of this group: bar_id (heads), bar_id + 1 (tile biases)
     EpiCtx cx;
-    cx.sA = smem_u32(sA);
+    cx.slot = slot;
+    cx.trn = 0;
+    int& tr_n = cx.trn;
+    (void)tr_n;
+    cx.sA = smem_u32(sA) + (uint32_t)slot * slot_bytes;
     cx.s_bias = smem_u32(s_bias);
-    cx.s_vec0 = cx.s_bias + (uint32_t)((pg.vec_row >= 0 ? pg.vec_row : 0) * ACC_STRIDE * 4);
-    cx.s_vec1 = cx.s_bias + (uint32_t)((pg.vec_row1 >= 0 ? pg.vec_row1 : 0) * ACC_STRIDE * 4);
+    cx.s_vec0 = cx.s_bias + (uint32_t)((pg.vec_off0 >= 0 ? pg.vec_off0 : 0) * 4);
+    cx.s_vec1 = cx.s_bias + (uint32_t)((pg.vec_off1 >= 0 ? pg.vec_off1 : 0) * 4);
     cx.tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     cx.h = ew >> 2;
     cx.trow = q * 32 + lane;
@@ -687,32 +782,32 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     cx.rscale = pg.rscale ? *pg.rscale : 1.0f;
     cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
     cx.T = pg.mask_tiles;
-    cx.ready2_remote = PAIR ? mapa_u32(smem_u32(&ready2[0]), 0) : 0u;
+    cx.ready2_remote = PAIR ? mapa_u32(smem_u32(&ready2[slot * MAX_CHUNKS]), 0) : 0u;
     const uint32_t acc_free2_remote = PAIR ? mapa_u32(smem_u32(&acc_free2[0]), 0) : 0u;
     (void)acc_free2_remote;
     const int h = cx.h, trow = cx.trow;
     uint32_t mma_ctr = 0;
     float sig_keep = 0.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
+    for (int it = 0; it * SLOTS + slot < ntile; ++it) {
+      const int tile = (int)blockIdx.x + (it * SLOTS + slot) * (int)gridDim.x;
       cx.tile = tile;
-      cx.tr = (pg.trace && blockIdx.x == 0 && it == 2 && lane == 0) ? 40 + 10 * ew : 0;   // regions 4..: one per warp
+      cx.tr = (pg.trace && blockIdx.x == 0 && it == 2 && lane == 0) ? 40 + 10 * ew + 80 * slot : 0;   // regions 4..: one per warp
       cx.row = (long long)tile * TILE_M + trow;
       cx.live = cx.row < pg.M;
       if (pg.has_tile_bias) {
         // per-ray bias rows (the hoisted per-ray-constant inputs) when a tile never straddles two rays: staged once
         // per tile and then read like any bias.  First barrier: every warp is done with the previous tile's rows.
-        named_bar(5, EPI_THREADS);
-        const int et = threadIdx.x - 64;
+        named_bar(bar_id + 1, EPI_THREADS);
+        const int et = threadIdx.x - 64 - slot * EPI_THREADS;
         long long row0 = (long long)tile * TILE_M;
         if (row0 >= pg.M) row0 = pg.M - 1;   // dead tile of an odd tile count (CTA pairs): any valid ray
         const size_t ray = (size_t)(row0 / pg.rep);
         for (int s = 0; s < pg.nsteps; ++s) {
           const Step& st = pg.st[s];
           if (st.tile_bias)
-            for (int i = et; i < st.n; i += EPI_THREADS) s_bias[st.bias_row * ACC_STRIDE + i] = st.rowbias[ray * st.n + i];
+            for (int i = et; i < st.n; i += EPI_THREADS) s_bias[st.bias_off + slot * st.n + i] = st.rowbias[ray * st.n + i];
         }
-        named_bar(5, EPI_THREADS);
+        named_bar(bar_id + 1, EPI_THREADS);
       }
       for (int s = 0; s < pg.nsteps; ++s) {
         const Step& st = pg.st[s];
@@ -730,8 +825,8 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           if (MWc == 2 && (st.n >> 6) * (4 / NH) > 4) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(pm1) : "l"(mp + TILE_M));
         }
         if (st.kc > 0) {
-          b = mma_ctr & 1;
-          wait_or_trap(&acc_full[b], (mma_ctr >> 1) & 1);
+          b = acc_of(slot, mma_ctr);
+          wait_or_trap(&acc_full[b], acc_phase(mma_ctr));
           tc_fence_after();
         }
         MODA_TR(cx.tr, cx.tr, s, 0);
@@ -744,11 +839,11 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         constexpr int HOT_FWD = E_BIAS | E_RELU | E_MASK_OUT | E_SMEM | LO;
         constexpr int HOT_BWD = E_MASK_IN | E_SMEM;
 #define MODA_FLAVOUR(FL) \
-  if (flags == (FL) && st.n == ACC_STRIDE) run_step<(FL), ACC_STRIDE, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
+  if (flags == (FL) && st.n == ACC_STRIDE) run_step<(FL), ACC_STRIDE, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1); else
 #define MODA_FLAVOUR_N(FL, NN) \
-  if (flags == (FL) && st.n == (NN)) run_step<(FL), (NN), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1); else
+  if (flags == (FL) && st.n == (NN)) run_step<(FL), (NN), NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1); else
 #define MODA_COLD(FL) \
-  if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready, hs, pm0, pm1); \
+  if (flags == (FL)) { float hs[3]; run_step_cold<(FL), NH, ACC_STRIDE, EPI_THREADS>(pg, maps, st, cx, acc_col, ready_slot, hs, pm0, pm1); \
                        if ((FL) & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs0 = hs[0]; hs1 = hs[1]; hs2 = hs[2]; } } else
         // Dispatch modes (per direction): 2 = every flavour a program uses inline, unrolled over its compile-time
         // width (default; measured on B200 against mode 0: trunk fwd 2.03 -> 1.65 ms, trunk bwd 2.08 -> 1.72 ms,
@@ -769,11 +864,11 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             MODA_FLAVOUR(E_BIAS | E_RELU | E_HEAD_SIGMA)                 // sigma-only program: last layer feeds the head only
             MODA_FLAVOUR(E_BIAS | E_SMEM)
             MODA_FLAVOUR_N(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM, 128)
-            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           } else {
             MODA_FLAVOUR(E_BIAS | E_SMEM | E_LO)
             MODA_FLAVOUR(E_BIAS | E_OUT_F32)
-            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           }
         } else if constexpr (PROG == P_BWD && MODA_CHAIN_DISPATCH_BWD == 2) {
           MODA_FLAVOUR(HOT_BWD)
@@ -783,43 +878,43 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             MODA_FLAVOUR_N(E_LOAD16 | E_SMEM, 128)
             MODA_FLAVOUR_N(E_SMEM, 64)
             MODA_FLAVOUR_N(E_ADD_SX | E_SMEM, 64)
-            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           } else {
             MODA_FLAVOUR(E_LOAD32 | E_SMEM)
             MODA_FLAVOUR(E_ADD_SX | E_SMEM)
-            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+            run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           }
         } else if constexpr (PROG == P_FWD && !MODA_CHAIN_DISPATCH_FWD) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_FLAVOUR(HOT_FWD & ~E_MASK_OUT)                            // no sign bits wanted: inference, grid queries
-          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (PROG == P_BWD && !MODA_CHAIN_DISPATCH_BWD) {
           MODA_FLAVOUR(HOT_BWD)
-          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (PROG == P_FWD && BOX_ROWS == 128) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_COLD(HOT_FWD | E_HEAD_SIGMA)
           MODA_COLD(E_BIAS | E_SMEM)                                   // xyz_encoding_final
           MODA_COLD(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM)             // dir layer + rgb head
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (PROG == P_FWD) {
           MODA_FLAVOUR(HOT_FWD)
           MODA_COLD(E_BIAS | E_SMEM | E_LO)
           MODA_COLD(E_BIAS | E_OUT_F32)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         } else if constexpr (BOX_ROWS == 128) {
           MODA_FLAVOUR(HOT_BWD)
           MODA_COLD(E_SMEM)
           MODA_COLD(E_LOAD16 | E_SMEM)
           MODA_COLD(E_ADD_SX | E_SMEM)
           MODA_COLD(E_RANK1 | E_MASK_IN | E_SMEM)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         } else {
           MODA_FLAVOUR(HOT_BWD)
           MODA_COLD(E_SMEM)
           MODA_COLD(E_LOAD32 | E_SMEM)
           MODA_COLD(E_ADD_SX | E_SMEM)
-          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready, hs0, hs1, hs2, pm0, pm1);
+          run_step_generic<NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
         }
 #undef MODA_COLD
 #undef MODA_FLAVOUR_N
@@ -828,28 +923,33 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (PAIR) mbar_arrive_remote(acc_free2_remote + 8u * (uint32_t)b); else mbar_arrive(&acc_free[b]); }
+          MODA_TR(cx.tr, cx.tr + 2, s, 0);
           ++mma_ctr;
         }
+        // head partial sums: the warps h >= 1 of a lane quarter hand theirs to warp h = 0 through shared memory
+        // (summation order h = 0, 1, ..: as before)
         if (flags & E_HEAD_SIGMA) {
-          s_head[(h * 128 + trow) * 4 + 3] = hs0;
-          named_bar(4, EPI_THREADS);
+          if (h > 0) s_head_slot[((h - 1) * 128 + trow) * 4 + 3] = hs0;
+          if (NH > 1) named_bar(bar_id, EPI_THREADS);
           if (h == 0) {
-            sig_keep = pg.bs[0];
+            sig_keep = pg.bs[0] + hs0;
 #pragma unroll
-            for (int k = 0; k < NH; ++k) sig_keep += s_head[(k * 128 + trow) * 4 + 3];
+            for (int k = 1; k < NH; ++k) sig_keep += s_head_slot[((k - 1) * 128 + trow) * 4 + 3];
             if (pg.sigma_only && cx.live) pg.raw[cx.row] = sig_keep;
           }
-          if (pg.sigma_only) named_bar(4, EPI_THREADS);   // s_head is reused by the next tile's partials
+          if (pg.sigma_only && NH > 1) named_bar(bar_id, EPI_THREADS);   // s_head is reused by the next tile's partials
         }
         if (flags & E_HEAD_RGB) {
-          float* mine = s_head + (h * 128 + trow) * 4;
-          mine[0] = hs0; mine[1] = hs1; mine[2] = hs2;
-          named_bar(4, EPI_THREADS);
+          if (h > 0) {
+            float* mine = s_head_slot + ((h - 1) * 128 + trow) * 4;
+            mine[0] = hs0; mine[1] = hs1; mine[2] = hs2;
+          }
+          if (NH > 1) named_bar(bar_id, EPI_THREADS);
           if (h == 0 && cx.live) {
-            float o0 = pg.br[0], o1 = pg.br[1], o2 = pg.br[2];
+            float o0 = pg.br[0] + hs0, o1 = pg.br[1] + hs1, o2 = pg.br[2] + hs2;
 #pragma unroll
-            for (int k = 0; k < NH; ++k) {
-              const float* part = s_head + (k * 128 + trow) * 4;
+            for (int k = 1; k < NH; ++k) {
+              const float* part = s_head_slot + ((k - 1) * 128 + trow) * 4;
               o0 += part[0]; o1 += part[1]; o2 += part[2];
             }
             float4 o;
@@ -859,24 +959,29 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             o.w = sig_keep;
             *reinterpret_cast<float4*>(pg.raw + cx.row * 4) = o;
           }
-          named_bar(4, EPI_THREADS);   // s_head is reused by the next tile's sigma partials
+          if (NH > 1) named_bar(bar_id, EPI_THREADS);   // s_head is reused by the next tile's sigma partials
         }
       }
     }
-  } else if (warp < 2 + EPI_WARPS + PE_WARPS) {
+  } else if (warp < 2 + SLOTS * EPI_WARPS + PE_WARPS) {
     // ================================================================== positional-encoding producers
+    // (two tile slots: the one producer warp serves them alternately, in the order the tiles start)
     if (pg.pe_chunk >= 0) {
-      const int pw = warp - 2 - EPI_WARPS;
+      const int pw = warp - 2 - SLOTS * EPI_WARPS;
       const bool lead = (pw == 0) && lane == 0;
       (void)lead;
-      int it = 0;
-      const uint32_t pe_base = smem_u32(sA) + (uint32_t)(pg.pe_chunk * CHUNK_BYTES);
-      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
+      int tr_n = 0;
+      (void)tr_n;
+      for (int j = 0; j < ntile; ++j) {
+        const int slot = j % SLOTS, it = j / SLOTS;
+        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        const uint32_t pe_base = smem_u32(sA) + (uint32_t)slot * slot_bytes + (uint32_t)(pg.pe_chunk * CHUNK_BYTES);
         // channels: [x(3) | w_k sin(2^k x)(3) | w_k cos(2^k x)(3)]_k, zero padded to 64 (nnutils/nerf.py:35-75);
         // values go straight to the swizzled chunk rows as they are produced (PE_ROWS rows per thread)
-        const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && lead;
+        const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && slot == 0 && lead;
+        (void)tr;
         MODA_TR(tr, 30, 0, 0);
-        if (lead) s_dbg[3] = it;
+        if (lead) s_dbg[3] = j;
         // this thread's PE_ROWS consecutive rows of xyz: fetched before the wait, so the global-load latency hides
         // behind it
         float xs[PE_ROWS][3];
@@ -887,7 +992,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 #pragma unroll
           for (int c = 0; c < 3; ++c) xs[rr][c] = in ? __ldg(pg.xyz + row * 3 + c) : 0.f;
         }
-        wait_or_trap<0>(pe_free, (it & 1) ^ 1);   // the previous tile's last reader of the PE chunk(s) has completed
+        wait_or_trap<0>(&pe_free[slot], (it & 1) ^ 1);   // the slot's previous tile's last reader of the PE chunk(s) has completed
         MODA_TR(tr, 31, 0, 0);
 #pragma unroll 1
         for (int rr = 0; rr < PE_ROWS; ++rr) {
@@ -949,9 +1054,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&ready[pg.pe_chunk]);
-          if (pg.pe_lo) mbar_arrive(&ready[pg.pe_chunk + 1]);
-          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&ready2[pg.pe_chunk]), 0));
+          mbar_arrive(&ready[slot * MAX_CHUNKS + pg.pe_chunk]);
+          if (pg.pe_lo) mbar_arrive(&ready[slot * MAX_CHUNKS + pg.pe_chunk + 1]);
+          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&ready2[slot * MAX_CHUNKS + pg.pe_chunk]), 0));
         }
       }
     }
@@ -962,41 +1067,52 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     // because pe_free is committed steps later, after the MMA thread has seen this step's stores_done.
     if (lane == 0) {
       const uint32_t sA_u32 = smem_u32(sA);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++it) {
-        int d = 0;
+      int tr_n = 0;
+      (void)tr_n;
+      for (int it = 0; it * SLOTS < ntile; ++it) {
+        const int nact = (ntile - it * SLOTS < SLOTS) ? ntile - it * SLOTS : SLOTS;
+        int d0 = 0;
         for (int s = 0; s < pg.nsteps; ++s) {
-          bool any = false, work = false;
-          while (d < pg.nduty && pg.duty[d].step == s) {
-            work = true;
-            const int c = pg.duty[d].chunk;
-            const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + pg.duty[d].gen;
-            s_dbg[4] = it * 1000 + s * 10 + (d % 10); s_dbg[5] = 0;
-            wait_or_trap<0>(&ready[c], gen & 1);
-            s_dbg[5] = 1;
-            MODA_TR(pg.trace && blockIdx.x == 0 && it == 2, 20, s, c);
+          int d_end = d0;
+          // two tile slots: the slots' epilogues of a step run one after the other (the MMA thread alternates), so
+          // their chunks are served in that order
+          for (int slot = 0; slot < nact; ++slot) {
+            const int tile = (int)blockIdx.x + (it * SLOTS + slot) * (int)gridDim.x;
+            bool any = false, work = false;
+            int d = d0;
+            while (d < pg.nduty && pg.duty[d].step == s) {
+              work = true;
+              const int c = pg.duty[d].chunk;
+              const uint32_t gen = (uint32_t)it * (uint32_t)pg.wpt[c] + pg.duty[d].gen;
+              s_dbg[4] = it * 1000 + s * 10 + (d % 10); s_dbg[5] = 0;
+              wait_or_trap<0>(&ready[slot * MAX_CHUNKS + c], gen & 1);
+              s_dbg[5] = 1;
+              MODA_TR(pg.trace && blockIdx.x == 0 && it == 2 && slot == 0, 20, s, c);
 #ifdef MODA_EXP_NO_STORE
-            if (false) {
+              if (false) {
 #else
-            if (pg.duty[d].map >= 0) {
+              if (pg.duty[d].map >= 0) {
 #endif
 #ifdef MODA_EXP_STORE_L2
-              const int trow0 = (tile & 63) * TILE_M;   // experiment: every store lands in the same L2-resident rows
+                const int trow0 = (tile & 63) * TILE_M;   // experiment: every store lands in the same L2-resident rows
 #else
-              const int trow0 = tile * TILE_M;
+                const int trow0 = tile * TILE_M;
 #endif
-              tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)(c * CHUNK_BYTES), (int)pg.duty[d].col * 64,
-                               trow0);
-              bulk_commit();
-              any = true;
+                tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)slot * slot_bytes + (uint32_t)(c * CHUNK_BYTES),
+                                 (int)pg.duty[d].col * 64, trow0);
+                bulk_commit();
+                any = true;
+              }
+              ++d;
             }
-            ++d;
+            d_end = d;
+            s_dbg[5] = 2;
+            if (any) bulk_wait_read0();
+            MODA_TR(pg.trace && blockIdx.x == 0 && it == 2 && slot == 0 && any, 21, s, 0);
+            if (work) { if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&stores_done2[slot]), 0)); else mbar_arrive(&stores_done[slot]); }
+            s_dbg[5] = 3;
           }
-          s_dbg[5] = 2;
-          if (any) bulk_wait_read0();
-          MODA_TR(pg.trace && blockIdx.x == 0 && it == 2 && any, 21, s, 0);
-          if (work) { if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(stores_done2), 0)); else mbar_arrive(stores_done); }
-          s_dbg[5] = 3;
+          d0 = d_end;
         }
       }
       bulk_wait_all0();
@@ -1021,17 +1137,18 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 using namespace moda;
 using namespace moda::chain;
 
-static long long* g_trace = nullptr;
-#ifndef MODA_TRUNK_PAIR
-#define MODA_TRUNK_PAIR 1   // default of the run-time switch below (measured: +1.7 % on the training step, +5.5 % on the grid)
-#endif
-// 1: the 256-wide chains (nerf_coarse forward, density-only, adjoint) run as CTA pairs (tcgen05 cta_group::2)
-static int g_pair = MODA_TRUNK_PAIR;
+#include <atomic>
+// Launch mode of the 256-wide chains is a PER-CALL argument (`mode`): bit 0 = CTA pairs (tcgen05 cta_group::2), bit 1 =
+// two tiles in flight per CTA (needs bit 0).  The only process-wide state is (a) a sticky flag that a cluster launch
+// failed once on this process's device/partition (then every later call uses the single-CTA kernels) and (b) the debug
+// trace hook below, both atomics.
+constexpr int MODE_PAIR = 1, MODE_TWO_SLOTS = 2;
+static std::atomic<int> g_pair_unavailable{0};
+static std::atomic<long long*> g_trace{nullptr};
 constexpr int PAIR_UNAVAILABLE = -77;   // launch<..., PAIR = 1> could not place the cluster: the caller relaunches single-CTA
-extern "C" int moda_chain_set_pair(int on) { g_pair = on ? 1 : 0; return 0; }
-extern "C" int moda_chain_get_pair(void) { return g_pair; }   // 0 after a fallback, whatever was requested
+extern "C" int moda_chain_pair_available(void) { return g_pair_unavailable.load() ? 0 : 1; }
 // debug: device buffer of >= 4 + 4 * 4000 int64 (zeroed by the caller) that the next chain launches fill with a timeline
-extern "C" int moda_chain_set_trace(long long* buf) { g_trace = buf; return 0; }
+extern "C" int moda_chain_set_trace(long long* buf) { g_trace.store(buf); return 0; }
 
 namespace {
 
@@ -1040,15 +1157,17 @@ struct Builder {
   Maps maps;
   int nsave = 0;
   int gen[MAX_CHUNKS];   // writes issued so far to each chunk within the tile
+  int by_mma_step[MAX_CHUNKS];   // the latest write of the chunk comes from the epilogue of an MMA step (not PE / load)
   int err = 0;
 
   Builder() {
     memset(&pg, 0, sizeof(pg));
     memset(&maps, 0, sizeof(maps));
     memset(gen, 0, sizeof(gen));
+    memset(by_mma_step, 0, sizeof(by_mma_step));
     pg.pe_chunk = -1;
     pg.pe_save_map = -1;
-    pg.vec_row = pg.vec_row1 = -1;
+    pg.vec_off0 = pg.vec_off1 = -1;
   }
   // registers an fp16 (rows, cols) output for TMA stores; returns its descriptor index, -1 when ptr is null
   int save(const void* ptr, long long rows, int cols) {
@@ -1061,13 +1180,12 @@ struct Builder {
     Step& st = pg.st[pg.nsteps++];
     st.n = n; st.flags = flags; st.kc = 0;
     st.out_chunk = st.out_lo_chunk = st.save_map = -1;
-    st.mask_slot = 0; st.release_pe = 0; st.bias_row = 0; st.bias = nullptr; st.rowbias = nullptr; st.tile_bias = 0;
+    st.mask_slot = 0; st.release_pe = 0; st.bias_off = 0; st.bias = nullptr; st.rowbias = nullptr; st.tile_bias = 0;
     return st;
   }
   // K chunk: A from shared-memory chunk `a` (its latest write), B from packed-weight chunk `bcol`
   void k(Step& st, int a, int bcol) {
-    st.a_chunk[st.kc] = (unsigned char)a;
-    st.a_gen[st.kc] = (unsigned char)(gen[a] - 1);
+    st.a_info[st.kc] = (unsigned int)a | ((unsigned int)(gen[a] - 1) << 8) | ((unsigned int)(by_mma_step[a] ? 1 : 0) << 16);
     st.b_col[st.kc] = (unsigned short)bcol;
     ++st.kc;
   }
@@ -1085,10 +1203,12 @@ struct Builder {
     st.out_lo_chunk = lo_first;
     st.flags |= E_SMEM | (lo_first >= 0 ? E_LO : 0);
     const int step = (int)(&st - pg.st);
+    const int mma_step = (st.flags & (E_LOAD16 | E_LOAD32)) ? 0 : 1;   // k() calls precede out() for MMA steps
     for (int i = 0; i < count; ++i) {
       add_duty(first + i, gen[first + i], step, i, st.save_map);
       ++gen[first + i];
-      if (lo_first >= 0) ++gen[lo_first + i];
+      by_mma_step[first + i] = mma_step;
+      if (lo_first >= 0) { ++gen[lo_first + i]; by_mma_step[lo_first + i] = mma_step; }
     }
   }
   void pe(int chunk, bool lo, int save_map) {
@@ -1096,9 +1216,11 @@ struct Builder {
     pg.from_pe[chunk] = 1;
     add_duty(chunk, gen[chunk], 0, 0, save_map);
     ++gen[chunk];
-    if (lo) { pg.from_pe[chunk + 1] = 1; ++gen[chunk + 1]; }
+    by_mma_step[chunk] = 0;
+    if (lo) { pg.from_pe[chunk + 1] = 1; ++gen[chunk + 1]; by_mma_step[chunk + 1] = 0; }
   }
-  void finish(int acc_stride) {
+  // slots: tile slots of the kernel that will run the program (per-tile bias rows get one copy per slot).  Idempotent.
+  void finish(int slots) {
     for (int i = 0; i < MAX_CHUNKS; ++i) pg.wpt[i] = gen[i];
     int phases = 0, d = 0;
     for (int s = 0; s < pg.nsteps; ++s) {
@@ -1108,41 +1230,47 @@ struct Builder {
       if (work) ++phases;
     }
     pg.sd_per_tile = phases;
-    pg.nbias = 0;
+    // bias / head-vector table: regions packed back to back (every width is a multiple of 64 floats, so the 128-bit
+    // reads of the epilogue stay aligned)
+    int off = 0;
     for (int s = 0; s < pg.nsteps; ++s) {
       Step& st = pg.st[s];
-      if (st.bias) { st.bias_row = pg.nbias++; st.flags |= E_BIAS; }
+      if (st.bias) { st.bias_off = off; off += st.n; st.flags |= E_BIAS; }
       if (st.rowbias) {
-        if (pg.rep % TILE_M == 0) { st.bias_row = pg.nbias++; st.flags |= E_BIAS; st.tile_bias = 1; pg.has_tile_bias = 1; }
+        if (pg.rep % TILE_M == 0) { st.bias_off = off; off += slots * st.n; st.flags |= E_BIAS; st.tile_bias = 1; pg.has_tile_bias = 1; }
         else st.flags |= E_ROWBIAS;
       }
     }
-    if (pg.vec0) { pg.vec_row = pg.nbias; pg.nbias += (pg.vec_len0 + acc_stride - 1) / acc_stride; }
-    if (pg.vec1) { pg.vec_row1 = pg.nbias; pg.nbias += (pg.vec_len1 + acc_stride - 1) / acc_stride; }
+    if (pg.vec0) { pg.vec_off0 = off; off += (pg.vec_len0 + 63) & ~63; }
+    if (pg.vec1) { pg.vec_off1 = off; off += (pg.vec_len1 + 63) & ~63; }
+    pg.bias_floats = off;
   }
 };
 
-template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR = 0>
-int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
-  if (b.err) return b.err;
-  b.finish((BOX_ROWS == 128) ? 256 : 64);
-  b.pg.trace = g_trace;
+template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR = 0, int SLOTS = 1>
+int launch(Builder& bld, const void* wpack, int wrows, int wcols, cudaStream_t stream) {
+  if (bld.err) return bld.err;
+  Builder b = bld;   // the caller's program stays untouched: a fallback relaunches it in another mode
+  b.finish(SLOTS);
+  b.pg.trace = g_trace.load();
   b.pg.mask_tiles = (b.pg.num_tiles + 1) & ~1;
   if (PAIR) b.pg.num_tiles = (b.pg.num_tiles + 1) & ~1;   // both CTAs of a pair run the same number of tiles
-  if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, PAIR ? 32 : BOX_ROWS)) return e;
   constexpr int STAGE_BYTES = PAIR ? BOX_ROWS * 128 : ((BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128);
-  constexpr int ACC_STRIDE = (BOX_ROWS == 128) ? 256 : 64;
-  constexpr int THREADS = (3 + EPI_WARPS + PE_WARPS) * 32;
-  const size_t smem = 1024 + (size_t)b.pg.nchunks * CHUNK_BYTES + (size_t)b.pg.stages * STAGE_BYTES + head_smem(EPI_WARPS / 4) +
-                      (size_t)b.pg.nbias * ACC_STRIDE * 4 + 512 + 32;
+  constexpr int THREADS = (3 + SLOTS * EPI_WARPS + PE_WARPS) * 32;
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
-  MODA_REQUIRE(smem <= cap, "chain: needs %zu B of shared memory (limit %zu)", smem, cap);
-  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS, PROG, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-    attr_set = true;
-  }
+  // weight ring: as many stages as fit (16 KB stages for CTA pairs, 32 KB otherwise), at most the program's request
+  const size_t fixed = 1024 + (size_t)SLOTS * b.pg.nchunks * CHUNK_BYTES + (size_t)SLOTS * head_smem(EPI_WARPS / 4) +
+                       (size_t)b.pg.bias_floats * 4 + 512 + 32;
+  MODA_REQUIRE(fixed + 2 * STAGE_BYTES <= cap, "chain: needs %zu B of shared memory (limit %zu)", fixed + 2 * STAGE_BYTES, cap);
+  int stages = (int)((cap - fixed) / STAGE_BYTES);
+  if (stages > b.pg.stages) stages = b.pg.stages;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  b.pg.stages = stages;
+  const size_t smem = fixed + (size_t)stages * STAGE_BYTES;
+  if (int e = make_map(&b.maps.w, wpack, wrows, wcols, wcols, PAIR ? 32 : BOX_ROWS)) return e;
+  auto kern = chain_kernel<BOX_ROWS, EPI_WARPS, PE_WARPS, MIN_CTAS, PROG, PAIR, SLOTS>;
+  // per-device function attribute: set on every launch (cheap), so a second device in the same process gets it too
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
   const int slots = PAIR ? ((sm_count() * MIN_CTAS) & ~1) : sm_count() * MIN_CTAS;
   const int grid = b.pg.num_tiles < slots ? b.pg.num_tiles : slots;
   if (PAIR) {
@@ -1156,13 +1284,35 @@ int launch(Builder& b, const void* wpack, int wrows, int wcols, cudaStream_t str
     if (e != cudaSuccess) {
       // a device / partition that cannot co-schedule the CTA pair: fall back to the single-CTA kernels for good
       (void)cudaGetLastError();
-      g_pair = 0;
+      g_pair_unavailable.store(1);
       return PAIR_UNAVAILABLE;
     }
   } else {
     kern<<<grid, THREADS, smem, stream>>>(b.pg, b.maps);
   }
   return check_launch("chain");
+}
+
+// launches a 256-wide program in the requested mode (see MODE_*), falling back to the single-CTA kernel when a cluster
+// cannot be placed.  Two tile slots only pay when every CTA gets at least two tiles.
+template <int PROG>
+int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_t stream) {
+  const bool pair = (mode & MODE_PAIR) && !g_pair_unavailable.load();
+  if (pair) {
+    const int ctas = sm_count() & ~1;
+    const int tiles = (b.pg.num_tiles + 1) & ~1;
+    int e;
+    if ((mode & MODE_TWO_SLOTS) && tiles >= 2 * ctas) {
+      b.pg.stages = 3;
+      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 2>(b, wpack, 256, wcols, stream);
+    } else {
+      b.pg.stages = 8;
+      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 1>(b, wpack, 256, wcols, stream);
+    }
+    if (e != PAIR_UNAVAILABLE) return e;
+  }
+  b.pg.stages = 4;   // single-CTA weight ring: 4 stages of 32 KB
+  return launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 0, 1>(b, wpack, 256, wcols, stream);
 }
 
 // the epilogue reads these operands with 128-bit loads
@@ -1185,14 +1335,14 @@ void fill_win(Program& pg, int F, const float* win) {
 extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int F, const float* win, const void* wpack,
                                     const float* const* biases, const float* rowbias, const float* ws, const float* bs,
                                     const float* Wr, const float* br, void* A0, void* H, void* fin, void* dfe,
-                                    unsigned int* maskbits, float* raw, cudaStream_t stream) {
+                                    unsigned int* maskbits, float* raw, int mode, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && rowbias && ws && bs && Wr && br && raw && rep > 0 && F >= 0 && F <= 10,
                "chain_trunk_fwd: bad arguments");
   MODA_REQUIRE(al16(rowbias) && al16(raw) && al16(wpack), "chain_trunk_fwd: rowbias, raw and wpack must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = rep; pg.nchunks = 5;
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.Wr = Wr; pg.br = br; pg.raw = raw; pg.maskbits = maskbits;
   pg.vec0 = ws; pg.vec_len0 = 256; pg.vec1 = Wr; pg.vec_len1 = 3 * 128;
@@ -1229,12 +1379,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(dfe, P, 128);
     b.out(st, 0, 2);
   }
-  if (g_pair) {
-    const int e = launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 1>(b, wpack, 256, col * 64, stream);
-    if (e != PAIR_UNAVAILABLE) return e;
-    b.pg.stages = 4;   // single-CTA weight ring: 4 stages of 32 KB
-  }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 0>(b, wpack, 256, col * 64, stream);
+  return launch_trunk<P_FWD>(b, mode, wpack, col * 64, stream);
 }
 
 // Density only (the grid query of mesh extraction, nnutils/train_utils.py:1377-1404 -> nerf.py:176-180 with
@@ -1242,13 +1387,13 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
 // saved.  sigma (P) fp32.
 extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, const float* win, const void* wpack,
                                       const float* const* biases, const float* ws, const float* bs, float* sigma,
-                                      cudaStream_t stream) {
+                                      int mode, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && ws && bs && sigma && F >= 0 && F <= 10, "chain_trunk_sigma: bad arguments");
   MODA_REQUIRE(al16(wpack) && al16(ws), "chain_trunk_sigma: wpack and ws must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5;
   pg.xyz = xyz; fill_win(pg, F, win);
   pg.ws = ws; pg.bs = bs; pg.raw = sigma; pg.sigma_only = 1;
   pg.vec0 = ws; pg.vec_len0 = 256;
@@ -1267,12 +1412,7 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
     if (l == 7) st.flags |= E_HEAD_SIGMA;   // the last layer's activations only feed the head: not written back
     else b.out(st, 0, 4);
   }
-  if (g_pair) {
-    const int e = launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 1>(b, wpack, 256, 38 * 64, stream);
-    if (e != PAIR_UNAVAILABLE) return e;
-    b.pg.stages = 4;   // single-CTA weight ring: 4 stages of 32 KB
-  }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_FWD, 0>(b, wpack, 256, 38 * 64, stream);
+  return launch_trunk<P_FWD>(b, mode, wpack, 38 * 64, stream);
 }
 
 // Adjoint chain of nerf_coarse.  Packed transposed weights wpackT: fp16 (256, 42*64); rows = input channel of the
@@ -1285,13 +1425,13 @@ extern "C" int moda_chain_trunk_sigma(const float* xyz, long long P, int F, cons
 // Out (fp16): d_fin (P,256), dY (8,P,256) with dY[i] = gradient at layer i's pre-activation, d_pe (P,64).
 extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const float* ws, const float* rscale,
                                     const void* wpackT, const unsigned int* maskbits, long long P, void* d_fin,
-                                    void* dY, void* d_pe, cudaStream_t stream) {
+                                    void* dY, void* d_pe, int mode, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && d_fin && dY && d_pe, "chain_trunk_bwd: null pointer");
   MODA_REQUIRE(al16(d_dfe) && al16(wpackT), "chain_trunk_bwd: d_dfe and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
-  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5; pg.stages = g_pair ? 8 : 4;   // weight ring: 16 KB stages for CTA pairs, 32 KB otherwise
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 5;
   pg.gsig = gsig; pg.cvec = ws; pg.rscale = rscale; pg.maskbits = const_cast<unsigned int*>(maskbits);
   pg.vec0 = ws; pg.vec_len0 = 256;
   pg.load_src = d_dfe; pg.load_ld = 128; pg.load_cols = 128;
@@ -1332,12 +1472,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     st.save_map = b.save(d_pe, P, 64);
     b.out(st, SX, 1);
   }
-  if (g_pair) {
-    const int e = launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, 1>(b, wpackT, 256, col * 64, stream);
-    if (e != PAIR_UNAVAILABLE) return e;
-    b.pg.stages = 4;   // single-CTA weight ring: 4 stages of 32 KB
-  }
-  return launch<128, MODA_TRUNK_EPI, 1, 1, P_BWD, 0>(b, wpackT, 256, col * 64, stream);
+  return launch_trunk<P_BWD>(b, mode, wpackT, col * 64, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin

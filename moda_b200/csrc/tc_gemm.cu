@@ -516,12 +516,8 @@ static int launch_linear(const AMaps& a, const CUtensorMap& b, int M, const Chun
     if (smem <= 232448) break;
   }
   MODA_REQUIRE(smem <= 232448, "tc_linear: K=%d N=%d needs %zu B of shared memory", KC * 64, N_TILE, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tc_linear_kernel<N_TILE, ROWBIAS, RANK1, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         232448);
-    attr_set = true;
-  }
+  // a per-DEVICE function attribute: set on every launch (cheap) so that a second device of the process gets it too
+  cudaFuncSetAttribute(tc_linear_kernel<N_TILE, ROWBIAS, RANK1, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   const int tiles = (M + TILE_M - 1) / TILE_M;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   tc_linear_kernel<N_TILE, ROWBIAS, RANK1, MASK><<<grid, LIN_THREADS, smem, stream>>>(a, b, M, ct, stages, ep);
@@ -629,11 +625,7 @@ template <int NOUT, int KIN>
 static int launch_wgrad(const WgMaps& maps, int npair, int M, float* dW, int ldw, int n_valid, int k_valid,
                         const float* oscale, float* dbias, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + WG_BOX_BYTES + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tc_wgrad_kernel<NOUT, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(tc_wgrad_kernel<NOUT, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);   // per device: every launch
   const int chunks = (M + WG_ROWS - 1) / WG_ROWS;
   const int grid = chunks < sm_count() ? chunks : sm_count();
   tc_wgrad_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(maps, npair, M, dW, ldw, n_valid, k_valid, oscale,

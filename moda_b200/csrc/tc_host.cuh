@@ -41,14 +41,18 @@ static inline int make_map(CUtensorMap* map, const void* ptr, long long rows, in
   return 0;
 }
 
+// SM count of the CURRENT device (cached per device: a process may drive several)
 static inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n;   // benign race: every writer stores the same value
   }
-  return n;
+  return cache[dev];
 }
 
 

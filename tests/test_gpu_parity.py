@@ -395,11 +395,12 @@ def test_fused_chains_match_layer_by_layer_kernels():
         config.fused = True
 
 
-def test_trunk_chains_as_cta_pairs_match_single_cta_kernels():
-    """The CTA-pair launch mode of the 256-wide chains (tcgen05 cta_group::2, csrc/chain.cu PAIR = 1) performs the
-    same arithmetic in the same order as the single-CTA kernels: outputs and the data gradients are bit-identical,
-    the weight gradients (atomic accumulation order) agree to rounding.  Sizes: an odd tile count (the pair's dead
-    tile), a ragged last tile, and more tile pairs than CTAs."""
+def test_trunk_chain_launch_modes_are_bit_identical():
+    """The launch modes of the 256-wide chains (csrc/chain.cu) perform the same arithmetic in the same order per tile:
+    single-CTA kernels, CTA pairs (tcgen05 cta_group::2, PAIR = 1) and CTA pairs with TWO tiles in flight per CTA
+    (SLOTS = 2).  Outputs and the data gradients are bit-identical, the weight gradients (atomic accumulation order)
+    agree to rounding.  Sizes: an odd tile count (the pair's dead tile), a ragged last tile, more tile pairs than CTAs,
+    and enough tiles that every CTA runs several tiles per slot with an odd tile count on some CTAs."""
     from moda_b200 import config, geom_utils as G, synth, models as MM
     from moda_b200.extract import density_grid
     config.set_precision("fp16")
@@ -420,26 +421,30 @@ def test_trunk_chains_as_cta_pairs_match_single_cta_kernels():
         data = {"pts": pts.grad.clone(), "dir": de.grad.clone(), "env": env.grad.clone()}
         par = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
         with torch.no_grad():
-            vol = density_grid(model, 24, (0.3, 0.3, 0.3), emb["xyz"])
+            vol = density_grid(model, 24 if R < 1000 else 48, (0.3, 0.3, 0.3), emb["xyz"])
         return out.detach().clone(), data, par, vol
 
-    was = config.trunk_pair
+    was = (config.trunk_pair, config.trunk_slots)
     try:
-        for R, S in ((3, 128), (37, 64), (700, 128)):
+        for R, S in ((3, 128), (37, 64), (700, 128), (2401, 128)):
             config.set_trunk_pair(False)
             a = run(R, S)
-            config.set_trunk_pair(True)
-            b = run(R, S)
-            assert torch.equal(a[0], b[0]), (R, S, max_abs(a[0], b[0]))
-            assert torch.equal(a[3], b[3]), (R, S, "density grid")
-            for k in ("pts",):
-                assert torch.equal(a[1][k], b[1][k]), (R, S, k, max_abs(a[1][k], b[1][k]))
-            for k in ("dir", "env"):
-                assert nrel(b[1][k], a[1][k]) < 1e-5, (R, S, k)
-            worst = max((nrel(b[2][k], a[2][k]), k) for k in a[2])
-            assert worst[0] < 1e-4, (R, S, worst)
+            for slots in (1, 2):
+                config.set_trunk_pair(True)
+                config.set_trunk_slots(slots)
+                b = run(R, S)
+                tag = (R, S, "slots=%d" % slots)
+                assert torch.equal(a[0], b[0]), (tag, max_abs(a[0], b[0]))
+                assert torch.equal(a[3], b[3]), (tag, "density grid")
+                for k in ("pts",):
+                    assert torch.equal(a[1][k], b[1][k]), (tag, k, max_abs(a[1][k], b[1][k]))
+                for k in ("dir", "env"):
+                    assert nrel(b[1][k], a[1][k]) < 1e-5, (tag, k)
+                worst = max((nrel(b[2][k], a[2][k]), k) for k in a[2])
+                assert worst[0] < 1e-4, (tag, worst)
     finally:
-        config.set_trunk_pair(was)
+        config.set_trunk_pair(was[0])
+        config.set_trunk_slots(was[1])
 
 
 def test_training_step_on_flat_parameter_buffer():
