@@ -261,7 +261,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, sampler=None):
+    def timed(fn, steps, sampler=None):  # noqa: E306
         barrier()
         if sampler:
             sampler.start()
@@ -277,6 +277,21 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, clocks
 
+    # BASELINE configs[2] (strong scaling): the SAME 8192-ray global batch sharded N ways, measured next to the weak-
+    # scaling headline (8192 rays per GPU) in the same run
+    strong = None
+    if world > 1 and R % world == 0:
+        Rs = R // world
+        sub = {k: v[rank * Rs:(rank + 1) * Rs].detach().clone() for k, v in rays.items()}
+        for k in ("bone_rts", "time_embedded", "env_code", "rays_o", "rays_d"):
+            sub[k].requires_grad_(True)
+        for _ in range(max(args.warmup, 3)):
+            step(sub)
+        ms_strong, _ = timed(lambda: step(sub), args.steps)
+        strong = {"global_rays": R, "rays_per_gpu": Rs, "ms_per_step": round(ms_strong, 3),
+                  "value": round(R / (ms_strong * 1e-3), 1), "unit": "rays/s",
+                  "note": "same step on the 8192-ray global batch sharded over the ranks (BASELINE configs[2]); "
+                          "efficiency vs N=1 = value / (N=1 value of the headline metric)"}
     for _ in range(max(args.warmup, 3)):
         step(rays)
     launches0 = _lib.LAUNCHES
@@ -334,11 +349,22 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_rays=args.cpu_rays, repeats=2)
+    # secondary figures of BASELINE.json's metric, folded into the same line so that the driver's BENCH / SCALE files
+    # carry them: the DQ-skinning microbench (configs[3], one GPU) and the density grid (configs[4], sharded over the ranks)
+    extra = {}
+    if not args.no_extra:
+        torch.cuda.empty_cache()
+        g = measure_grid(args, dev, world, rank, with_cpu=False, steps=3)
+        if rank == 0:
+            extra["grid"] = g
+        if world == 1:
+            extra["dqs"] = measure_dqs(args, dev, with_cpu=False, steps=3)
     if rank == 0:
         rays_s = R * world / (ms_step * 1e-3)
         out = {"metric": "train rays/s (128 samp/ray)", "value": round(rays_s, 1), "unit": "rays/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f16 operands / f32 accumulate (tcgen05 MLP chains; nerf_skin forward split hi+lo fp16); f32 elsewhere",
                "data": "synthetic",
                "config": {"workload": "full fwd+bwd training step of render_rays: %d rays/GPU x %d samples, %d bones, "
                                       "8x256 nerf_coarse + 5x64 nerf_skin, AdamW step, grad all-reduce" % (R, SAMPLES, BONES),
@@ -350,7 +376,8 @@ def run_ours(args):
                "e2e": {"value": round(R * world / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
                        "input_pipeline": "pinned host rays -> double-buffered H2D prefetch on a copy stream, one copy set per step"},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "strong_scaling": strong, "extra": extra}
         _emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -433,16 +460,26 @@ def _event_ms(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def run_dqs(args):
+def _traffic_of(key):
+    """DRAM bytes per launch of one kernel from the committed ncu capture (profiles/traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    k = json.load(open(p)).get("kernels", {}).get(key)
+    return k["dram_bytes_per_launch"] if k else None
+
+
+def measure_dqs(args, dev, with_cpu=True, steps=None):
     """BASELINE configs[3]: 16.78 M points (131072 rays x 128) x 25 Gaussian bones, per-ray dual quaternions;
     Gaussian skinning + backward warp, then skinning + forward warp (geom_utils.py:202-302, 372-517), forward and
-    backward timed separately, without and with streamed delta-logits (pitch 32 fp32)."""
+    backward timed separately, without and with streamed delta-logits (pitch 32 fp32).  Returns the JSON object."""
     from moda_b200 import synth, geom_utils as G, _lib
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
     assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
+    steps = steps or args.steps
     R, S, B = args.dqs_rays, SAMPLES, BONES
     sp = synth.make_skin_problem(R, S, seed=0)
+    xyz_host = sp["xyz"].pin_memory()
+    rts_host = sp["bone_rts"].pin_memory()
     xyz = sp["xyz"].to(dev).requires_grad_(True)
     bones = sp["bones_rst"].to(dev).requires_grad_(True)
     aux = sp["skin_aux"].to(dev).requires_grad_(True)
@@ -450,6 +487,8 @@ def run_dqs(args):
     P = R * S
     peaks, src = _peaks()
     out = {}
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
     for tag, with_delta in (("no_delta", False), ("delta_streamed", True)):
         d_bw = d_fw = None
         if with_delta:
@@ -472,8 +511,8 @@ def run_dqs(args):
             leaves = [xyz, bones, aux, rts] + ([d_bw, d_fw] if with_delta else [])
             torch.autograd.grad([can, cyc], leaves, [g1, g2], retain_graph=True)
 
-        ms_f = _event_ms(fwd, args.steps, max(args.warmup, 3))
-        ms_b = _event_ms(bwd, args.steps, max(args.warmup, 3))
+        ms_f = _event_ms(fwd, steps, max(args.warmup, 3))
+        ms_b = _event_ms(bwd, steps, max(args.warmup, 3))
         # algorithmic bytes per point: forward 12 in + 2 x 12 out + 1800/128 per-ray bone data
         # [+ 2 x 25 x 4 delta]; backward: xyz, xyz_can, 2 gradients in, 1 out = 60 + 14 [+ 2 x 2 x 25 x 4 read+write]
         bf = 50.1 + (200.0 if with_delta else 0.0)
@@ -484,8 +523,24 @@ def run_dqs(args):
                     "bwd_hbm_frac": round(bb * P / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                     "alg_bytes_per_point": {"fwd": bf, "bwd": bb}}
         del state, d_bw, d_fw
+    # end to end through the public API with HOST buffers: points + per-ray transforms copied in, both warped point
+    # sets copied out, inside the timed region
+    can_host = torch.empty(R, S, 3).pin_memory()
+    cyc_host = torch.empty(R, S, 3).pin_memory()
+
+    def e2e():
+        with torch.no_grad():
+            x = xyz_host.to(dev, non_blocking=True)
+            r = rts_host.to(dev, non_blocking=True)
+            can = G.warp_points(x, bones, r, aux, None, backward=True)
+            cyc = G.warp_points(can, bones, r, aux, None, backward=False)
+            can_host.copy_(can, non_blocking=True)
+            cyc_host.copy_(cyc, non_blocking=True)
+
+    ms_e = _event_ms(e2e, steps, 2)
+    clocks = sampler.stop()
     cpu = None
-    if not args.no_cpu:
+    if with_cpu:
         from oracle import restated as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -502,24 +557,119 @@ def run_dqs(args):
         cpu = {"value": round(Rc * S / best / 1e9, 5), "unit": "Gpts/s", "cores": cores, "kind": "port",
                "sample": "%d points forward (both warps, no delta), best of 2 after 1 warm-up" % (Rc * S)}
     a = out["delta_streamed"]
-    _emit(({"metric": "DQ skinning Gpts/s (bw + fw warp, 25 Gaussian bones)", "value": out["no_delta"]["fwd_gpts_s"],
-                      "unit": "Gpts/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-                      "ms_per_step": out["no_delta"]["fwd_ms"], "higher_is_better": True, "scaling": "replicas only",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "DQ skinning microbench: %d points x %d bones, fw+bw warp" % (P, B),
-                                 "l2_policy": "working set (>0.6 GB) exceeds the 126 MB L2"},
-                      "variants": out,
-                      "roofline": {"bound": "hbm", "kernel": "skin_warp_fwd_kernel x2 with streamed delta logits",
-                                   "achieved": round(a["fwd_hbm_frac"] * peaks["hbm_gbs"], 1), "peak": peaks["hbm_gbs"],
-                                   "unit": "GB/s", "frac": a["fwd_hbm_frac"], "peak_source": src, "traffic": None},
-                      "cpu_baseline": cpu}))
+    return {"metric": "DQ skinning Gpts/s (bw + fw warp, 25 Gaussian bones)", "value": out["no_delta"]["fwd_gpts_s"],
+            "unit": "Gpts/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": out["no_delta"]["fwd_ms"], "higher_is_better": True, "scaling": "replicas only",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DQ skinning microbench: %d points x %d bones, fw+bw warp" % (P, B),
+                       "l2_policy": "working set (>0.6 GB) exceeds the 126 MB L2"},
+            "variants": out,
+            "e2e": {"value": round(P / ms_e / 1e6, 3), "unit": "Gpts/s", "ms_per_step": round(ms_e, 3),
+                    "h2d_bytes_per_step": int(xyz_host.numel() * 4 + rts_host.numel() * 4),
+                    "d2h_bytes_per_step": int(2 * can_host.numel() * 4),
+                    "note": "forward (both warps, no delta) from pinned host points to pinned host results"},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "skin_warp_fwd_kernel x2 with streamed delta logits",
+                         "achieved": round(a["fwd_hbm_frac"] * peaks["hbm_gbs"], 1), "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": a["fwd_hbm_frac"], "peak_source": src,
+                         "traffic": _traffic_of("skin_warp_fwd_delta")},
+            "cpu_baseline": cpu}
 
 
-def run_grid(args):
-    """BASELINE configs[4]: canonical density on a G^3 lattice (train_utils.py:1377-1404), x-slabs per rank."""
+def run_dqs(args):
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _emit(measure_dqs(args, dev, with_cpu=not args.no_cpu))
+
+
+def measure_grid(args, dev, world, rank, with_cpu=True, steps=None):
+    """BASELINE configs[4]: canonical density on a G^3 lattice (train_utils.py:1377-1404), x-slabs per rank, gathered
+    with one all-gather.  Every rank calls this; rank 0 gets the JSON object, the others None."""
     import torch.distributed as dist
     from moda_b200 import synth, models as MM, _lib
     from moda_b200.extract import density_grid
+    assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
+    steps = steps or args.steps
+    Gs = args.grid
+    prob = synth.make_problem(8, seed=0)
+    models, emb, _ = MM.build_models(prob, dev, requires_grad=False)
+    lo, hi = rank * Gs // world, (rank + 1) * Gs // world
+    full = torch.empty(Gs, Gs, Gs, device=dev) if world > 1 else None
+    vol_host = torch.empty(Gs, Gs, Gs).pin_memory() if rank == 0 else None
+
+    def step():
+        vol = density_grid(models["coarse"], Gs, (0.3, 0.3, 0.3), emb["xyz"], x_range=(lo, hi))
+        if world > 1:
+            dist.all_gather_into_tensor(full, vol)
+            return full
+        return vol
+
+    def step_e2e():   # what extract_mesh does next: the volume goes to the host for marching cubes
+        v = step()
+        if rank == 0:
+            vol_host.copy_(v, non_blocking=True)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(step)
+    ms_e = timed(step_e2e)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return None
+    peaks, src = _peaks()
+    pts = Gs ** 3
+    flop = pts * 491264 * 2.0
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * world
+    cpu = None
+    if world == 1 and with_cpu:
+        from oracle import restated as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Gc = 48
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.density_grid(prob["coarse"], Gc, (0.3, 0.3, 0.3))
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(Gc ** 3 / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
+               "sample": "%d^3 grid (%.2f s), one pass" % (Gc, dt)}
+    return {"metric": "density-grid Mpts/s (sigma_only nerf_coarse, %d^3)" % Gs, "value": round(pts / ms / 1e3, 1),
+            "unit": "Mpts/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": "mesh-extraction density query, %d^3 lattice, x-slabs over %d rank(s)" % (Gs, world)},
+            "e2e": {"value": round(pts / ms_e / 1e3, 1), "unit": "Mpts/s", "ms_per_step": round(ms_e, 3),
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(pts * 4),
+                    "note": "lattice generated on the device (it is a function of G and the bound); the (G,G,G) fp32 "
+                            "volume is copied to pinned host memory inside the timed region"},
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "chain_kernel sigma-only program", "achieved": round(flop / (ms * 1e-3) / 1e12, 2),
+                         "peak": peak, "unit": "TFLOP/s", "frac": round(flop / (ms * 1e-3) / 1e12 / peak, 4),
+                         "peak_source": src + " bf16 sustained", "traffic": _traffic_of("chain_trunk_sigma")},
+            "cpu_baseline": cpu}
+
+
+def run_grid(args):
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -527,62 +677,9 @@ def run_grid(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    assert _lib.lib().moda_device_check() == 0, _lib.lib().moda_last_error()
-    Gs = args.grid
-    prob = synth.make_problem(8, seed=0)
-    models, emb, _ = MM.build_models(prob, dev, requires_grad=False)
-    lo, hi = rank * Gs // world, (rank + 1) * Gs // world
-    full = torch.empty(Gs, Gs, Gs, device=dev) if world > 1 else None
-
-    def step():
-        vol = density_grid(models["coarse"], Gs, (0.3, 0.3, 0.3), emb["xyz"], x_range=(lo, hi))
-        if world > 1:
-            dist.all_gather_into_tensor(full, vol)
-        return vol
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms)
+    out = measure_grid(args, dev, world, rank, with_cpu=not args.no_cpu)
     if rank == 0:
-        peaks, src = _peaks()
-        pts = Gs ** 3
-        flop = pts * 491264 * 2.0
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * world
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            from oracle import restated as O
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            Gc = 48
-            t0 = time.perf_counter()
-            with torch.no_grad():
-                O.density_grid(prob["coarse"], Gc, (0.3, 0.3, 0.3))
-            dt = time.perf_counter() - t0
-            cpu = {"value": round(Gc ** 3 / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
-                   "sample": "%d^3 grid (%.2f s), one pass" % (Gc, dt)}
-        _emit(({"metric": "density-grid Mpts/s (sigma_only nerf_coarse, %d^3)" % Gs, "value": round(pts / ms / 1e3, 1),
-                          "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
-                          "config": {"workload": "mesh-extraction density query, %d^3 lattice, x-slabs over %d rank(s)" % (Gs, world)},
-                          "roofline": {"bound": "tensor", "kernel": "chain_kernel sigma-only program", "achieved": round(flop / (ms * 1e-3) / 1e12, 2),
-                                       "peak": peak, "unit": "TFLOP/s", "frac": round(flop / (ms * 1e-3) / 1e12 / peak, 4),
-                                       "peak_source": src + " bf16 sustained", "traffic": None},
-                          "cpu_baseline": cpu}))
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -596,6 +693,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--cpu-rays", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the DQ-skinning / density-grid figures of the default line")
     ap.add_argument("--workload", default="train", choices=["train", "dqs", "grid"],
                     help="train: the headline training step (default); dqs / grid: BASELINE configs[3] / configs[4]")
     ap.add_argument("--dqs-rays", type=int, default=131072)
