@@ -117,6 +117,12 @@ int moda_composite_bwd(const float* rgb, int ld_rgb, const float* sigma, int ld_
                        float* g_rgbs, int ld_grgb, float* g_sigma, int ld_gsigma, float* g_beta, float* g_nd,
                        float* g_xa, float* g_xb, int R, int S, cudaStream_t stream);
 
+/* ---- per-ray expectations under the compositing weights: feat_final = sum_s w f (nnutils/rendering.py:233) ----
+ * w (R,S), v (R,S,C), C <= 32 -> out (R,C).  Adjoint: gw (R,S) = sum_c gout v, gv (R,S,C) = w gout (either may be NULL). */
+int moda_wsum_fwd(const float* w, const float* v, float* out, int R, int S, int C, cudaStream_t stream);
+int moda_wsum_bwd(const float* w, const float* v, const float* gout, float* gw, float* gv, int R, int S, int C,
+                  cudaStream_t stream);
+
 /* ---- linear layers of NeRF.forward (nnutils/nerf.py:147-198) with evaluate_mlp's input assembly
  * (nnutils/geom_utils.py:19-57) folded in.  The A operand is a virtual row-wise concatenation of nseg
  * (<=3) column segments described by HOST arrays: seg_ptr[i] device pointer, seg_ld[i] row stride,

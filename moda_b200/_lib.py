@@ -69,6 +69,8 @@ SIGNATURES = {
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 6,
     "moda_chain_set_trace": [c_p],
     "moda_chain_pair_available": [],
+    "moda_wsum_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "moda_wsum_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "moda_act_bwd": [c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_p],
 }
 

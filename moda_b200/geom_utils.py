@@ -199,3 +199,216 @@ def warp_points(xyz, bones_rst, rts_fw, skin_aux, dskin, backward=True):
     y, _ = SkinWarpFn.apply(xyz, bones_rst.reshape(B, 10), rts_fw.reshape(-1, B, 8), skin_aux, dskin, None,
                             bool(backward), bool(backward), True, False)
     return y
+
+
+# ------------------------------------------------------------------------------------------------ cameras, rays, flow
+# Per-RAY (not per-sample) bookkeeping of the caller side and the small projective pieces of the
+# flow / reprojection terms (rank 1).  These run on whatever device their inputs live on; the per-sample work they feed
+# (warps, MLPs, compositing) goes through the CUDA kernels above.
+
+def obj_to_cam(in_verts, Rmat, Tmat):
+    """geom_utils.py:567-581: verts (...,N,3) -> R verts + T with per-batch R (...,3,3), T (...,3)."""
+    verts = in_verts
+    if verts.dim() == 2:
+        verts = verts[None]
+    verts = verts.reshape(-1, verts.shape[1], 3)
+    Rt = Rmat.reshape(-1, 3, 3).permute(0, 2, 1)
+    verts = verts.matmul(Rt) + Tmat.reshape(-1, 1, 3)
+    return verts.reshape(in_verts.shape)
+
+
+def K2mat(K):
+    """geom_utils.py:596-610: (fx, fy, px, py) -> 3x3 intrinsics."""
+    K = K.reshape(-1, 4)
+    Kmat = torch.zeros(K.shape[0], 3, 3, device=K.device, dtype=K.dtype)
+    Kmat[:, 0, 0], Kmat[:, 1, 1], Kmat[:, 0, 2], Kmat[:, 1, 2], Kmat[:, 2, 2] = K[:, 0], K[:, 1], K[:, 2], K[:, 3], 1
+    return Kmat
+
+
+def mat2K(Kmat):
+    """geom_utils.py:612-627."""
+    shape = Kmat.shape[:-2]
+    Kmat = Kmat.reshape(-1, 3, 3)
+    K = torch.stack([Kmat[:, 0, 0], Kmat[:, 1, 1], Kmat[:, 0, 2], Kmat[:, 1, 2]], -1)
+    return K.reshape(shape + (4,))
+
+
+def K2inv(K):
+    """geom_utils.py:638-652: inverse intrinsics matrix from (fx, fy, px, py)."""
+    K = K.reshape(-1, 4)
+    Kmat = torch.zeros(K.shape[0], 3, 3, device=K.device, dtype=K.dtype)
+    Kmat[:, 0, 0], Kmat[:, 1, 1] = 1.0 / K[:, 0], 1.0 / K[:, 1]
+    Kmat[:, 0, 2], Kmat[:, 1, 2], Kmat[:, 2, 2] = -K[:, 2] / K[:, 0], -K[:, 3] / K[:, 1], 1
+    return Kmat
+
+
+def Kmatinv(Kmat):
+    """geom_utils.py:629-636."""
+    return K2inv(mat2K(Kmat)).reshape(Kmat.shape)
+
+
+def pinhole_cam(in_verts, K):
+    """geom_utils.py:654-672: verts (...,N,3), K (...,4) -> (x / z, y / z, z) with z guarded by 1e-6."""
+    verts = in_verts.reshape(-1, in_verts.shape[1], 3)
+    Kt = K2mat(K.reshape(-1, 4)).permute(0, 2, 1)
+    verts = verts.matmul(Kt)
+    z = verts[:, :, 2:3]
+    xy = verts[:, :, :2] / (1e-6 + z)
+    return torch.cat([xy, z], -1).reshape(in_verts.shape)
+
+
+def vrender_flo(weights_coarse, xyz_coarse_target, xys, img_size):
+    """geom_utils.py:1704-1743: expected 2-D motion of a ray's samples projected into the target view.
+    weights (...,S), xyz_target (...,S,3) already projected (x, y, depth), xys (...,2) -> flo (...,2), valid (...,1)."""
+    wshape = weights_coarse.shape
+    xyz_t = xyz_coarse_target.reshape(wshape + (3,))
+    xy_t = xyz_t[..., :2]
+    invalid = torch.logical_or(xyz_t[..., -1] < 1e-5, xy_t.norm(2, -1).abs() > 2 * img_size)
+    w = torch.where(invalid, torch.zeros_like(weights_coarse), weights_coarse)
+    xy_t = torch.where(invalid[..., None], torch.zeros_like(xy_t), xy_t)
+    w = w / (1e-9 + w.sum(-1)[..., None])
+    flo = (w[..., None] * (xy_t - xys.reshape(wshape[:-1] + (1, 2)))).sum(-2)
+    flo = flo / img_size * 2
+    valid = (invalid.sum(-1) == 0).float()[..., None]
+    return flo, valid
+
+
+def diff_flo(pts_target, xys, img_size):
+    """geom_utils.py:1745-1757."""
+    return (pts_target.reshape(xys.shape) - xys) / img_size * 2
+
+
+def raycast(xys, Rmat, Tmat, Kinv, near_far):
+    """geom_utils.py:746-794: pixel coordinates -> rays in the root frame.  Returns the reference's ``rays`` dict
+    (rays_o, rays_d, near, far, rtk_vec, xys, nsample, bs), every per-ray tensor (bs, nsample, ·)."""
+    Rmat = Rmat.reshape(-1, 3, 3).float()
+    Tmat = Tmat.reshape(-1, 1, 3).float()
+    Kinv = Kinv.reshape(-1, 3, 3).float()
+    xys = xys.float()
+    bs, nsample, _ = xys.shape
+    xy1s = torch.cat([xys, torch.ones_like(xys[:, :, :1])], 2)
+    xyz3d = xy1s.matmul(Kinv.permute(0, 2, 1))
+    ray_directions = xyz3d.matmul(Rmat)
+    ray_origins = -Tmat.matmul(Rmat)
+    if near_far is not None:
+        znear = torch.ones(bs, nsample, 1, device=xys.device) * near_far[:, 0, None, None]
+        zfar = torch.ones(bs, nsample, 1, device=xys.device) * near_far[:, 1, None, None]
+    else:
+        lbound, ubound = -1.5, 1.5
+        znear = (Tmat[:, :, -1:].repeat(1, nsample, 1) + lbound).clamp_min(1e-5)
+        zfar = Tmat[:, :, -1:].repeat(1, nsample, 1) + ubound
+    rtk_vec = torch.cat([Rmat.reshape(-1, 1, 9), Tmat.reshape(-1, 1, 3), Kinv.reshape(-1, 1, 9)], -1)
+    return {"rays_o": ray_origins.repeat(1, nsample, 1), "rays_d": ray_directions, "near": znear, "far": zfar,
+            "rtk_vec": rtk_vec.repeat(1, nsample, 1), "xys": xys, "nsample": nsample, "bs": bs}
+
+
+def sample_xy(img_size, bs, nsample, device, return_all=False, lineid=None):
+    """geom_utils.py:796-827: pixel samples (rand_inds (bs,ns) long, xys (bs,ns,2)); same draws (torch.multinomial)."""
+    ax = torch.arange(img_size, device=device, dtype=torch.float32)
+    gy, gx = torch.meshgrid(ax, ax, indexing="ij")
+    xygrid = torch.stack([gx, gy], -1).reshape(1, -1, 2)
+    if return_all:
+        xys = xygrid.repeat(bs, 1, 1)
+        nsample = xys.shape[1]
+        rand_inds = torch.arange(nsample, dtype=torch.float32)[None].repeat(bs, 1)
+    else:
+        if lineid is None:
+            probs = torch.ones(img_size ** 2, device=device)
+            rand_inds = torch.multinomial(probs, bs * nsample, replacement=False).view(bs, nsample)
+            xys = xygrid[0][rand_inds]
+        else:
+            probs = torch.ones(img_size, device=device)
+            rand_inds = torch.multinomial(probs, bs * nsample, replacement=True).view(bs, nsample)
+            xys = xygrid[0][rand_inds].clone()
+            xys[..., 1] = xys[..., 1] + lineid[:, None]
+    return rand_inds.long(), xys
+
+
+def chunk_rays(rays, start, delta):
+    """geom_utils.py:829-838."""
+    return {k: v.reshape(-1, v.shape[-1])[start:start + delta] for k, v in rays.items() if torch.is_tensor(v)}
+
+
+# ------------------------------------------------------------------------------------------------ rest-pose correction
+def correct_bones(model, bones_rst, inverse=False, neudbs=True):
+    """geom_utils.py:933-949: rest bones moved by the rest-pose transform Jb* = rts_head(rest_pose_code)."""
+    if not neudbs:
+        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
+    from . import dual_quat as DQ
+    dev = bones_rst.device
+    rest_pose_code = model.rest_pose_code(torch.zeros(1, dtype=torch.long, device=dev))
+    bone_rts_rst = model.nerf_body_rts[1](rest_pose_code)[0]
+    if inverse:
+        shape = bone_rts_rst.shape
+        bone_rts_rst = DQ.dq_inverse(bone_rts_rst.reshape(-1, bones_rst.shape[-2], 8)).reshape(shape)
+    bones_rst = bone_transform(bones_rst, bone_rts_rst, neudbs, is_vec=True)[0]
+    return bones_rst, bone_rts_rst
+
+
+def correct_rest_pose(opts, bone_rts_fw, bone_rts_rst, neudbs):
+    """geom_utils.py:951-972: delta transform Jb (Jb*)^-1 in dual-quaternion algebra."""
+    if not neudbs:
+        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
+    from . import dual_quat as DQ
+    rts_shape = bone_rts_fw.shape
+    B = opts.num_bones
+    inv = DQ.dq_inverse(bone_rts_rst.reshape(-1, B, 8))
+    fw = bone_rts_fw.reshape(-1, B, 8)
+    inv = inv.expand(fw.shape[0], B, 8).contiguous()
+    return DQ.dq_mul(inv, fw.contiguous()).reshape(rts_shape)
+
+
+# ------------------------------------------------------------------------------------------------ mesh-extraction warps
+def _frame_inputs(opts, model, npts, embedid):
+    """Shared by warp_bw / warp_fw (geom_utils.py:974-1073): per-point frame id -> pose code, corrected bones and the
+    delta bone transforms of that frame."""
+    query_time = torch.ones(npts, 1, device=model.device).long() * embedid
+    bone_rts_fw = model.nerf_body_rts(query_time)
+    bones_rst, bone_rts_rst = correct_bones(model, model.bones, neudbs=opts.neudbs)
+    bone_rts_fw = correct_rest_pose(opts, bone_rts_fw, bone_rts_rst, opts.neudbs)
+    return query_time, bones_rst, bone_rts_fw
+
+
+def warp_bw(opts, model, rt_dict, query_xyz_chunk, embedid):
+    """geom_utils.py:974-1027 (articulated branch): view-space points of frame ``embedid`` -> canonical space."""
+    if getattr(opts, "flowbw", False) or getattr(opts, "lbs", False):
+        raise NotImplementedError("warp_bw: only the neudbs motion model is implemented")
+    n = query_xyz_chunk.shape[0]
+    query_time, bones_rst, bone_rts_fw = _frame_inputs(opts, model, n, embedid)
+    pts = query_xyz_chunk[:, None]
+    nerf_skin = model.nerf_skin if opts.nerf_skin else None
+    time_embedded = model.pose_code(query_time)
+    nerf_dis = model.nerf_dis if getattr(opts, "nerf_dis", False) else None
+    if nerf_dis is None:   # fused weights + warp
+        dskin = mlp_skinning(nerf_skin, time_embedded, pts, embed_xyz=model.embedding_xyz, _pitched=True)
+        out = warp_points(pts, bones_rst, bone_rts_fw, model.skin_aux, dskin, backward=True)
+        bones_dfm = bone_transform(bones_rst, bone_rts_fw, opts.neudbs, is_vec=True)
+    else:                  # the residual field is evaluated at the un-warped points: two-step path as in the reference
+        bones_dfm = bone_transform(bones_rst, bone_rts_fw, opts.neudbs, is_vec=True)
+        skin = gauss_mlp_skinning(pts, model.embedding_xyz, bones_dfm, time_embedded, nerf_skin, skin_aux=model.skin_aux)
+        out, bones_dfm, _ = neu_dbs(bones_rst, bone_rts_fw, skin, pts, nerf_dis, model.embedding_xyz, time_embedded)
+    rt_dict["bones"] = bones_dfm
+    return out[:, 0], rt_dict
+
+
+def warp_fw(opts, model, rt_dict, vertices, embedid):
+    """geom_utils.py:1029-1073 (articulated branch): canonical mesh vertices -> frame ``embedid``.  Returns a numpy
+    array like the reference (the mesh is assembled on the host)."""
+    if getattr(opts, "flowbw", False) or getattr(opts, "lbs", False):
+        raise NotImplementedError("warp_fw: only the neudbs motion model is implemented")
+    pts_can = torch.as_tensor(vertices, dtype=torch.float32).to(model.device)[:, None]
+    n = pts_can.shape[0]
+    _, bones_rst, bone_rts_fw = _frame_inputs(opts, model, n, embedid)
+    nerf_skin = model.nerf_skin if opts.nerf_skin else None
+    rest_pose_code = model.rest_pose_code(torch.zeros(1, dtype=torch.long, device=bones_rst.device))
+    nerf_dis = model.nerf_dis if getattr(opts, "nerf_dis", False) else None
+    if nerf_dis is None:
+        dskin = mlp_skinning(nerf_skin, rest_pose_code, pts_can, embed_xyz=model.embedding_xyz, _pitched=True)
+        pts_dfm = warp_points(pts_can, bones_rst, bone_rts_fw, model.skin_aux, dskin, backward=False)
+        bones_dfm = bone_transform(bones_rst, bone_rts_fw, opts.neudbs, is_vec=True)
+    else:   # weights from the undisplaced points, blend applied to the displaced ones (geom_utils.py:423-429)
+        skin = gauss_mlp_skinning(pts_can, model.embedding_xyz, bones_rst, rest_pose_code, nerf_skin, skin_aux=model.skin_aux)
+        pts_dfm, bones_dfm, _ = neu_dbs(bones_rst, bone_rts_fw, skin, pts_can, nerf_dis, model.embedding_xyz, rest_pose_code,
+                                        backward=False)
+    rt_dict["bones"] = bones_dfm
+    return pts_dfm[:, 0].detach().cpu().numpy(), rt_dict

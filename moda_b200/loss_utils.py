@@ -1,0 +1,139 @@
+"""Loss terms that ``inference_deform`` evaluates inside the renderer at MoDA's default flags (nnutils/loss_utils.py):
+feature matching against the canonical feature volume, key-point reprojection, and the visibility-field loss.
+
+Per-sample work (the MLPs on P points, the skinning warps) goes through the CUDA kernels of this package
+(``geom_utils.evaluate_mlp`` / ``warp_points``).  The (rays x 8000) soft-argmax / Sinkhorn algebra of ``feat_match``
+and the per-ray camera algebra are expressed with device tensor ops: they are O(rays), not O(samples), and are listed
+in DESIGN.md as the next candidates for fused kernels.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import geom_utils as G
+
+
+def visibility_loss(mlp, embed, xyz_pos, w_pos, bound, chunk):
+    """loss_utils.py:125-149.  w_pos: (rays, samples) transmittance returned by the compositor; negatives are drawn
+    uniformly in the object bound (same draw as the reference: torch.rand(1, nsample, 3) on the host)."""
+    device = next(mlp.parameters()).device
+    xyz_pos = xyz_pos.detach()
+    w_pos = w_pos.detach()
+    nsample = w_pos.shape[0] * w_pos.shape[1]
+    # the reference draws on the host and uploads 12 B per sample (loss_utils.py:138); same distribution, drawn on the
+    # device instead
+    bound_t = torch.as_tensor(np.asarray(bound), dtype=torch.float32, device=device)[None, None]
+    xyz_neg = torch.rand(1, nsample, 3, device=device) * 2 * bound_t - bound_t
+    vis_neg_pred = G.evaluate_mlp(mlp, xyz_neg, embed_xyz=embed, chunk=chunk)[..., 0]
+    vis_loss_neg = -F.logsigmoid(-vis_neg_pred).sum() * 0.1 / nsample
+    vis_pos_pred = G.evaluate_mlp(mlp, xyz_pos, embed_xyz=embed, chunk=chunk)[..., 0]
+    vis_loss_pos = -(F.logsigmoid(vis_pos_pred) * w_pos).sum() / nsample
+    return vis_loss_pos + vis_loss_neg
+
+
+def compute_pts_exp(pts_prob, pts):
+    """loss_utils.py:162-172: expected 3-D point of a ray under its (renormalised) compositing weights."""
+    ndepth = pts_prob.shape[-1]
+    p = pts_prob.reshape(-1, ndepth, 1)
+    p = p / (1e-9 + p.sum(1)[:, None])
+    return (pts * p).sum(1)
+
+
+def feat_match_loss(nerf_feat, embedding_xyz, feats, pts, pts_prob, bound, use_corr=True, use_ot=False,
+                    is_training=True):
+    """loss_utils.py:174-209.  feats (...,F) pixel features, pts (...,S,3), pts_prob (...,S)."""
+    base_shape = feats.shape[:-1]
+    nfeat = feats.shape[-1]
+    ndepth = pts_prob.shape[-1]
+    feats = feats.reshape(-1, nfeat)
+    pts = pts.reshape(-1, ndepth, 3)
+    pts_exp = compute_pts_exp(pts_prob, pts)
+    pts_pred, corr_err = feat_match(nerf_feat, embedding_xyz, feats, bound, grid_size=20, use_corr=use_corr,
+                                    use_ot=use_ot, is_training=is_training)
+    feat_err = (pts_pred - pts_exp).norm(2, -1)
+    pts_pred = pts_pred.reshape(base_shape + (3,))
+    pts_exp = pts_exp.reshape(base_shape + (3,))
+    feat_err = feat_err.reshape(base_shape + (1,))
+    if use_corr:
+        corr_err = corr_err.reshape(base_shape + (1,))
+    return pts_pred, pts_exp, feat_err, corr_err
+
+
+def feat_match(nerf_feat, embedding_xyz, feats, bound, grid_size=20, use_corr=True, use_ot=False, is_training=True,
+               init_pts=None, rt_entropy=False):
+    """loss_utils.py:273-405: soft-argmax of pixel features over the canonical feature volume sampled on a
+    grid_size^3 lattice (softmax with temperature |beta|, or 20 Sinkhorn iterations at eps = 0.03 when ``use_ot``)."""
+    if init_pts is not None:
+        raise NotImplementedError("feat_match(init_pts=...) is only used by the reference's offline pose refinement")
+    device = feats.device
+    feats = F.normalize(feats, 2, -1)
+    bound = np.asarray(bound, dtype=np.float32)
+    pxd = np.linspace(-bound[0], bound[0], grid_size).astype(np.float32)
+    pyd = np.linspace(-bound[1], bound[1], grid_size).astype(np.float32)
+    pzd = np.linspace(-bound[2], bound[2], grid_size).astype(np.float32)
+    query_yxz = torch.from_numpy(np.stack(np.meshgrid(pyd, pxd, pzd), -1)).to(device).reshape(-1, 3)
+    query_xyz = torch.cat([query_yxz[:, 1:2], query_yxz[:, 0:1], query_yxz[:, 2:3]], -1)[None]
+    if is_training:   # jitter the lattice (loss_utils.py:305-308)
+        bound_t = torch.from_numpy(bound)[None, None].to(device)
+        query_xyz = query_xyz + torch.randn_like(query_xyz) * bound_t * 0.05
+    # canonical features on the lattice: one MLP evaluation over all grid_size^3 points (the reference chunks by 8192)
+    vol_feat = G.evaluate_mlp(nerf_feat, query_xyz[0][:, None], embed_xyz=embedding_xyz)[:, 0]
+    vol_feat = F.normalize(vol_feat, 2, -1)
+    cost_vol = feats.matmul(vol_feat.t())
+    if not use_ot:
+        cost_vol = cost_vol * (nerf_feat.beta.abs() + 1e-9)
+    if use_ot:
+        K = torch.exp(-(1.0 - cost_vol[None]) / 0.03)
+        n1, n2 = K.shape[1], K.shape[2]
+        a = torch.ones(1, n1, 1, device=device, dtype=K.dtype) / n1
+        prob1 = torch.ones(1, n1, 1, device=device, dtype=K.dtype) / n1
+        prob2 = torch.ones(1, n2, 1, device=device, dtype=K.dtype) / n2
+        for _ in range(20):
+            KTa = torch.bmm(K.transpose(1, 2), a)
+            b = prob2 / (KTa + 1e-8)
+            Kb = torch.bmm(K, b)
+            a = prob1 / (Kb + 1e-8)
+        T_m = a * K * b.transpose(1, 2)
+        prob_vol = (T_m / T_m.sum(2, keepdim=True))[0]
+    else:
+        prob_vol = cost_vol.softmax(-1)
+    if use_corr:
+        T_T = prob_vol.matmul(prob_vol.t())
+        corr_err = (T_T - torch.eye(prob_vol.shape[0], device=device)).norm(2, -1)
+    else:
+        corr_err = 0
+    pts_pred = (prob_vol[..., None] * query_xyz).sum(1)
+    if rt_entropy:
+        match_unc = (-prob_vol * prob_vol.clamp(1e-9, 1 - 1e-9).log()).sum(1)[:, None] / np.log(grid_size ** 3)
+        return pts_pred, match_unc, corr_err
+    return pts_pred, corr_err
+
+
+def kp_reproj(pts_pred, models, embedding_xyz, rays, to_target=False, neudbs=True):
+    """loss_utils.py:224-270: canonical points -> (forward warp of their frame) -> camera -> pixels.  (...,3) -> (N,1,2)."""
+    if not neudbs:
+        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
+    N = pts_pred.reshape(-1, 3).shape[0]
+    xyz = pts_pred.reshape(-1, 1, 3)
+    rtk_vec = (rays["rtk_vec_target"] if to_target else rays["rtk_vec"]).reshape(N, -1)
+    if "bones" in models:
+        bone_rts_fw = (rays["bone_rts_target"] if to_target else rays["bone_rts"]).reshape(N, -1)
+        bones = models["bones_rst"]
+        rest_pose_code = models["rest_pose_code"](torch.zeros(1, dtype=torch.long, device=bones.device))
+        dskin = G.mlp_skinning(models.get("nerf_skin"), rest_pose_code, xyz, embed_xyz=embedding_xyz, _pitched=True)
+        xyz = G.warp_points(xyz, bones, bone_rts_fw, models["skin_aux"], dskin, backward=False)
+    Rmat = rtk_vec[:, 0:9].reshape(N, 1, 3, 3)
+    Tmat = rtk_vec[:, 9:12].reshape(N, 1, 3)
+    Kinv = rtk_vec[:, 12:21].reshape(N, 1, 3, 3)
+    K = G.mat2K(G.Kmatinv(Kinv))
+    xyz = G.obj_to_cam(xyz, Rmat, Tmat)
+    xyz = G.pinhole_cam(xyz, K)
+    return xyz[..., :2]
+
+
+def kp_reproj_loss(pts_pred, xys, models, embedding_xyz, rays, neudbs=True):
+    """loss_utils.py:211-222."""
+    xys = xys.reshape(-1, 1, 2)
+    xy_reproj = kp_reproj(pts_pred, models, embedding_xyz, rays, neudbs=neudbs)
+    proj_err = (xys - xy_reproj[..., :2]).norm(2, -1)
+    return proj_err.reshape(pts_pred.shape[:-1] + (1,))

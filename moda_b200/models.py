@@ -29,10 +29,24 @@ def build_models(prob, device="cuda", requires_grad=True):
     return models, embeddings, rays
 
 
+def build_full_models(prob, device="cuda", requires_grad=True):
+    """``build_models`` + nerf_feat (5x128 -> 16 features, init_beta 1) and nerf_vis (5x64 -> 1) as nnutils/moda.py:344-348
+    and 447-449 construct them; prob from synth.make_full_problem."""
+    models, embeddings, rays = build_models(prob, device, requires_grad)
+    feat = NeRF(in_channels_xyz=63, D=5, W=128, out_channels=16, in_channels_dir=0, raw_feat=True, init_beta=1.)
+    vis = NeRF(in_channels_xyz=63, D=5, W=64, out_channels=1, in_channels_dir=0, raw_feat=True)
+    feat.load_state_dict(prob["nerf_feat"])
+    vis.load_state_dict(prob["nerf_vis"])
+    models["nerf_feat"], models["nerf_vis"] = feat.to(device), vis.to(device)
+    if requires_grad and "bone_rts_target" in rays:
+        rays["bone_rts_target"].requires_grad_(True)
+    return models, embeddings, rays
+
+
 def parameters_of(models):
     """Every leaf tensor of ``models`` that receives a gradient from ``render_rays``."""
     ps = []
-    for k in ("coarse", "nerf_skin", "rest_pose_code"):
+    for k in ("coarse", "nerf_skin", "rest_pose_code", "nerf_feat", "nerf_vis"):
         if k in models:
             ps += [p for p in models[k].parameters()]
     for k in ("bones_rst", "skin_aux"):

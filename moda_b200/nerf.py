@@ -99,3 +99,76 @@ class NeRF(nn.Module):
         dir_segs = [(SEG_DENSE, 0, self.in_channels_dir, 1, cx)] if self.in_channels_dir > 0 else []
         out = self.run(x2.shape[0], [x2], xyz_segs, dir_segs, None, sigma_only)
         return out.reshape(lead + (out.shape[-1],))
+
+
+class DQ_RTHead(NeRF):
+    """Pose MLP -> one dual quaternion per bone (nnutils/nerf.py:239-279): out (bs, 1, B*8) with
+    dq = [normalize(r), 0.5 * (0, 0.1 t) (x) normalize(r)].  Evaluated once per FRAME (moda.py:1304), not per sample."""
+
+    def __init__(self, use_quat, **kwargs):
+        super().__init__(**kwargs)
+        if not use_quat:
+            raise NotImplementedError("DQ_RTHead is only used with use_quat=True (moda.py:313-317)")
+        self.use_quat = use_quat
+        self.num_output = 7
+        for m in self.modules():
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    def forward(self, x):
+        from . import dual_quat as DQ
+        x = super().forward(x)
+        bs = x.shape[0]
+        rts = x.reshape(-1, self.num_output)
+        tmat = rts[:, 0:3] * 0.1
+        rquat = DQ.q_normalize(rts[:, 3:7].contiguous())
+        tquat = torch.cat((torch.zeros_like(tmat[:, :1]), tmat), -1)
+        dq_d = 0.5 * DQ.q_mul(tquat.contiguous(), rquat)
+        return torch.cat((rquat, dq_d), -1).reshape(bs, 1, -1)
+
+
+class Transhead(NeRF):
+    """Translation flow field (nnutils/nerf.py:200-210): 0.1 * MLP(x)."""
+
+    def forward(self, x, xyz=None, sigma_only=False):
+        return super().forward(x, sigma_only=sigma_only) * 0.1
+
+
+def fid_reindex(fid, num_vids, vid_offset):
+    """geom_utils.py:1759-1777: absolute frame id -> (video id, frame id relative to the middle of its video,
+    normalised by the longest video)."""
+    tid = torch.zeros_like(fid).float()
+    vid = torch.zeros_like(fid)
+    max_ts = float((vid_offset[1:] - vid_offset[:-1]).max())
+    for i in range(num_vids):
+        assign = torch.logical_and(fid >= int(vid_offset[i]), fid < int(vid_offset[i + 1]))
+        vid = torch.where(assign, torch.full_like(vid, i), vid)
+        doffset = float(vid_offset[i])
+        dnmax = float(vid_offset[i + 1]) - doffset
+        tid = torch.where(assign, (fid.float() - doffset - dnmax / 2) / max_ts * 2, tid)
+    return vid, tid
+
+
+class FrameCode(nn.Module):
+    """Frame index -> code through a per-video Fourier basis (nnutils/nerf.py:346-380): pose / environment codes."""
+
+    def __init__(self, num_freq, embedding_dim, vid_offset, scale=1):
+        super().__init__()
+        import numpy as np
+        self.vid_offset = np.asarray(vid_offset)
+        self.num_vids = len(vid_offset) - 1
+        max_ts = (self.vid_offset[1:] - self.vid_offset[:-1]).max()
+        self.num_freq = 2 * int(np.log2(max_ts)) - 2
+        self.fourier_embed = Embedding(1, num_freq, alpha=num_freq)
+        self.basis_mlp = nn.Linear(self.num_vids * self.fourier_embed.out_channels, embedding_dim)
+        self.scale = scale
+
+    def forward(self, fid):
+        bs = fid.shape[0]
+        vid, tid = fid_reindex(fid, self.num_vids, self.vid_offset)
+        tid = (tid * self.scale).reshape(bs, 1)
+        vid = vid.reshape(bs, 1)
+        coeff = self.fourier_embed(tid)
+        onehot = torch.nn.functional.one_hot(vid, num_classes=self.num_vids)
+        coeff = (coeff[..., None] * onehot).reshape(bs, -1)
+        return torch.nn.functional.linear(coeff, self.basis_mlp.weight, self.basis_mlp.bias)

@@ -560,6 +560,30 @@ class CompositeFn(torch.autograd.Function):
         return g_raw, None, gd, g_beta.reshape(beta.shape), None, None, g_xa, g_xb
 
 
+class WeightedSumFn(torch.autograd.Function):
+    """out (R,C) = sum_s w (R,S) * v (R,S,C): feature compositing (nnutils/rendering.py:233)."""
+
+    @staticmethod
+    def forward(ctx, w, v):
+        w, v = f32(w), f32(v)
+        R, S = w.shape
+        C = v.shape[-1]
+        out = torch.empty(R, C, device=w.device, dtype=torch.float32)
+        call("moda_wsum_fwd", ptr(w), ptr(v), ptr(out), R, S, C, stream())
+        ctx.save_for_backward(w, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, v = ctx.saved_tensors
+        R, S = w.shape
+        C = v.shape[-1]
+        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        gv = torch.empty_like(v) if ctx.needs_input_grad[1] else None
+        call("moda_wsum_bwd", ptr(w), ptr(v), ptr(f32(g)), ptr(gw), ptr(gv), R, S, C, stream())
+        return gw, gv
+
+
 class SamplePdfFn(torch.autograd.Function):
     """sample_pdf (nnutils/rendering.py:582-623); with ``z_vals`` also the sorted union of rendering.py:103-110.
     Outputs are detached in the reference (:105-106), so there is no backward."""

@@ -2,20 +2,23 @@
 the CUDA kernels of this package: sample generation, nerf_skin delta logits, fused Gaussian-skinning +
 dual-quaternion backward / forward warps, the 8x256 trunk, and the compositor with the cycle term.
 
-What is implemented is SURVEY.md section 8(a)'s core path: ``models`` keys {coarse, bones, bones_rst,
-skin_aux, nerf_skin, rest_pose_code} (+ nerf_vis for ``render_vis``), ``rays`` keys {rays_o, rays_d, near,
-far, xys, time_embedded, bone_rts, env_code} (+ the ``*_at_samp`` per-ray loss inputs).  Branches that
-SURVEY.md section 8(f) lists as "next" (flow fields, LBS, feature matching, flow rendering, nerf_unc) raise
-NotImplementedError instead of silently doing something else.
+Implemented: SURVEY.md section 8(a)'s core path -- ``models`` keys {coarse, bones, bones_rst, skin_aux, nerf_skin,
+rest_pose_code}, ``rays`` keys {rays_o, rays_d, near, far, xys, time_embedded, bone_rts, env_code} -- and, since round
+2, what MoDA's DEFAULT flags add to a training step (section 8(f) rank 1): ``nerf_feat`` feature rendering +
+``feat_match_loss`` + key-point reprojection, the third warp to the paired frame with flow rendering
+(``rtk_vec_target`` / ``bone_rts_target`` / ``*_dentrg``), ``nerf_vis`` (``render_vis`` masking and ``vis_loss``),
+``nerf_dis`` residual fields, ``symm_shape`` and the per-ray loss terms.  Branches that remain out of scope (free-form
+flow fields, LBS, nerf_unc, appearance codes, s3im) raise NotImplementedError instead of silently doing something else.
 """
 import torch
+import torch.nn.functional as F
 
 from . import geom_utils as G
-from .ops import CompositeFn, PointsFromDepthsFn, SampleRaysFn, SamplePdfFn
+from . import loss_utils as L
+from .ops import CompositeFn, PointsFromDepthsFn, SampleRaysFn, SamplePdfFn, WeightedSumFn
 
-_UNSUPPORTED_MODELS = ("flowbw", "flowfw", "nerf_feat", "nerf_unc", "nerf_dis")
-_UNSUPPORTED_RAYS = ("rtk_vec_target", "rtk_vec_dentrg", "feats_at_samp", "bone_rts_target", "bone_rts_dentrg",
-                     "appearance_code")
+_UNSUPPORTED_MODELS = ("flowbw", "flowfw", "nerf_unc")
+_UNSUPPORTED_RAYS = ("appearance_code",)
 
 
 def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=1, chunk=1024 * 32,
@@ -29,6 +32,8 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
             raise NotImplementedError("rays['%s'] is outside the accelerated core path (SURVEY.md 8(f))" % k)
     if opts is not None and (getattr(opts, "lbs", False) or not getattr(opts, "neudbs", True)) and "bones" in models:
         raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
+    if opts is not None and getattr(opts, "s3im_loss", False):
+        raise NotImplementedError("opts.s3im_loss is off in every MoDA script (moda.py:170) and not implemented")
     if use_fine:
         N_samples = N_samples // 2
     embedding_xyz, embedding_dir = embeddings["xyz"], embeddings["dir"]
@@ -94,6 +99,9 @@ def inference(models, embedding_xyz, xyz_, dir_, dir_embedded, z_vals, N_rays, N
         raw = torch.cat([torch.zeros(N_rays, S, 3, device=out.device), out], -1)
     else:
         raw = out
+    feat = None
+    if "nerf_feat" in models:   # rendering.py:174-178
+        feat = G.evaluate_mlp(models["nerf_feat"], xyz_input, embed_xyz=embedding_xyz, chunk=4096)
     # the reference draws the noise unconditionally (rendering.py:193): keep the generator in step
     noise = torch.randn(N_rays, S, device=raw.device)
     noise = noise * noise_std if noise_std != 0 else None
@@ -106,17 +114,34 @@ def inference(models, embedding_xyz, xyz_, dir_, dir_embedded, z_vals, N_rays, N
         mask = m2 if mask is None else (mask | m2)
     xa, xb = cyc_pair if cyc_pair is not None else (None, None)
     rgb, depth, sil, weights, vis, cyc = CompositeFn.apply(raw, z_vals, dir_, nerf_sdf.beta, noise, mask, xa, xb)
-    feat = torch.zeros_like(rgb)
+    if feat is not None:
+        feat = WeightedSumFn.apply(weights, feat)   # rendering.py:233
+    else:
+        feat = torch.zeros_like(rgb)
     if cyc_pair is not None:
         return rgb, feat, depth, weights, vis, sil, cyc
     return rgb, feat, depth, weights, vis, sil
 
 
+def _project(xyz, rtk_vec, N_rays):
+    """rendering.py:428-449: root-frame points (N,S,3) -> pixels of the view described by rtk_vec (N,21)."""
+    Rmat = rtk_vec[:, 0:9].reshape(N_rays, 1, 3, 3)
+    Tmat = rtk_vec[:, 9:12].reshape(N_rays, 1, 3)
+    Kinv = rtk_vec[:, 12:21].reshape(N_rays, 1, 3, 3)
+    K = G.mat2K(G.Kmatinv(Kinv))
+    return G.pinhole_cam(G.obj_to_cam(xyz, Rmat, Tmat), K)
+
+
 def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays, embedding_xyz, rays_d, noise_std,
                      obj_bound, dir_embedded, z_vals, img_size, progress, opts, fine_iter=True, render_vis=False):
-    """rendering.py:239-579, core path: backward warp, cycle forward warp, trunk + compositing, per-ray terms."""
+    """rendering.py:239-579: backward warp, cycle forward warp (+ the warps to the paired frames), trunk + feature +
+    compositing, and the per-ray terms of the training losses."""
     is_training = models["coarse"].training
+    dist_corresp = bool(getattr(opts, "dist_corresp", False))
+    use_corresp = bool(getattr(opts, "use_corresp", False))
+    xys = rays.get("xys")
     xyz_coarse_frame = xyz_coarse_sampled
+    xyz_coarse_target = xyz_coarse_dentrg = xyz_coarse_sampled
     result = {}
     cyc_pair = None
     has_bones = "bones" in models
@@ -127,17 +152,37 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
         rest_pose_code = models["rest_pose_code"]
         rest_pose_code = rest_pose_code(torch.zeros(1, dtype=torch.long, device=bones_rst.device))
         nerf_skin = models.get("nerf_skin")
+        nerf_dis = models.get("nerf_dis")
         time_embedded = rays["time_embedded"]
         # backward warp (rendering.py:303-322): delta logits, then skinning + DQ blend fused in one kernel
         dskin_bw = G.mlp_skinning(nerf_skin, time_embedded, xyz_coarse_sampled, embed_xyz=embedding_xyz, _pitched=True)
-        xyz_coarse_sampled = G.warp_points(xyz_coarse_sampled, bones_rst, bone_rts_fw, skin_aux, dskin_bw,
-                                           backward=True)
+        xyz_in = xyz_coarse_sampled
+        xyz_coarse_sampled = G.warp_points(xyz_in, bones_rst, bone_rts_fw, skin_aux, dskin_bw, backward=True)
+        if nerf_dis is not None:   # geom_utils.py:416-418: the residual is evaluated at the un-warped points
+            xyz_dis = G.evaluate_mlp(nerf_dis, xyz_in, embedding_xyz, code=time_embedded[:, None], chunk=xyz_in.shape[0])
+            xyz_coarse_sampled = xyz_coarse_sampled - xyz_dis
+            result["dis_reg"] = torch.norm(xyz_dis, dim=2, keepdim=False)
         if fine_iter:
-            # cycle forward warp (rendering.py:330-341)
+            # cycle forward warp (rendering.py:330-341) and the warps of the same canonical points to the paired frames
+            # (:345-360): one set of forward skinning weights (delta logits from the rest pose code), three transforms
             dskin_fw = G.mlp_skinning(nerf_skin, rest_pose_code, xyz_coarse_sampled, embed_xyz=embedding_xyz, _pitched=True)
-            xyz_coarse_frame_cyc = G.warp_points(xyz_coarse_sampled, bones_rst, bone_rts_fw, skin_aux, dskin_fw,
-                                                 backward=False)
+            if nerf_dis is None:
+                fw = lambda rts: G.warp_points(xyz_coarse_sampled, bones_rst, rts, skin_aux, dskin_fw, backward=False)
+            else:
+                # geom_utils.py:423-429: the weights come from the undisplaced canonical points, the blend acts on the
+                # displaced ones -> explicit weights, then the blend kernel
+                skin_fw = G.skinning(bones_rst, xyz_coarse_sampled, dskin_fw, skin_aux=skin_aux)
+                xyz_dis_fw = G.evaluate_mlp(nerf_dis, xyz_coarse_sampled, embedding_xyz, code=rest_pose_code,
+                                            chunk=xyz_coarse_sampled.shape[0])
+                result["dis_reg_forward"] = torch.norm(xyz_dis_fw, dim=2, keepdim=False)
+                xyz_disp = xyz_coarse_sampled + xyz_dis_fw
+                fw = lambda rts: G.neu_dbs(bones_rst, rts, skin_fw, xyz_disp, backward=False)[0]
+            xyz_coarse_frame_cyc = fw(bone_rts_fw)
             cyc_pair = (xyz_coarse_frame, xyz_coarse_frame_cyc)
+            if dist_corresp and "bone_rts_target" in rays:
+                xyz_coarse_target = fw(rays["bone_rts_target"])
+            if dist_corresp and "bone_rts_dentrg" in rays:
+                xyz_coarse_dentrg = fw(rays["bone_rts_dentrg"])
     env_code = rays.get("env_code")
     if render_vis:
         clip_bound = obj_bound
@@ -146,42 +191,106 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
     else:
         clip_bound, vis_pred = None, None
     if opts is not None and getattr(opts, "symm_shape", False):
-        raise NotImplementedError("symm_shape is outside the accelerated core path")
-    out = inference(models, embedding_xyz, xyz_coarse_sampled, rays_d, dir_embedded, z_vals, N_rays, N_samples,
+        # rendering.py:385-391: half of the samples (a fresh draw per call) are evaluated at their x-mirror image
+        xyz_x = xyz_coarse_sampled[..., :1]
+        symm_mask = torch.rand_like(xyz_x) < 0.5
+        xyz_input = torch.cat([torch.where(symm_mask, -xyz_x, xyz_x), xyz_coarse_sampled[..., 1:3]], -1)
+    else:
+        xyz_input = xyz_coarse_sampled
+    out = inference(models, embedding_xyz, xyz_input, rays_d, dir_embedded, z_vals, N_rays, N_samples,
                     chunk, noise_std, env_code=env_code, clip_bound=clip_bound, vis_pred=vis_pred,
                     scale_rgb=getattr(opts, "scale_rgb", 1.3), rgb_filter=getattr(opts, "rgb_filter", False),
                     cyc_pair=cyc_pair)
-    rgb_coarse, _, depth_rnd, weights_coarse, vis_coarse, sil_coarse = out[:6]
+    rgb_coarse, feat_rnd, depth_rnd, weights_coarse, vis_coarse, sil_coarse = out[:6]
     result["img_coarse"] = rgb_coarse
     result["depth_rnd"] = depth_rnd
     result["sil_coarse"] = sil_coarse
     if render_vis:
         result["vis_pred"] = (vis_pred * weights_coarse).sum(-1)
-    if fine_iter:
-        result["xyz_camera_vis"] = xyz_coarse_frame
-        if has_bones:
-            result["xyz_canonical_vis"] = xyz_coarse_sampled
-            result["frame_cyc_dis"] = out[6]
-        if "img_at_samp" in rays:
-            _per_ray_losses(result, rays, rgb_coarse, sil_coarse, is_training)
+    if not fine_iter:
+        return result, weights_coarse
+
+    pts_target = None
+    if use_corresp and not dist_corresp and "rtk_vec_target" in rays:   # rendering.py:407-411
+        pts_exp = L.compute_pts_exp(weights_coarse, xyz_coarse_sampled)
+        pts_target = L.kp_reproj(pts_exp, models, embedding_xyz, rays, to_target=True, neudbs=opts.neudbs)
+    if "feats_at_samp" in rays:   # rendering.py:413-432: feature matching + 3d-2d reprojection
+        pts_pred, pts_exp, feat_err, corr_err = L.feat_match_loss(
+            models["nerf_feat"], embedding_xyz, rays["feats_at_samp"], xyz_coarse_sampled, weights_coarse, obj_bound,
+            getattr(opts, "use_corr", False), getattr(opts, "use_ot", False), is_training=is_training)
+        proj_err = L.kp_reproj_loss(pts_pred, xys, models, embedding_xyz, rays, neudbs=opts.neudbs)
+        result["pts_pred"], result["pts_exp"] = pts_pred, pts_exp
+        result["feat_err"] = feat_err
+        if getattr(opts, "use_corr", False):
+            result["corr_err"] = corr_err
+        result["proj_err"] = proj_err / img_size * 2
+    if dist_corresp and "rtk_vec_target" in rays:   # :434-446
+        xyz_coarse_target = _project(xyz_coarse_target, rays["rtk_vec_target"], N_rays)
+    if dist_corresp and "rtk_vec_dentrg" in rays:   # :448-459
+        xyz_coarse_dentrg = _project(xyz_coarse_dentrg, rays["rtk_vec_dentrg"], N_rays)
+
+    result["xyz_camera_vis"] = xyz_coarse_frame
+    if has_bones:
+        result["xyz_canonical_vis"] = xyz_coarse_sampled
+    if "feats_at_samp" in rays:
+        result["pts_exp_vis"] = pts_exp
+        result["pts_pred_vis"] = pts_pred
+    if has_bones:
+        result["frame_cyc_dis"] = out[6]
+    if is_training and "nerf_vis" in models:   # :475-477
+        result["vis_loss"] = L.visibility_loss(models["nerf_vis"], embedding_xyz, xyz_coarse_sampled, vis_coarse,
+                                               obj_bound, chunk)
+    flo_coarse = flo_valid = None
+    if "rtk_vec_target" in rays:   # :480-489
+        if dist_corresp:
+            flo_coarse, flo_valid = G.vrender_flo(weights_coarse, xyz_coarse_target, xys, img_size)
+        else:
+            if pts_target is None:
+                raise RuntimeError("rtk_vec_target without dist_corresp needs opts.use_corresp (rendering.py:407-411)")
+            flo_coarse = G.diff_flo(pts_target, xys, img_size)
+            flo_valid = torch.ones_like(flo_coarse[..., :1])
+        result["flo_coarse"], result["flo_valid"] = flo_coarse, flo_valid
+    if "rtk_vec_dentrg" in rays:   # :491-499
+        if not dist_corresp:
+            raise NotImplementedError("rtk_vec_dentrg without dist_corresp reads an undefined variable in the reference "
+                                      "(rendering.py:496)")
+        result["fdp_coarse"], result["fdp_valid"] = G.vrender_flo(weights_coarse, xyz_coarse_dentrg, xys, img_size)
+    if "img_at_samp" in rays:
+        _per_ray_losses(result, rays, rgb_coarse, sil_coarse, is_training, flo_coarse, flo_valid)
+    if "feats_at_samp" in rays:   # :572-578
+        feat_n = F.normalize(feat_rnd, 2, -1)
+        frnd_loss_samp = (feat_n - rays["feats_at_samp"]).pow(2).mean(-1)
+        result["frnd_loss_samp"] = frnd_loss_samp * rays["sil_at_samp"][..., 0]
     return result, weights_coarse
 
 
-def _per_ray_losses(result, rays, rgb_coarse, sil_coarse, is_training):
-    """rendering.py:516-566 without the flow term: O(N_rays) bookkeeping on already-rendered values."""
+def _per_ray_losses(result, rays, rgb_coarse, sil_coarse, is_training, flo_coarse=None, flo_valid=None):
+    """rendering.py:516-570: O(N_rays) bookkeeping on already-rendered values."""
     img_at_samp, sil_at_samp, vis_at_samp = rays["img_at_samp"], rays["sil_at_samp"], rays["vis_at_samp"]
     img_loss_samp = (rgb_coarse - img_at_samp).pow(2).mean(-1)[..., None]
     sil_balance_wt = 1
     if is_training:
         # the reference tests `sil_at_samp.sum()>0` on the host (a device sync, rendering.py:535); the same
         # weights are formed on the device and selected with where()
-        pos = sil_at_samp[vis_at_samp > 0].sum() if False else (sil_at_samp * (vis_at_samp > 0)).sum()
+        vis_on = (vis_at_samp > 0).to(sil_at_samp.dtype)
+        pos = (sil_at_samp * vis_on).sum()
         tot = vis_at_samp.sum()
-        neg = ((1 - sil_at_samp) * (vis_at_samp > 0)).sum()
+        neg = ((1 - sil_at_samp) * vis_on).sum()
         wt = 0.5 * (tot / pos) * sil_at_samp + 0.5 * (tot / neg) * (1 - sil_at_samp)
         ok = (sil_at_samp.sum() > 0) & ((1 - sil_at_samp).sum() > 0)
         sil_balance_wt = torch.where(ok, wt, torch.ones_like(wt))
     sil_loss_samp = (sil_coarse[..., None] - sil_at_samp).pow(2) * sil_balance_wt * vis_at_samp
     result["img_at_samp"], result["sil_at_samp"], result["vis_at_samp"] = img_at_samp, sil_at_samp, vis_at_samp
+    if flo_coarse is not None and "flo_at_samp" in rays:   # :545-553
+        flo_at_samp, cfd_at_samp = rays["flo_at_samp"], rays["cfd_at_samp"]
+        flo_loss_samp = (flo_coarse - flo_at_samp).pow(2).sum(-1)
+        sil_at_samp_flo = (sil_at_samp > 0) & (flo_valid == 1) & ~(cfd_at_samp == 0)
+        sel = sil_at_samp_flo.to(cfd_at_samp.dtype)
+        cnt = sel.sum()
+        mean_cfd = (cfd_at_samp * sel).sum() / cnt.clamp_min(1)
+        cfd = torch.where(cnt > 0, cfd_at_samp / mean_cfd, cfd_at_samp)
+        result["sil_at_samp_flo"] = sil_at_samp_flo
+        result["flo_at_samp"] = flo_at_samp
+        result["flo_loss_samp"] = flo_loss_samp[..., None] * cfd * sil_at_samp
     result["img_loss_samp"] = img_loss_samp * sil_at_samp
     result["sil_loss_samp"] = sil_loss_samp

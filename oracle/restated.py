@@ -492,3 +492,179 @@ def require_grads(prob):
         prob["rays"][k].requires_grad_(True)
         leaves["rays." + k] = prob["rays"][k]
     return leaves
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the default-flag training step -- nerf_feat / nerf_vis, feature matching,
+# key-point reprojection, the third warp with flow rendering, per-ray loss terms
+
+FEAT_SPEC = NerfSpec(5, 128, 63, 0, 16, (4,), True)
+VIS_SPEC = NerfSpec(5, 64, 63, 0, 1, (4,), True)
+
+
+def obj_to_cam(verts, Rmat, Tmat):
+    """geom_utils.py:567-581.  verts (N,S,3), Rmat (N,3,3), Tmat (N,3)."""
+    return verts.matmul(Rmat.transpose(1, 2)) + Tmat[:, None]
+
+
+def rtk_split(rtk_vec):
+    """rendering.py:437-441 / loss_utils.py:259-262: (N,21) -> R (N,3,3), T (N,3), K (N,4) = (fx, fy, px, py) recovered
+    from Kinv via Kmatinv + mat2K (geom_utils.py:612-652)."""
+    N = rtk_vec.shape[0]
+    Rmat = rtk_vec[:, 0:9].reshape(N, 3, 3)
+    Tmat = rtk_vec[:, 9:12]
+    Kinv = rtk_vec[:, 12:21].reshape(N, 3, 3)
+    k = torch.stack([Kinv[:, 0, 0], Kinv[:, 1, 1], Kinv[:, 0, 2], Kinv[:, 1, 2]], -1)      # mat2K(Kinv)
+    K = torch.stack([1.0 / k[:, 0], 1.0 / k[:, 1], -k[:, 2] / k[:, 0], -k[:, 3] / k[:, 1]], -1)  # mat2K(K2inv(k))
+    return Rmat, Tmat, K
+
+
+def pinhole_cam(verts, K):
+    """geom_utils.py:654-672.  verts (N,S,3), K (N,4)."""
+    x = verts[..., 0] * K[:, None, 0] + verts[..., 2] * K[:, None, 2]
+    y = verts[..., 1] * K[:, None, 1] + verts[..., 2] * K[:, None, 3]
+    z = verts[..., 2]
+    return torch.stack([x / (1e-6 + z), y / (1e-6 + z), z], -1)
+
+
+def project(xyz, rtk_vec):
+    Rmat, Tmat, K = rtk_split(rtk_vec)
+    return pinhole_cam(obj_to_cam(xyz, Rmat, Tmat), K)
+
+
+def vrender_flo(weights, xyz_target, xys, img_size):
+    """geom_utils.py:1704-1743."""
+    xy = xyz_target[..., :2]
+    invalid = (xyz_target[..., 2] < 1e-5) | (xy.norm(2, -1) > 2 * img_size)
+    w = torch.where(invalid, torch.zeros_like(weights), weights)
+    xy = torch.where(invalid[..., None], torch.zeros_like(xy), xy)
+    w = w / (1e-9 + w.sum(-1, keepdim=True))
+    flo = (w[..., None] * (xy - xys[:, None])).sum(-2) / img_size * 2
+    return flo, (invalid.sum(-1) == 0).to(weights.dtype)[..., None]
+
+
+def compute_pts_exp(pts_prob, pts):
+    """loss_utils.py:162-172."""
+    p = pts_prob / (1e-9 + pts_prob.sum(-1, keepdim=True))
+    return (pts * p[..., None]).sum(1)
+
+
+def feat_match(feat_sd, feats, bound, beta, n_freqs=10, alpha=10, grid_size=20, use_ot=True, noise=None,
+               spec=FEAT_SPEC):
+    """loss_utils.py:273-405 (use_corr off).  noise: the N(0,1) draw of :308 (1, grid^3, 3) or None (eval mode)."""
+    dt = feats.dtype
+    feats = F.normalize(feats, 2, -1)
+    ax = [torch.linspace(-float(b), float(b), grid_size, dtype=torch.float32).to(dt) for b in bound]
+    # np.meshgrid(pyd, pxd, pzd) (default 'xy' indexing) -> (y,x,z) columns, then reordered to (x,y,z): :296-298
+    gy, gx, gz = torch.meshgrid(ax[1], ax[0], ax[2], indexing="xy")
+    q = torch.stack([gx, gy, gz], -1).reshape(-1, 3)
+    if noise is not None:
+        q = q + noise.reshape(-1, 3).to(dt) * torch.as_tensor([float(b) for b in bound], dtype=dt)[None] * 0.05
+    vol = nerf_forward(feat_sd, spec, embed(q, n_freqs, alpha))
+    vol = F.normalize(vol, 2, -1)
+    cost = feats.matmul(vol.t())
+    if use_ot:
+        K = torch.exp(-(1.0 - cost) / 0.03)
+        n1, n2 = K.shape
+        a = torch.full((n1, 1), 1.0 / n1, dtype=dt)
+        for _ in range(20):
+            b = (1.0 / n2) / (K.t().matmul(a) + 1e-8)
+            a = (1.0 / n1) / (K.matmul(b) + 1e-8)
+        T = a * K * b.t()
+        prob = T / T.sum(1, keepdim=True)
+    else:
+        prob = (cost * (beta.abs() + 1e-9)).softmax(-1)
+    return prob.matmul(q)
+
+
+def visibility_loss(vis_sd, xyz_pos, w_pos, bound, neg_u, n_freqs=10, alpha=10, spec=VIS_SPEC):
+    """loss_utils.py:125-149.  neg_u: the U[0,1) draw of :138, (1, P, 3)."""
+    dt = xyz_pos.dtype
+    n = w_pos.numel()
+    b = torch.as_tensor([float(x) for x in bound], dtype=dt)[None, None]
+    xyz_neg = neg_u.to(dt) * 2 * b - b
+    neg = nerf_forward(vis_sd, spec, embed(xyz_neg, n_freqs, alpha))[..., 0]
+    pos = nerf_forward(vis_sd, spec, embed(xyz_pos.detach(), n_freqs, alpha))[..., 0]
+    return -(F.logsigmoid(pos) * w_pos.detach()).sum() / n + -F.logsigmoid(-neg).sum() * 0.1 / n
+
+
+def render_rays_full(prob, n_samples=128, noise=None, fm_noise=None, vis_u=None, xyz_freqs=10, dir_freqs=4, alpha=10,
+                     use_ot=True, is_training=True):
+    """rendering.py:19-579 at MoDA's default flags (dist_corresp, use_corresp, use_ot on; use_corr off), perturb = 0:
+    ``prob`` from moda_b200.synth.make_full_problem.  Random inputs of the reference's in-call draws are arguments."""
+    rays = prob["rays"]
+    img_size, bound = prob["img_size"], [float(b) for b in prob["obj_bound"]]
+    R = rays["rays_d"].shape[0]
+    d = rays["rays_d"]
+    dir_embedded = embed(d / d.norm(2, -1)[:, None], dir_freqs, alpha)
+    z = sample_depths(rays["near"], rays["far"], n_samples)
+    xyz_frame = rays["rays_o"].unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)
+    S = n_samples
+    bones_rst, skin_aux = prob["bones_rst"], prob["skin_aux"]
+    rest_code = prob["rest_pose_code"][0:1]
+    skin_sd = prob["nerf_skin"]
+    bones_dfm = bone_transform(bones_rst, rays["bone_rts"])
+    skin_bw = gauss_mlp_skinning(xyz_frame, xyz_freqs, alpha, bones_dfm, rays["time_embedded"][:, None], skin_sd, SKIN_SPEC,
+                                 skin_aux)
+    xyz, _ = neu_dbs(bones_rst, rays["bone_rts"], skin_bw, xyz_frame, backward=True)
+    skin_fw = gauss_mlp_skinning(xyz, xyz_freqs, alpha, bones_rst, rest_code, skin_sd, SKIN_SPEC, skin_aux)
+    xyz_cyc, _ = neu_dbs(bones_rst, rays["bone_rts"], skin_fw, xyz, backward=False)
+    cyc = (xyz_frame - xyz_cyc).norm(2, -1)
+    xyz_target, _ = neu_dbs(bones_rst, rays["bone_rts_target"], skin_fw, xyz, backward=False)
+    dir_rep = dir_embedded[:, None].expand(R, S, dir_embedded.shape[-1])
+    out = evaluate_mlp(prob["coarse"], COARSE_SPEC, xyz, xyz_freqs, alpha, dir_embedded=dir_rep, code=rays["env_code"],
+                       chunk=4096)
+    feat = evaluate_mlp(prob["nerf_feat"], FEAT_SPEC, xyz, xyz_freqs, alpha, chunk=4096)
+    rgb, depth, sil, weights, vis = composite(out[..., :3], out[..., 3], z, d, prob["coarse"]["beta"], noise=noise)
+    feat_rnd = (weights.unsqueeze(-1) * feat).sum(-2)
+    res = {"img_coarse": rgb, "depth_rnd": depth, "sil_coarse": sil}
+    # feature matching + reprojection (rendering.py:413-432)
+    pts_exp = compute_pts_exp(weights, xyz)
+    pts_pred = feat_match(prob["nerf_feat"], rays["feats_at_samp"], bound, prob["nerf_feat"]["beta"], xyz_freqs, alpha,
+                          use_ot=use_ot, noise=fm_noise if is_training else None)
+    res["pts_pred"], res["pts_exp"] = pts_pred, pts_exp
+    res["feat_err"] = (pts_pred - pts_exp).norm(2, -1)[:, None]
+    pp = pts_pred[:, None]
+    skin_kp = gauss_mlp_skinning(pp, xyz_freqs, alpha, bones_rst, rest_code, skin_sd, SKIN_SPEC, skin_aux)
+    kp, _ = neu_dbs(bones_rst, rays["bone_rts"], skin_kp, pp, backward=False)
+    xy_reproj = project(kp, rays["rtk_vec"])[..., :2]
+    res["proj_err"] = (rays["xys"][:, None] - xy_reproj).norm(2, -1) / img_size * 2
+    xyz_target = project(xyz_target, rays["rtk_vec_target"])
+    res["xyz_camera_vis"], res["xyz_canonical_vis"] = xyz_frame, xyz
+    res["pts_exp_vis"], res["pts_pred_vis"] = pts_exp, pts_pred
+    res["frame_cyc_dis"] = (cyc * weights.detach()).sum(-1)
+    if is_training:
+        res["vis_loss"] = visibility_loss(prob["nerf_vis"], xyz, vis, bound, vis_u, xyz_freqs, alpha)
+    flo, flo_valid = vrender_flo(weights, xyz_target, rays["xys"], img_size)
+    res["flo_coarse"], res["flo_valid"] = flo, flo_valid
+    # per-ray losses (rendering.py:516-578)
+    img_s, sil_s, vis_s = rays["img_at_samp"], rays["sil_at_samp"], rays["vis_at_samp"]
+    img_loss = (rgb - img_s).pow(2).mean(-1)[..., None]
+    wt = 1
+    if is_training and sil_s.sum() > 0 and (1 - sil_s).sum() > 0:
+        pos_wt = vis_s.sum() / sil_s[vis_s > 0].sum()
+        neg_wt = vis_s.sum() / (1 - sil_s[vis_s > 0]).sum()
+        wt = 0.5 * pos_wt * sil_s + 0.5 * neg_wt * (1 - sil_s)
+    sil_loss = (sil[..., None] - sil_s).pow(2) * wt * vis_s
+    flo_loss = (flo - rays["flo_at_samp"]).pow(2).sum(-1)
+    cfd = rays["cfd_at_samp"]
+    sel = (sil_s > 0) & (flo_valid == 1) & (cfd != 0)
+    if sel.sum() > 0:
+        cfd = cfd / cfd[sel].mean()
+    res.update(img_at_samp=img_s, sil_at_samp=sil_s, vis_at_samp=vis_s, sil_at_samp_flo=sel, flo_at_samp=rays["flo_at_samp"])
+    res["img_loss_samp"] = img_loss * sil_s
+    res["sil_loss_samp"] = sil_loss
+    res["flo_loss_samp"] = flo_loss[..., None] * cfd * sil_s
+    res["frnd_loss_samp"] = (F.normalize(feat_rnd, 2, -1) - rays["feats_at_samp"]).pow(2).mean(-1) * sil_s[..., 0]
+    return res
+
+
+FULL_LOSS_KEYS = ("img_loss_samp", "sil_loss_samp", "flo_loss_samp", "feat_err", "proj_err", "frnd_loss_samp", "frame_cyc_dis")
+
+
+def full_loss(res):
+    """The scalar of oracle/make_golden2.py:full_loss."""
+    loss = res["vis_loss"]
+    for k in FULL_LOSS_KEYS:
+        loss = loss + res[k].mean()
+    return loss

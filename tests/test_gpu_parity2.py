@@ -311,3 +311,46 @@ def test_two_rank_nccl_gradients_equal_single_rank():
     print("2-rank vs 1-rank flat gradient: max rel diff %.2e over %d values" % (e, single.numel()))
     dump_table("r02_two_rank_vs_single_rank", ["max |g2 - g1| / max |g1| = %.3e over %d values" % (e, single.numel())])
     assert e < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_default_flag_training_step_against_reference_golden(mode):
+    """SURVEY 8(f) rank 1 / VERDICT r1 missing #1-#2: a ``models`` dict built as nnutils/moda.py:271-348, 447-449 builds
+    it (coarse, bones, skin_aux, nerf_skin, rest_pose_code, nerf_vis, nerf_feat) and the ``rays`` of a paired-frame
+    training batch (rtk_vec[_target], bone_rts_target, feats_at_samp, *_at_samp) run through render_rays at the
+    reference's default flags (dist_corresp, use_corresp, use_ot).  Every result key and every gradient against the
+    real reference (fp64 run as truth, fp32 run for the slack), in-call random draws replayed."""
+    from moda_b200 import config, synth, models as MM
+    from moda_b200.rendering import render_rays
+    from oracle import restated as O
+    config.set_precision(mode)
+    nets = ("coarse", "nerf_skin", "nerf_vis", "nerf_feat")
+    prob, g = fixture_problem("render_full_n16_fp32.npz", nets=nets)
+    g64 = load_npz("render_full_n16_fp64.npz")
+    models, emb, rays = MM.build_full_models(prob, DEV)
+    for m in nets:
+        models[m].train()
+    with ReplayRng(g, DEV) as tape:
+        res = render_rays(models, emb, rays, N_samples=128, perturb=0, noise_std=0, chunk=32768,
+                          obj_bound=prob["obj_bound"].numpy(), img_size=512, opts=synth.full_opts())
+    assert tape.i == len(tape.draws) == 3, "same random draws, in the reference's order"
+    assert set(res) == {k[4:] for k in g if k.startswith("out.")} - {"loss"}
+    loss = O.full_loss(res)
+    loss.backward()
+    tab = []
+    for k in sorted(res):
+        ref = np.asarray(g64["out." + k], dtype=np.float64).reshape(tuple(res[k].shape))
+        e = max_abs(res[k].double() if res[k].dtype != torch.bool else res[k].double(), ref)
+        scale = float(np.abs(ref).max())
+        tab.append("%-20s max abs err %.2e (|ref|max %.2e)" % (k, e, scale))
+        # rendered values 1e-3 absolute; pixel-unit quantities (flow / reprojection in normalised image units of
+        # O(1), feature-matched points) relative to their scale
+        assert e <= 1e-3 * max(1.0, scale), tab[-1]
+    print("\n".join(tab))
+    dump_table("r02_full_step_outputs_%s" % mode, tab)
+    assert abs(float(loss.detach()) - float(g64["out.loss"])) < 2e-3
+    got = _gpu_grads(models, rays, nets=nets)
+    truth = {k[5:]: torch.from_numpy(g64[k]) for k in g64 if k.startswith("grad.")}
+    ref32 = {k[5:]: torch.from_numpy(g[k]) for k in g if k.startswith("grad.")}
+    got["skin_aux"], truth["skin_aux"], ref32["skin_aux"] = got["skin_aux"][:1], truth["skin_aux"][:1], ref32["skin_aux"][:1]
+    _check_grads("r02_full_step_grads_%s" % mode, got, truth, ref32, bar=GRAD_BAR if mode == "fp16" else 1e-3)

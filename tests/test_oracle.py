@@ -112,3 +112,47 @@ def test_oracle_against_live_reference_random_seed():
         res = O.render_rays(prob, n_samples=64, perturb=1.0, perturb_rand=jitter)
     for k in ("img_coarse", "depth_rnd", "sil_coarse", "frame_cyc_dis", "xyz_canonical_vis"):
         assert max_abs(res[k], res_ref[k]) < 2e-6, k
+
+
+def test_restated_full_default_flag_step_against_reference_golden():
+    """Round 2: the default-flag training step (nerf_feat + feat_match with Sinkhorn OT + key-point reprojection +
+    third warp with flow rendering + nerf_vis loss + per-ray terms), oracle vs the real reference's outputs and
+    gradients (fixture written by oracle/make_golden2.py, in-call random draws replayed)."""
+    import numpy as np
+    from tests.util import fixture_problem
+    nets = ("coarse", "nerf_skin", "nerf_vis", "nerf_feat")
+    for name, dt, otol, gtol in (("render_full_n16_fp32.npz", torch.float32, 2e-5, 1e-3),
+                                 ("render_full_n16_fp64.npz", torch.float64, 5e-6, 5e-5)):
+        prob, g = fixture_problem(name, nets=nets, dtype=dt)
+        g32 = load_npz("render_full_n16_fp32.npz")
+        prob["img_size"] = 512
+        leaves = {}
+        for net in nets:
+            for k, v in prob[net].items():
+                leaves[net + "." + k] = v.requires_grad_(True)
+        for k in ("bones_rst", "skin_aux", "rest_pose_code"):
+            leaves[k] = prob[k].requires_grad_(True)
+        for k in ("bone_rts", "time_embedded", "env_code", "rays_o", "rays_d", "bone_rts_target"):
+            leaves["rays." + k] = prob["rays"][k].requires_grad_(True)
+        t = lambda k: torch.from_numpy(g32[k]).to(dt)
+        res = O.render_rays_full(prob, noise=None, fm_noise=t("rng.1"), vis_u=t("rng.2"))
+        loss = O.full_loss(res)
+        loss.backward()
+        assert abs(float(loss) - float(g["out.loss"])) < otol
+        keys = [k for k in g if k.startswith("out.") and k[4:] in res]
+        assert len(keys) >= 20
+        for k in keys:
+            got = res[k[4:]].detach().double()
+            assert max_abs(got, np.asarray(g[k], dtype=np.float64).reshape(tuple(got.shape))) < otol, k
+        n = 0
+        for k in g:
+            if not k.startswith("grad."):
+                continue
+            gr = leaves[k[5:]].grad
+            gr = torch.zeros_like(leaves[k[5:]]) if gr is None else gr
+            if float(np.abs(g[k]).max()) == 0:
+                assert float(gr.abs().max()) == 0, k
+            else:
+                assert rel_err(gr, g[k]) < gtol, (k, rel_err(gr, g[k]))
+            n += 1
+        assert n >= 60
