@@ -187,11 +187,12 @@ def golden_full(ref, name, dtype=torch.float32, replay=None):
     loss = full_loss(res)
     loss.backward()
     out = {}
-    out.update(flat("in.rays.", prob["rays"]))
-    for k in ("bones_rst", "skin_aux", "rest_pose_code", "obj_bound"):
-        out["in." + k] = prob[k].numpy()
-    for net in ("coarse", "nerf_skin", "nerf_vis", "nerf_feat"):
-        out.update(flat("net.%s." % net, prob[net]))
+    if replay is None:   # inputs, weights and draws live in the fp32 file only (the fp64 run replays them)
+        out.update(flat("in.rays.", prob["rays"]))
+        for k in ("bones_rst", "skin_aux", "rest_pose_code", "obj_bound"):
+            out["in." + k] = prob[k].numpy()
+        for net in ("coarse", "nerf_skin", "nerf_vis", "nerf_feat"):
+            out.update(flat("net.%s." % net, prob[net]))
     for k, v in res.items():
         out["out." + k] = v.detach().numpy()
     out["out.loss"] = loss.detach().numpy()

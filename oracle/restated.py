@@ -65,6 +65,8 @@ class NerfSpec:
 
 COARSE_SPEC = NerfSpec(8, 256, 63, 27 + 64, 3, (4,), False)
 SKIN_SPEC = NerfSpec(5, 64, 63 + 128, 0, 25, (4,), True)
+FEAT_SPEC = NerfSpec(5, 128, 63, 0, 16, (4,), True)   # nerf_feat, moda.py:447-449
+VIS_SPEC = NerfSpec(5, 64, 63, 0, 1, (4,), True)      # nerf_vis, moda.py:344-348
 
 
 def nerf_forward(sd, spec, x, sigma_only=False):
@@ -450,8 +452,9 @@ def skin_warp_roundtrip(bones_rst, bone_rts, skin_aux, xyz):
 
 
 def density_grid(coarse_sd, grid_size, bound, spec=COARSE_SPEC, n_freqs=10, alpha=10, chunk=32768,
-                 x_range=None):
-    """train_utils.py:1377-1404: sigma on a G^3 lattice, (x,y,z) C-order, 32768-point chunks."""
+                 x_range=None, vis_sd=None, symm_shape=False):
+    """train_utils.py:1377-1425: sigma on a G^3 lattice, (x,y,z) C-order, 32768-point chunks; with ``vis_sd`` the
+    visibility pass (:1407-1425: density -1 where sigmoid(nerf_vis) < 0.5), with ``symm_shape`` evaluation at |x| (:1398)."""
     G = grid_size
     dt = coarse_sd["sigma.weight"].dtype
     ax = [torch.linspace(-float(b), float(b), G, dtype=dt) for b in bound]
@@ -459,8 +462,14 @@ def density_grid(coarse_sd, grid_size, bound, spec=COARSE_SPEC, n_freqs=10, alph
     pts = torch.stack(torch.meshgrid(xs, ax[1], ax[2], indexing="ij"), -1).reshape(-1, 3)
     out = []
     for i in range(0, pts.shape[0], chunk):
-        e = embed(pts[i:i + chunk], n_freqs, alpha)
-        out.append(nerf_forward(coarse_sd, spec, e, sigma_only=True))
+        q = pts[i:i + chunk]
+        if symm_shape:
+            q = torch.cat([q[:, :1].abs(), q[:, 1:]], -1)
+        sig = nerf_forward(coarse_sd, spec, embed(q, n_freqs, alpha), sigma_only=True)
+        if vis_sd is not None:
+            vis = nerf_forward(vis_sd, VIS_SPEC, embed(pts[i:i + chunk], n_freqs, alpha))[..., 0].sigmoid()
+            sig = torch.where(vis[:, None] < 0.5, torch.full_like(sig, -1.0), sig)
+        out.append(sig)
     return torch.cat(out, 0).reshape(len(xs), G, G)
 
 
@@ -497,10 +506,6 @@ def require_grads(prob):
 # ------------------------------------------------------------------------------------------------
 # round 2: the default-flag training step -- nerf_feat / nerf_vis, feature matching,
 # key-point reprojection, the third warp with flow rendering, per-ray loss terms
-
-FEAT_SPEC = NerfSpec(5, 128, 63, 0, 16, (4,), True)
-VIS_SPEC = NerfSpec(5, 64, 63, 0, 1, (4,), True)
-
 
 def obj_to_cam(verts, Rmat, Tmat):
     """geom_utils.py:567-581.  verts (N,S,3), Rmat (N,3,3), Tmat (N,3)."""

@@ -123,8 +123,8 @@ def test_restated_full_default_flag_step_against_reference_golden():
     nets = ("coarse", "nerf_skin", "nerf_vis", "nerf_feat")
     for name, dt, otol, gtol in (("render_full_n16_fp32.npz", torch.float32, 2e-5, 1e-3),
                                  ("render_full_n16_fp64.npz", torch.float64, 5e-6, 5e-5)):
-        prob, g = fixture_problem(name, nets=nets, dtype=dt)
-        g32 = load_npz("render_full_n16_fp32.npz")
+        prob, g32 = fixture_problem("render_full_n16_fp32.npz", nets=nets, dtype=dt)
+        g = load_npz(name)
         prob["img_size"] = 512
         leaves = {}
         for net in nets:
