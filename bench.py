@@ -203,7 +203,7 @@ def run_ours(args):
     models["nerf_skin"].train()
     opts = synth.default_opts()
     flat = FlatParams(MM.parameters_of(models))
-    optim = torch.optim.AdamW([flat.flat], lr=1e-4, fused=True)
+    optim = torch.optim.AdamW([flat.flat], lr=1e-4, fused=True, capturable=True)
     ray_keys = ("rays_o", "rays_d", "near", "far", "time_embedded", "bone_rts", "env_code")
     host = {k: prob["rays"][k].pin_memory() for k in ray_keys}
     h2d_bytes = sum(v.numel() * 4 for v in host.values())
@@ -277,6 +277,43 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, clocks
 
+    def capture(rays_static):
+        """The whole step (zero-grad, forward, backward, gradient all-reduce, AdamW) as ONE CUDA graph over static
+        input buffers: ~180 C-ABI launches + ~100 small framework kernels replayed with a single launch call.  Every
+        rank captures (the all-reduce is part of the graph).  Returns (graph, loss tensor, launches per step) or the
+        reason why capture was not possible (the eager path is then timed instead)."""
+        try:
+            barrier()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.LAUNCHES
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss = step(rays_static)
+            n = _lib.LAUNCHES - n0
+            for _ in range(2):
+                g.replay()
+            barrier()
+            if not bool(torch.isfinite(loss.detach()).all()):
+                return "graph replay produced a non-finite loss"
+            return g, loss, n
+        except Exception as e:  # noqa: BLE001 -- any capture failure selects the eager path
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            return "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
+
+    def agree(ok):
+        """Capture is a collective decision: every rank replays, or none does."""
+        t = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t))
+
+    use_graph = args.graph != "off"
+    try:   # the autograd nodes of the flat parameter views were created on the default stream: expected, not a problem
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except Exception:
+        pass
     # BASELINE configs[2] (strong scaling): the SAME 8192-ray global batch sharded N ways, measured next to the weak-
     # scaling headline (8192 rays per GPU) in the same run
     strong = None
@@ -288,10 +325,20 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             step(sub)
         ms_strong, _ = timed(lambda: step(sub), args.steps)
-        strong = {"global_rays": R, "rays_per_gpu": Rs, "ms_per_step": round(ms_strong, 3),
-                  "value": round(R / (ms_strong * 1e-3), 1), "unit": "rays/s",
-                  "note": "same step on the 8192-ray global batch sharded over the ranks (BASELINE configs[2]); "
-                          "efficiency vs N=1 = value / (N=1 value of the headline metric)"}
+        strong = {"global_rays": R, "rays_per_gpu": Rs, "ms_per_step_eager": round(ms_strong, 3), "cuda_graph": False}
+        if use_graph:
+            cap = capture(sub)
+            if agree(not isinstance(cap, str)):
+                ms_g, _ = timed(cap[0].replay, args.steps)
+                strong["cuda_graph"] = True
+                ms_strong = min(ms_strong, ms_g)
+                strong["ms_per_step_graph"] = round(ms_g, 3)
+            else:
+                strong["cuda_graph_unavailable"] = cap if isinstance(cap, str) else "another rank could not capture"
+            del cap
+        strong.update({"ms_per_step": round(ms_strong, 3), "value": round(R / (ms_strong * 1e-3), 1), "unit": "rays/s",
+                       "note": "same step on the 8192-ray global batch sharded over the ranks (BASELINE configs[2]); "
+                               "efficiency vs N=1 = value / (N=1 value of the headline metric)"})
     for _ in range(max(args.warmup, 3)):
         step(rays)
     launches0 = _lib.LAUNCHES
@@ -300,6 +347,46 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    graph_info = {"used": False}
+    if use_graph:
+        # static input set for the graph; the e2e variant copies each step's host rays into a staging set on the copy
+        # stream (as above) and from there into the static set with device-to-device copies on the compute stream
+        static = {k: (rays[k].detach().clone().requires_grad_(rays[k].requires_grad) if torch.is_tensor(rays[k]) else rays[k])
+                  for k in rays}
+        cap = capture(static)
+        if agree(not isinstance(cap, str)):
+            g, g_loss, g_launches = cap
+            ms_g, clocks_g = timed(g.replay, args.steps, ClockSampler(local) if rank == 0 else None)
+
+            def step_e2e_graph():
+                slot = pipe["i"] & 1
+                if not pipe["primed"]:
+                    issue_copy(slot)
+                    pipe["primed"] = True
+                issue_copy(slot ^ 1)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ready_ev[slot])
+                with torch.no_grad():
+                    for k in ray_keys:
+                        static[k].copy_(bufs[slot][k], non_blocking=True)
+                free_ev[slot].record(cur)
+                g.replay()
+                loss_host.copy_(g_loss.detach().reshape(1), non_blocking=True)
+                pipe["i"] += 1
+
+            pipe["primed"] = False
+            for _ in range(2):
+                step_e2e_graph()
+            ms_e2e_g, _ = timed(step_e2e_graph, args.steps)
+            graph_info = {"used": True, "ms_per_step_eager": round(ms_step, 3), "ms_per_step_graph": round(ms_g, 3),
+                          "e2e_ms_per_step_eager": round(ms_e2e, 3), "e2e_ms_per_step_graph": round(ms_e2e_g, 3),
+                          "kernels": "the step captured once as a CUDA graph (zero-grad, forward, backward, NCCL "
+                                     "all-reduce, AdamW) and replayed; same kernels, same work"}
+            if ms_g < ms_step:
+                ms_step, clocks, launches = ms_g, clocks_g, g_launches
+            ms_e2e = min(ms_e2e, ms_e2e_g)
+        else:
+            graph_info = {"used": False, "unavailable": cap if isinstance(cap, str) else "another rank could not capture"}
 
     # per-kernel device time of one step (CUDA events around every C-ABI call on the launching stream)
     roof = None
@@ -377,10 +464,24 @@ def run_ours(args):
                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
                        "input_pipeline": "pinned host rays -> double-buffered H2D prefetch on a copy stream, one copy set per step"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-               "strong_scaling": strong, "extra": extra}
+               "strong_scaling": strong, "cuda_graph": graph_info, "extra": extra}
         _emit(out)
+    _finish(world)
+
+
+def _finish(world):
+    """Leaves the process without tearing NCCL down: destroying a process group while captured graphs that contain its
+    collectives are still alive can block forever (seen at N = 2), and nothing is left to do after the JSON line."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 def cpu_baseline(sample_rays=512, repeats=2):
@@ -693,6 +794,8 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--cpu-rays", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"],
+                    help="auto: also time the step replayed as one CUDA graph and report the faster of the two")
     ap.add_argument("--no-extra", action="store_true", help="skip the DQ-skinning / density-grid figures of the default line")
     ap.add_argument("--workload", default="train", choices=["train", "dqs", "grid"],
                     help="train: the headline training step (default); dqs / grid: BASELINE configs[3] / configs[4]")
