@@ -194,9 +194,13 @@ __device__ __forceinline__ void trace_rec(long long* tr, int ev, int a, int b, i
 #define MODA_TR(on, ev, a, b) do { } while (0)   // product build: no trace code in the hot loops (tools/build_variant.sh trace -DMODA_CHAIN_TRACE)
 #endif
 
+// fp32 pair -> packed fp16 pair, round to nearest, SATURATING to +-65504: an overflowing gradient in the adjoint chains
+// (fp16 under a single power-of-two loss scale) is clamped instead of turning into inf and, one layer later, NaN in
+// the flat gradient buffer that is all-reduced to every rank
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));   // d = {hi: first source, lo: second}
+  return r;
 }
 __device__ __forceinline__ uint32_t pack2_lo(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);

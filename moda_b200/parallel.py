@@ -43,10 +43,30 @@ class FlatParams:
         self.numel = n
 
     def zero_grad(self):
+        """Zeroes the flat gradient buffer in place.  Do NOT use ``optimizer.zero_grad()`` (set_to_none=True drops the
+        views the kernels accumulate into): ``check()`` below catches that instead of silently training on stale
+        gradients."""
         self.grad.zero_()
+
+    optimizer_zero_grad = zero_grad
+
+    def check(self):
+        """The fused MLP backward adds straight into ``t.grad`` (a view of ``self.grad``) and hands autograd None, which
+        is only correct while those views are intact.  Raises if something (optimizer.zero_grad(set_to_none=True),
+        module.zero_grad(), a fresh .grad assignment) replaced them."""
+        if self.flat.grad is not self.grad:
+            raise RuntimeError("FlatParams: flat.grad was replaced (optimizer.zero_grad(set_to_none=True)?); use "
+                               "FlatParams.zero_grad() so that the parameter .grad views stay attached")
+        lo, hi = self.grad.data_ptr(), self.grad.data_ptr() + 4 * self.numel
+        for t, off in zip(self.tensors, self.offsets):
+            g = t.grad
+            if g is None or g.data_ptr() != lo + 4 * off or not (lo <= g.data_ptr() < hi):
+                raise RuntimeError("FlatParams: a parameter's .grad no longer aliases the flat gradient buffer "
+                                   "(module.zero_grad() / set_to_none?); use FlatParams.zero_grad()")
 
     def allreduce(self, scale=None):
         """Sum of the per-rank gradients (each rank scales its loss by its share of the global batch)."""
+        self.check()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
         if scale is not None:

@@ -82,3 +82,23 @@ def test_shard_rays_ragged():
     parts = [shard_rays(rays, r, 4)["x"] for r in range(4)]
     assert torch.equal(torch.cat(parts), rays["x"])
     assert [p.numel() for p in parts] == [3, 3, 3, 1]
+
+
+def test_flat_params_refuses_detached_gradient_views():
+    """the fused backward accumulates straight into the .grad views of the flat buffer; dropping those views
+    (optimizer.zero_grad(set_to_none=True), module.zero_grad()) must raise instead of silently freezing training."""
+    import pytest
+    from moda_b200.parallel import FlatParams
+    a, b = torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7))
+    fp = FlatParams([a, b])
+    fp.check()
+    opt = torch.optim.SGD([fp.flat], lr=0.1)
+    fp.zero_grad()
+    fp.check()
+    opt.zero_grad()          # set_to_none=True by default: flat.grad becomes None
+    with pytest.raises(RuntimeError):
+        fp.allreduce()
+    fp2 = FlatParams([torch.nn.Parameter(torch.randn(4))])
+    fp2.tensors[0].grad = None
+    with pytest.raises(RuntimeError):
+        fp2.check()
