@@ -677,6 +677,67 @@ def measure_dqs(args, dev, with_cpu=True, steps=None):
             "cpu_baseline": cpu}
 
 
+FULL_LOSS_KEYS = ("img_loss_samp", "sil_loss_samp", "flo_loss_samp", "feat_err", "proj_err", "frnd_loss_samp", "frame_cyc_dis")
+
+
+def measure_full(args, dev, steps=None):
+    """The DEFAULT-flag MoDA training step: core path + nerf_feat feature rendering + Sinkhorn
+    feature matching + key-point reprojection + third warp with flow rendering + nerf_vis loss + per-ray terms
+    (nnutils/moda.py:344-348, 447-449; rendering.py:405-578), 8192 rays x 128 samples, fwd + bwd + AdamW, one GPU."""
+    from moda_b200 import synth, models as MM, _lib
+    from moda_b200.parallel import FlatParams
+    from moda_b200.rendering import render_rays
+    steps = steps or args.steps
+    R = args.rays
+    prob = synth.make_full_problem(R, seed=0)
+    models, emb, rays = MM.build_full_models(prob, dev)
+    for k in ("coarse", "nerf_skin", "nerf_feat", "nerf_vis"):
+        models[k].train()
+    opts = synth.full_opts()
+    flat = FlatParams(MM.parameters_of(models))
+    optim = torch.optim.AdamW([flat.flat], lr=1e-4, fused=True)
+    bound = prob["obj_bound"].numpy()
+
+    def step():
+        flat.zero_grad()
+        res = render_rays(models, emb, rays, N_samples=SAMPLES, perturb=1.0, noise_std=0.0, chunk=32768, obj_bound=bound,
+                          img_size=prob["img_size"], opts=opts)
+        loss = res["vis_loss"]
+        for k in FULL_LOSS_KEYS:
+            loss = loss + res[k].mean()
+        loss.backward()
+        flat.allreduce()
+        optim.step()
+        return loss
+
+    sampler = ClockSampler(dev.index or 0)
+    n0 = _lib.LAUNCHES
+    step()
+    launches = _lib.LAUNCHES - n0
+    sampler.start()
+    ms = _event_ms(step, steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    _lib.PROFILE = {}
+    step()
+    summ = _lib.profile_summary()
+    _lib.PROFILE = None
+    loss = float(step().detach())
+    return {"metric": "train rays/s, default-flag step (128 samp/ray)", "value": round(R / (ms * 1e-3), 1), "unit": "rays/s",
+            "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "data": "synthetic", "loss_finite": bool(loss == loss and abs(loss) < 1e30), "gpu_launches": int(launches),
+            "config": {"workload": "default-flag MoDA step: %d rays x %d samples, %d bones, nerf_coarse + nerf_skin + nerf_feat "
+                                   "(5x128) + nerf_vis (5x64), Sinkhorn feature matching on a 20^3 lattice, reprojection, "
+                                   "third warp + flow rendering, AdamW" % (R, SAMPLES, BONES)},
+            "clocks": clocks,
+            "per_entry_ms": {k: round(v[1], 3) for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])[:12]}}
+
+
+def run_full(args):
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _emit(measure_full(args, dev))
+
+
 def run_dqs(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
@@ -797,7 +858,7 @@ def main():
     ap.add_argument("--graph", default="auto", choices=["auto", "off"],
                     help="auto: also time the step replayed as one CUDA graph and report the faster of the two")
     ap.add_argument("--no-extra", action="store_true", help="skip the DQ-skinning / density-grid figures of the default line")
-    ap.add_argument("--workload", default="train", choices=["train", "dqs", "grid"],
+    ap.add_argument("--workload", default="train", choices=["train", "dqs", "grid", "full"],
                     help="train: the headline training step (default); dqs / grid: BASELINE configs[3] / configs[4]")
     ap.add_argument("--dqs-rays", type=int, default=131072)
     ap.add_argument("--grid", type=int, default=256)
@@ -807,6 +868,8 @@ def main():
         return run_dqs(args)
     if args.workload == "grid":
         return run_grid(args)
+    if args.workload == "full":
+        return run_full(args)
     if args.impl == "reference":
         args.steps = min(args.steps, 3)
         run_reference(args)

@@ -6,7 +6,7 @@ SURVEY.md section 8(f).
 """
 import torch
 
-from . import chain_tc, config, skin_tc, trunk_tc
+from . import chain_tc, config, generic_tc, skin_tc, trunk_tc
 from .ops import (BoneTransformFn, SkinWarpFn, SEG_DENSE, SEG_BCAST, SEG_PE)
 
 
@@ -98,6 +98,12 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
             and embed_xyz.N_freqs == 10 and trunk_tc.supported(model, model.in_channels_dir)
             and not (torch.is_grad_enabled() and (pts2.requires_grad or any(p.requires_grad for p in model.parameters())))):
         return chain_tc.trunk_sigma(pts2, win, model.param_list()).reshape(Bn, nbins, 1)
+    # tensor-core path for the auxiliary raw-feature MLPs on a plain PE(xyz) input (nerf_feat, nerf_vis)
+    if (config.precision == "fp16" and not sigma_only and len(segs) == 1 and segs[0][0] == SEG_PE
+            and generic_tc.supported(model, embed_xyz, k)):
+        skip = model.skips[0] if model.skips else None
+        out = generic_tc.GenericTcFn.apply(pts2, win, torch.is_grad_enabled(), model.D, model.W, skip, *model.param_list())
+        return out.reshape(Bn, nbins, 32)[..., :model.out_channels]
     xyz_segs, dir_segs = _split_segments(segs, cx)
     if len(xyz_segs) > 2 or len(dir_segs) > 2:
         raise NotImplementedError("more than two column segments per input group")

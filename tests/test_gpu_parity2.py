@@ -354,3 +354,40 @@ def test_default_flag_training_step_against_reference_golden(mode):
     ref32 = {k[5:]: torch.from_numpy(g[k]) for k in g if k.startswith("grad.")}
     got["skin_aux"], truth["skin_aux"], ref32["skin_aux"] = got["skin_aux"][:1], truth["skin_aux"][:1], ref32["skin_aux"][:1]
     _check_grads("r02_full_step_grads_%s" % mode, got, truth, ref32, bar=GRAD_BAR if mode == "fp16" else 1e-3)
+
+
+def test_generic_tensor_core_mlp_matches_fp32_simt():
+    """moda_b200/generic_tc.py (nerf_feat 5x128 -> 16, nerf_vis 5x64 -> 1 on tcgen05, layer by layer) against the exact
+    fp32 SIMT path: values and every gradient at fp16-operand level.  Sizes include a ragged last tile."""
+    from moda_b200 import config, geom_utils as G, synth
+    from moda_b200.nerf import Embedding, NeRF
+    prob = synth.make_full_problem(4, seed=1)
+    emb = Embedding(3, 10, alpha=10)
+    nrel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
+    for name, kw in (("nerf_feat", dict(D=5, W=128, out_channels=16, init_beta=1.)), ("nerf_vis", dict(D=5, W=64, out_channels=1))):
+        model = NeRF(in_channels_xyz=63, in_channels_dir=0, raw_feat=True, **kw)
+        model.load_state_dict(prob[name])
+        model = model.to(DEV)
+        oc = kw["out_channels"]
+        for R, S in ((5, 128), (301, 100)):
+            gen = torch.Generator().manual_seed(3)
+            pts0 = (torch.rand(R, S, 3, generator=gen) * 0.6 - 0.3).to(DEV)
+            gout = torch.randn(R, S, oc, generator=gen).to(DEV) * 1e-3
+            outs = {}
+            for mode in ("fp32", "fp16"):
+                config.set_precision(mode)
+                model.zero_grad()
+                p = pts0.clone().requires_grad_(True)
+                out = G.evaluate_mlp(model, p, embed_xyz=emb)
+                assert out.shape == (R, S, oc)
+                (out * gout).sum().backward()
+                outs[mode] = (out.detach(), p.grad, {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None})
+                with torch.no_grad():
+                    assert torch.equal(G.evaluate_mlp(model, pts0, embed_xyz=emb), out.detach()) or mode == "fp32"
+            a, b = outs["fp32"], outs["fp16"]
+            scale = float(a[0].abs().max())
+            assert max_abs(b[0], a[0]) < 5e-3 * max(scale, 1.0), (name, R, max_abs(b[0], a[0]), scale)
+            assert nrel(b[1], a[1]) < 6e-2, (name, "gpts", nrel(b[1], a[1]))
+            assert set(a[2]) == set(b[2]), (name, set(a[2]) ^ set(b[2]))
+            worst = max((nrel(b[2][k], a[2][k]), k) for k in a[2])
+            assert worst[0] < 6e-2, (name, R, worst)

@@ -156,3 +156,36 @@ def test_restated_full_default_flag_step_against_reference_golden():
                 assert rel_err(gr, g[k]) < gtol, (k, rel_err(gr, g[k]))
             n += 1
         assert n >= 60
+
+
+def test_analytic_sinkhorn_adjoint_equals_autograd_through_the_reference_loop():
+    """moda_b200.loss_utils.SinkhornMatchFn (device-agnostic tensor code) against autograd through the loop of
+    loss_utils.py:347-386, fp64."""
+    from moda_b200.loss_utils import SinkhornMatchFn
+    torch.manual_seed(0)
+    dt = torch.float64
+    N, M = 37, 211
+    mk = lambda *s: torch.randn(*s, dtype=dt)
+    Fn = torch.nn.functional.normalize(mk(N, 16), 2, -1)
+    Vn = torch.nn.functional.normalize(mk(M, 16), 2, -1)
+    Q0 = mk(M, 3)
+
+    def reference(F_, V, Q):
+        K = torch.exp(-(1.0 - (F_ @ V.t())[None]) / 0.03)
+        a = torch.ones(1, N, 1, dtype=dt) / N
+        p1, p2 = torch.ones(1, N, 1, dtype=dt) / N, torch.ones(1, M, 1, dtype=dt) / M
+        for _ in range(20):
+            b = p2 / (torch.bmm(K.transpose(1, 2), a) + 1e-8)
+            a = p1 / (torch.bmm(K, b) + 1e-8)
+        T = a * K * b.transpose(1, 2)
+        return ((T / T.sum(2, keepdim=True))[0][..., None] * Q[None]).sum(1)
+
+    g = mk(N, 3)
+    outs = []
+    for fn in (reference, SinkhornMatchFn.apply):
+        F_, V, Q = (t.clone().requires_grad_(True) for t in (Fn, Vn, Q0))
+        out = fn(F_, V, Q)
+        out.backward(g)
+        outs.append((out.detach(), F_.grad, V.grad, Q.grad))
+    for a, b in zip(*outs):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-12
