@@ -161,6 +161,12 @@ int moda_tc_linear(const void* A1, int lda1, int K1, const void* A2, int lda2, i
 int moda_tc_wgrad(const void* dY, int ldy, int N, const void* X, int ldx, int K, int M, float* dW, int ldw,
                   int n_valid, int k_valid, const float* oscale, float* dbias /* NULL, or (N) += colsum(dY) */,
                   cudaStream_t stream);
+/* njobs (<= 9) weight gradients of ONE shape (N, K) over the same M rows in one launch (HOST arrays of length njobs;
+ * dbias[j] may be NULL): the grid is partitioned among the jobs, which removes the ramp-up / tail of a launch per layer
+ * and most of the red.global traffic of the final flush.  (N, K) in {256,128,64} x {256,128,64} as instantiated. */
+int moda_tc_wgrad_multi(int njobs, const void* const* dY, const int* ldy, const void* const* X, const int* ldx,
+                        float* const* dW, const int* ldw, const int* n_valid, const int* k_valid, float* const* dbias,
+                        int N, int K, int M, const float* oscale, cudaStream_t stream);
 /* fp16 operand staging for the trunk: positional encoding of (P,3) points into (P,64) [63 channels + zero pad]
  * (Embedding.forward, nerf.py:35-75) and its adjoint (gxyz (=|+=) (*inv_scale) J^T g16) */
 int moda_pe16_fwd(const float* xyz, void* out16, void* out16lo /* NULL, or low half of the split pair */, int ldo,

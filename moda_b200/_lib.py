@@ -49,6 +49,7 @@ SIGNATURES = {
     "moda_tc_linear": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p,
                        c_p, c_i, c_i, c_p, c_i, c_p, c_p],
     "moda_tc_wgrad": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "moda_tc_wgrad_multi": [c_i, c_pp, c_ip, c_pp, c_ip, c_pp, c_ip, c_ip, c_ip, c_pp, c_i, c_i, c_i, c_p, c_p],
     "moda_tc_linear_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_i,
                              c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p],
     "moda_tc_wgrad_split": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],

@@ -47,6 +47,17 @@ def _wgrad(dY, N, X, K, M, dW, col0, n_valid, k_valid, oscale, dbias=None):
          n_valid, k_valid, ptr(oscale), ptr(dbias), stream())
 
 
+def _wgrad_multi(jobs, N, K, M, oscale):
+    """jobs: list of (dY, X, dW, col0, n_valid, k_valid, dbias | None) sharing the shape (N, K): ONE launch
+    (moda_tc_wgrad_multi) whose grid is partitioned among them."""
+    n = len(jobs)
+    P_, I_ = ctypes.c_void_p * n, ctypes.c_int * n
+    call("moda_tc_wgrad_multi", n, P_(*[ptr(j[0]) for j in jobs]), I_(*[j[0].stride(0) for j in jobs]),
+         P_(*[ptr(j[1]) for j in jobs]), I_(*[j[1].stride(0) for j in jobs]),
+         P_(*[ptr(j[2]) + 4 * j[3] for j in jobs]), I_(*[j[2].stride(0) for j in jobs]), I_(*[j[4] for j in jobs]),
+         I_(*[j[5] for j in jobs]), P_(*[ptr(j[6]) if j[6] is not None else None for j in jobs]), N, K, M, ptr(oscale), stream())
+
+
 def _al16(t):
     """The chain kernels read head vectors with 128-bit loads: a parameter that is a view at an odd offset of some
     larger buffer is copied (a few hundred floats) instead of being refused."""
@@ -274,14 +285,13 @@ class TrunkChainFn(torch.autograd.Function):
         wa, _ = _win_array(win)
         with _Alternate(dev) as alt:   # the launches below are independent of each other
             alt.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
-            alt.run(_wgrad, d_fin, 256, H[7], 256, P, g[16], 0, 256, 256, isc, dbias=g[17])
+            # the eight 256 x 256 weight gradients (final layer, layers 8..6, the hidden part of layer 5, layers 4..2) in
+            # ONE launch, the two PE-input ones (layers 5 and 1) in another
+            big = [(d_fin, H[7], g[16], 0, 256, 256, g[17])]
             for i in range(7, 0, -1):
-                if i == 4:
-                    alt.run(_wgrad, dY[4], 256, A0, 64, P, g[8], 0, 256, 63, isc)
-                    alt.run(_wgrad, dY[4], 256, H[3], 256, P, g[8], 63, 256, 256, isc, dbias=g[9])
-                else:
-                    alt.run(_wgrad, dY[i], 256, H[i - 1], 256, P, g[2 * i], 0, 256, 256, isc, dbias=g[2 * i + 1])
-            alt.run(_wgrad, dY[0], 256, A0, 64, P, g[0], 0, 256, 63, isc, dbias=g[1])
+                big.append((dY[i], H[i - 1], g[2 * i], 63 if i == 4 else 0, 256, 256, g[2 * i + 1]))
+            alt.run(_wgrad_multi, big, 256, 256, P, isc)
+            alt.run(_wgrad_multi, [(dY[4], A0, g[8], 0, 256, 63, None), (dY[0], A0, g[0], 0, 256, 63, g[1])], 256, 64, P, isc)
             alt.run(lambda: call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0,
                                  stream()))
         ctx.act = None
@@ -403,15 +413,14 @@ class SkinChainFn(torch.autograd.Function):
         rb0 = torch.zeros(1, 64, device=dev, dtype=torch.float32) if shared_row else None
         gpts = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
-        with _Alternate(dev) as alt:   # independent launches; the two that feed code_part stay on the current stream
-            _wgrad(dY[4], WD, A0, WD, P, g[8], 0, 64, 63, isc, dbias=rb4)
-            _wgrad(dY[0], WD, A0, WD, P, g[0], 0, 64, 63, isc, dbias=rb0)
-            alt.run(_wgrad, G, WD, dfe, WD, P, g[16], 0, oc, 32, isc, dbias=g[17])
-            alt.run(_wgrad, d_dfe, WD, fin, WD, P, g[12], 0, 32, 64, isc, dbias=g[13])
-            alt.run(_wgrad, d_fin, WD, H[4], WD, P, g[10], 0, 64, 64, isc, dbias=g[11])
-            alt.run(_wgrad, dY[4], WD, H[3], WD, P, g[8], 63 + nc, 64, 64, isc)
-            for i in (3, 2, 1):
-                alt.run(_wgrad, dY[i], WD, H[i - 1], WD, P, g[2 * i], 0, 64, 64, isc, dbias=g[2 * i + 1])
+        # all nine 64 x 64 weight gradients of the evaluation in ONE launch (bias gradients ride along; for a single
+        # shared pose-code row the column sums of dY[4] / dY[0] double as the code-part reductions)
+        jobs = [(dY[4], A0, g[8], 0, 64, 63, rb4), (dY[0], A0, g[0], 0, 64, 63, rb0),
+                (G, dfe, g[16], 0, oc, 32, g[17]), (d_dfe, fin, g[12], 0, 32, 64, g[13]), (d_fin, H[4], g[10], 0, 64, 64, g[11]),
+                (dY[4], H[3], g[8], 63 + nc, 64, 64, None)]
+        jobs += [(dY[i], H[i - 1], g[2 * i], 0, 64, 64, g[2 * i + 1]) for i in (3, 2, 1)]
+        _wgrad_multi(jobs, WD, WD, P, isc)
+        with _Alternate(dev) as alt:
             alt.run(lambda: call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0,
                                  stream()))
             code_part(dY[4], W[4], g[8], g[9], rb4)

@@ -495,6 +495,187 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW
   }
 }
 
+// Several weight gradients of ONE shape in one launch (a trunk pass has eight 256 x 256 ones, a nerf_skin pass nine
+// 64 x 64 ones): the grid is partitioned among the jobs, CTAs [cta0, cta0 + nctas) stream the rows of job j.  Against one
+// launch per layer this removes the ramp-up / tail of every launch and -- because a job's partial sums now come from
+// ~148 / njobs CTAs instead of 148 -- most of the red.global traffic of the final flush (256 KB per CTA for a 256 x 256
+// block), which is what kept the weight gradients at ~33 us per launch however small the batch (profiles/r02: 1.22 ms
+// of a 2.1 ms step at 1024 rays per GPU).
+constexpr int WG_MAX_JOBS = 9;
+struct WgJob { CUtensorMap y, x; float* dW; float* dbias; int ldw, n_valid, k_valid, cta0, nctas, pad_; };
+struct WgJobs { int njobs; int pad_[15]; WgJob job[WG_MAX_JOBS]; };
+
+template <int NOUT, int KIN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tc_wgrad_multi_kernel(const __grid_constant__ WgJobs jobs, int M, const float* oscale_p) {
+  // which job this CTA works on: CTAs [cta0, cta0 + nctas) of the grid belong to one job and split its row chunks
+  int jid = 0;
+  for (int j = 1; j < jobs.njobs; ++j)
+    if ((int)blockIdx.x >= jobs.job[j].cta0) jid = j;
+  const WgJob& J = jobs.job[jid];
+  const int cta = (int)blockIdx.x - J.cta0, nctas = J.nctas;
+  float* const dW = J.dW;
+  float* const dbias = J.dbias;
+  const int ldw = J.ldw, n_valid = J.n_valid, k_valid = J.k_valid;
+  constexpr int npair = 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int YB = NOUT / 64, XB = KIN / 64;       // boxes per operand per stage
+  constexpr int STAGE_BYTES = (YB + XB) * WG_BOX_BYTES;
+  constexpr int MB = (NOUT + 127) / 128;             // 128-row blocks of the accumulator
+  constexpr bool PAD_M = (NOUT == 64);
+  constexpr int TCOLS = MB * KIN <= 32 ? 32 : (MB * KIN <= 64 ? 64 : (MB * KIN <= 128 ? 128 : (MB * KIN <= 256 ? 256 : 512)));
+  static_assert(MB * KIN <= 512, "accumulator does not fit TMEM");
+  static_assert(NOUT == 64 || NOUT % 128 == 0, "output channels: 64 or blocks of 128");
+  uint8_t* zero_blk = smem + WG_STAGES * STAGE_BYTES;  // 8 KB of zeros (only used when PAD_M)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + WG_BOX_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WG_STAGES;
+  uint64_t* done = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_chunks = (M + WG_ROWS - 1) / WG_ROWS;
+
+  if (threadIdx.x == 0) {
+    // a stage is released by the MMA commit and, when bias gradients are wanted, by the 4 column-sum warps
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], dbias ? 5 : 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (PAD_M) {
+    for (int i = threadIdx.x; i < WG_BOX_BYTES / 16; i += WG_THREADS)
+      reinterpret_cast<uint4*>(zero_blk)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();  // make the generic-proxy zeros visible to the tensor core's async-proxy reads
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = cta < num_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&J.y);
+      prefetch_tmap(&J.x);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = cta; c < num_chunks; c += nctas) {
+        for (int p = 0; p < npair; ++p) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          for (int b = 0; b < YB; ++b) tma_load_2d(s + b * WG_BOX_BYTES, &J.y, &full[stage], b * 64, c * WG_ROWS);
+          for (int b = 0; b < XB; ++b)
+            tma_load_2d(s + (YB + b) * WG_BOX_BYTES, &J.x, &full[stage], b * 64, c * WG_ROWS);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      constexpr uint32_t idesc = make_idesc(128, KIN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int c = cta; c < num_chunks; c += nctas) {
+        for (int p = 0; p < npair; ++p) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t y_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t x_addr = y_addr + YB * WG_BOX_BYTES;
+          // LBO = distance to the next 64 MN elements: the next box, or the zero block when padding 64 -> 128
+          const uint32_t y_lbo = PAD_M ? (smem_u32(zero_blk) - y_addr) : (uint32_t)WG_BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < WG_ROWS / 16; ++k) {
+            // K advances by 16 rows = 2048 B; SBO = next 8 K rows
+            const uint64_t bd = make_desc(x_addr + k * 2048, WG_BOX_BYTES, 1024);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint64_t ad = make_desc(y_addr + mb * 2 * WG_BOX_BYTES + k * 2048, y_lbo, 1024);
+              umma_f16(tmem_base + (uint32_t)(mb * KIN), ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+            }
+          }
+          first = false;
+          umma_commit(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(done);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const float oscale = oscale_p ? *oscale_p : 1.0f;
+    if (dbias) {
+      // bias gradient = column sums of dY, taken from the operand boxes while the tensor core consumes them
+      // (pairs 0 and 1 carry dY's hi and lo halves; pair 2 repeats hi).  Box = 64 rows x 128 B, 128-byte swizzle:
+      // element (r, c) lives at r*128 + (((c >> 3) ^ (r & 7)) << 4) + (c & 7) * 2.
+      constexpr int PAIRS = NOUT / 2;            // column pairs
+      constexpr int GROUPS = 128 / PAIRS;        // row groups sharing the 128 threads
+      constexpr int RPG = WG_ROWS / GROUPS;      // rows per group
+      const int t = threadIdx.x - 64;
+      const int cp = t % PAIRS, grp = t / PAIRS;
+      const int box = cp >> 5, j = cp & 31;      // 32 column pairs per 64-column box
+      float s0 = 0.f, s1 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = cta; c < num_chunks; c += nctas) {
+        for (int p = 0; p < npair; ++p) {
+          mbar_wait(&full[stage], phase);
+          if (p < 2) {
+            const uint8_t* yb = smem + stage * STAGE_BYTES + box * WG_BOX_BYTES;
+#pragma unroll 8
+            for (int rr = 0; rr < RPG; ++rr) {
+              const int r = grp * RPG + rr;
+              const __half2 h = *reinterpret_cast<const __half2*>(yb + r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + (j & 3) * 4);
+              const float2 f = __half22float2(h);
+              s0 += f.x; s1 += f.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      const int col = cp * 2;
+      if (col < n_valid) atomicAdd(dbias + col, s0 * oscale);
+      if (col + 1 < n_valid) atomicAdd(dbias + col + 1, s1 * oscale);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int mb = 0; mb < MB; ++mb) {
+      const int n = mb * 128 + q * 32 + lane;  // output channel (row of dW)
+#pragma unroll 1
+      for (int c0 = 0; c0 < KIN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * KIN + c0), v);
+        if (n < n_valid) {
+          float* o = dW + (size_t)n * ldw + c0;
+          // 148 CTAs add their partial sums into the same (N, K) block: 128-bit reductions quarter the number of
+          // L2 atomic operations of the tail (rows whose start is not 16-byte aligned fall back to scalar adds)
+          if (c0 + 32 <= k_valid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j] * oscale),
+                           "f"(v[j + 1] * oscale), "f"(v[j + 2] * oscale), "f"(v[j + 3] * oscale)
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < k_valid) atomicAdd(o + j, v[j] * oscale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
 }  // namespace tc
 }  // namespace moda
 
@@ -673,4 +854,46 @@ extern "C" int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, 
   maps.x[1] = maps.x[0];
   if (int e = make_map(&maps.x[2], Xlo, M, K, ldx, WG_ROWS)) return e;
   return dispatch_wgrad(maps, 3, N, K, M, dW, ldw, n_valid, k_valid, oscale, dbias, stream);
+}
+
+template <int NOUT, int KIN>
+static int launch_wgrad_multi(const tc::WgJobs& jobs, int grid, int M, const float* oscale, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + WG_BOX_BYTES + 256;
+  cudaFuncSetAttribute(tc_wgrad_multi_kernel<NOUT, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  tc_wgrad_multi_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(jobs, M, oscale);
+  return check_launch("tc_wgrad_multi");
+}
+
+// njobs (<= 9) weight gradients of the same shape (N, K) over the same M rows in one launch:
+//   dW[j] (N, ldw[j]) += (*oscale) dY[j]^T X[j]  (first n_valid[j] rows / k_valid[j] columns),  dbias[j] += column sums.
+// Host arrays of length njobs; dbias[j] may be NULL.  Same operand rules as moda_tc_wgrad.
+extern "C" int moda_tc_wgrad_multi(int njobs, const void* const* dY, const int* ldy, const void* const* X, const int* ldx,
+                                   float* const* dW, const int* ldw, const int* n_valid, const int* k_valid,
+                                   float* const* dbias, int N, int K, int M, const float* oscale, cudaStream_t stream) {
+  if (M == 0 || njobs == 0) return 0;
+  MODA_REQUIRE(njobs > 0 && njobs <= WG_MAX_JOBS && dY && X && dW && ldy && ldx && ldw && n_valid && k_valid,
+               "tc_wgrad_multi: bad arguments (1..%d jobs)", WG_MAX_JOBS);
+  alignas(64) WgJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.njobs = njobs;
+  const int chunks = (M + WG_ROWS - 1) / WG_ROWS;
+  int total = sm_count();
+  if (total > chunks * njobs) total = chunks * njobs;
+  if (total < njobs) total = njobs;
+  int c0 = 0;
+  for (int j = 0; j < njobs; ++j) {
+    MODA_REQUIRE(dY[j] && X[j] && dW[j], "tc_wgrad_multi: null pointer in job %d", j);
+    WgJob& J = jobs.job[j];
+    if (int e = make_map(&J.y, dY[j], M, N, ldy[j], WG_ROWS)) return e;
+    if (int e = make_map(&J.x, X[j], M, K, ldx[j], WG_ROWS)) return e;
+    J.dW = dW[j]; J.dbias = dbias ? dbias[j] : nullptr; J.ldw = ldw[j]; J.n_valid = n_valid[j]; J.k_valid = k_valid[j];
+    J.cta0 = c0;
+    J.nctas = total / njobs + (j < total % njobs ? 1 : 0);
+    c0 += J.nctas;
+  }
+#define MODA_WGM(NN, KK) if (N == NN && K == KK) return launch_wgrad_multi<NN, KK>(jobs, c0, M, oscale, stream)
+  MODA_WGM(256, 256); MODA_WGM(256, 64); MODA_WGM(64, 64); MODA_WGM(128, 128); MODA_WGM(128, 64); MODA_WGM(64, 128);
+#undef MODA_WGM
+  MODA_REQUIRE(false, "tc_wgrad_multi: shape N=%d K=%d not instantiated", N, K);
+  return -1;
 }
