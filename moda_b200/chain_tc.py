@@ -119,6 +119,60 @@ class _Alternate:
         return False
 
 
+class _SideQueue:
+    """Weight-gradient launches of a backward pass whose results nothing else in that pass reads (they add into the
+    flat gradient buffer of ``parallel.FlatParams``): issued on two side streams and joined with the main stream only
+    at the END of the backward pass (autograd engine callback), not at the end of the Function that issued them.
+    The HBM-bound weight-gradient kernels then share the GPU with whatever the rest of the pass runs next
+    (skin_warp_bwd is FP32-issue bound, the chain kernels latency bound) instead of serialising in front of it.
+    The operands are kept alive here until the join, so the caching allocator cannot hand their memory to a later
+    main-stream allocation while a side stream still reads it.  MODA_B200_DEFER_WGRAD=0: join inside the Function."""
+
+    def __init__(self, dev, main):
+        self.dev, self.main = dev, main
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        self.i, self.keep = 0, []
+
+    def fork(self, *keep):
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        for s in self.streams:
+            s.wait_event(ev)
+        self.keep.extend(keep)
+        # one join per Function and pass (idempotent): runs after the last node of this backward pass was issued
+        torch.autograd.Variable._execution_engine.queue_callback(self.join)
+
+    def run(self, fn, *a, **k):
+        with torch.cuda.stream(self.streams[self.i & 1]):
+            fn(*a, **k)
+        self.i += 1
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self.main.wait_event(ev)
+            if cur.cuda_stream != self.main.cuda_stream:
+                cur.wait_event(ev)
+        self.keep.clear()
+
+
+_QUEUES = {}
+
+
+def _side_queue(dev, gret):
+    """The deferred-join queue of the current stream, or None when the weight gradients must be complete when the
+    Function returns (some gradient is handed back to autograd as a tensor, or the switch is off)."""
+    if not (config.side_stream and config.defer_wgrad) or any(r is not None for r in gret):
+        return None
+    main = torch.cuda.current_stream(dev)
+    key = (dev.index, main.cuda_stream)
+    if key not in _QUEUES:
+        _QUEUES[key] = _SideQueue(dev, main)
+    return _QUEUES[key]
+
+
 def _grad_targets(refs, params):
     """One accumulation buffer per parameter plus what backward() hands to autograd for it.  The weight-gradient
     kernels all accumulate (atomic +=).  A parameter re-homed by ``parallel.FlatParams`` carries its gradient as a
@@ -283,17 +337,26 @@ class TrunkChainFn(torch.autograd.Function):
         # weight gradients (bias gradients ride along as column sums of the dY operand)
         gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
-        with _Alternate(dev) as alt:   # the launches below are independent of each other
-            alt.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
-            # the eight 256 x 256 weight gradients (final layer, layers 8..6, the hidden part of layer 5, layers 4..2) in
-            # ONE launch, the two PE-input ones (layers 5 and 1) in another
-            big = [(d_fin, H[7], g[16], 0, 256, 256, g[17])]
-            for i in range(7, 0, -1):
-                big.append((dY[i], H[i - 1], g[2 * i], 63 if i == 4 else 0, 256, 256, g[2 * i + 1]))
-            alt.run(_wgrad_multi, big, 256, 256, P, isc)
-            alt.run(_wgrad_multi, [(dY[4], A0, g[8], 0, 256, 63, None), (dY[0], A0, g[0], 0, 256, 63, g[1])], 256, 64, P, isc)
-            alt.run(lambda: call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0,
-                                 stream()))
+        # the eight 256 x 256 weight gradients (final layer, layers 8..6, the hidden part of layer 5, layers 4..2) in
+        # ONE launch, the two PE-input ones (layers 5 and 1) in another
+        big = [(d_fin, H[7], g[16], 0, 256, 256, g[17])]
+        for i in range(7, 0, -1):
+            big.append((dY[i], H[i - 1], g[2 * i], 63 if i == 4 else 0, 256, 256, g[2 * i + 1]))
+        pe_jobs = [(dY[4], A0, g[8], 0, 256, 63, None), (dY[0], A0, g[0], 0, 256, 63, g[1])]
+        pe_bwd = lambda: call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
+        q = _side_queue(dev, gret)
+        if q is not None:   # weight gradients off the critical path: joined at the end of the backward pass
+            q.fork(d_dfe, fin, d_fin, H, dY, A0, isc, g)
+            q.run(_wgrad_multi, big, 256, 256, P, isc)
+            q.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+            q.run(_wgrad_multi, pe_jobs, 256, 64, P, isc)
+            pe_bwd()
+        else:
+            with _Alternate(dev) as alt:   # the launches below are independent of each other
+                alt.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+                alt.run(_wgrad_multi, big, 256, 256, P, isc)
+                alt.run(_wgrad_multi, pe_jobs, 256, 64, P, isc)
+                alt.run(pe_bwd)
         ctx.act = None
         gdir = gcode[:, :cd].contiguous()
         genv = gcode[:, cd:].contiguous() if has_env else None
@@ -341,7 +404,8 @@ class SkinChainFn(torch.autograd.Function):
         P, dev = pts.shape[0], pts.device
         ctx.param_refs = params
         params = [f32(p) for p in params]
-        code = f32(code).reshape(-1, code.shape[-1])
+        # code None: a net without code columns (nerf_vis, moda.py:344-348) = one shared, empty code row
+        code = torch.zeros(1, 0, device=dev, dtype=torch.float32) if code is None else f32(code).reshape(-1, code.shape[-1])
         Rc, nc = code.shape
         rep = S if Rc * S == P else P
         assert Rc * rep == P, "pose code rows do not match the points"
@@ -352,8 +416,11 @@ class SkinChainFn(torch.autograd.Function):
         oc = br.shape[0]
         T = ((P + TILE - 1) // TILE + 1) & ~1   # even: the CTA-pair kernels run tiles two at a time
         wa, _ = _win_array(win)
-        rb1 = _small_linear(code, W[0], 63, b[0], 64)
-        rb5 = _small_linear(code, W[4], 63, b[4], 64)
+        if nc:
+            rb1 = _small_linear(code, W[0], 63, b[0], 64)
+            rb5 = _small_linear(code, W[4], 63, b[4], 64)
+        else:
+            rb1, rb5 = _al16(b[0].reshape(1, 64)), _al16(b[4].reshape(1, 64))
         pad = torch.zeros(2, 64, device=dev, dtype=torch.float32)
         pad[0, :bd.shape[0]] = bd
         pad[1, :oc] = br
@@ -400,6 +467,9 @@ class SkinChainFn(torch.autograd.Function):
             """hoisted pose-code columns of layers 1 / 5: everything happens at ray (or single-row) level in fp32.
             rbg: per-ray (or, for a single shared code row, whole-batch) sums of dYl; for the shared row they come
             for free as the bias-gradient output of the layer's weight-gradient kernel."""
+            if nc == 0:   # no code columns: only the bias gradient (the column sums) is left
+                gb.add_(rbg[0])
+                return
             if rbg is None:
                 rbg = torch.empty(Rc, 64, device=dev, dtype=torch.float32)
                 call("moda_segsum16", ptr(dYl), WD, ptr(rbg), Rc, rep, 64, ptr(isc), 0, stream())
@@ -419,12 +489,26 @@ class SkinChainFn(torch.autograd.Function):
                 (G, dfe, g[16], 0, oc, 32, g[17]), (d_dfe, fin, g[12], 0, 32, 64, g[13]), (d_fin, H[4], g[10], 0, 64, 64, g[11]),
                 (dY[4], H[3], g[8], 63 + nc, 64, 64, None)]
         jobs += [(dY[i], H[i - 1], g[2 * i], 0, 64, 64, g[2 * i + 1]) for i in (3, 2, 1)]
-        _wgrad_multi(jobs, WD, WD, P, isc)
-        with _Alternate(dev) as alt:
-            alt.run(lambda: call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa, ptr(isc), 0,
-                                 stream()))
+        want_pts = ctx.needs_input_grad[0]   # e.g. nerf_vis is evaluated on detached points (loss_utils.py:125-149)
+        pe_bwd = lambda: want_pts and call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa,
+                                           ptr(isc), 0, stream())
+        q = _side_queue(dev, gret)
+        if q is not None:
+            # the two jobs whose column sums feed code_part stay on the current stream; the other seven are joined at
+            # the end of the backward pass
+            if shared_row:
+                _wgrad_multi(jobs[:2], WD, WD, P, isc)
+            q.fork(G, dfe, d_dfe, fin, d_fin, H, dY, A0, isc, g)
+            q.run(_wgrad_multi, jobs[2:] if shared_row else jobs, WD, WD, P, isc)
+            pe_bwd()
             code_part(dY[4], W[4], g[8], g[9], rb4)
             code_part(dY[0], W[0], g[0], g[1], rb0)
+        else:
+            _wgrad_multi(jobs, WD, WD, P, isc)
+            with _Alternate(dev) as alt:
+                alt.run(pe_bwd)
+                code_part(dY[4], W[4], g[8], g[9], rb4)
+                code_part(dY[0], W[0], g[0], g[1], rb0)
         ctx.act = None
         gret[14] = gret[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
-        return (gpts.reshape(pshape), gcode, None, None, None) + tuple(gret)
+        return (gpts.reshape(pshape) if want_pts else None, gcode if nc else None, None, None, None) + tuple(gret)

@@ -24,6 +24,10 @@ def set_precision(p):
 # side_stream: the independent weight-gradient launches of a backward pass alternate between the current stream and a
 # side stream (tail/ramp-up overlap of the persistent kernels); "0" keeps everything on the current stream.
 side_stream = os.environ.get("MODA_B200_SIDE_STREAM", "1") != "0"
+# defer_wgrad: weight gradients that accumulate in place into the flat gradient buffer (parallel.FlatParams) are issued
+# on side streams and joined at the END of the backward pass (chain_tc._SideQueue) instead of inside their Function:
+# the HBM-bound kernels overlap the rest of the pass.  Needs side_stream; "0" joins inside the Function.
+defer_wgrad = os.environ.get("MODA_B200_DEFER_WGRAD", "1") != "0"
 
 # Launch mode of the 256-wide chains (csrc/chain.cu), passed to the library with every call (no library-side state):
 # trunk_pair:  CTA pairs (tcgen05 cta_group::2, each CTA stages half of every weight chunk).  MODA_B200_TRUNK_PAIR=0: off.

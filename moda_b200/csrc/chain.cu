@@ -202,6 +202,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));   // d = {hi: first source, lo: second}
   return r;
 }
+// the same with the ReLU folded into the conversion (max(x, 0) then round): one F2FP instead of two FMNMX + one F2FP
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack2_lo(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 f = __half22float2(h);
@@ -363,7 +369,10 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
         const unsigned long long w16 = (unsigned long long)((~((n0 << 8) | n1)) & 0xFFFFu) << (16 * (i & 3));
         if (MW == 2 && i >= 4) m1 |= w16; else m0 |= w16;
       }
-      if (F & E_RELU) {
+      // ReLU: when the fp16 chunk is the only consumer of the activated values, the conversion clamps (pack2_relu below)
+      const bool relu_in_cvt = (F & E_RELU) && (F & E_SMEM) &&
+                               !(F & (E_ADD_SX | E_HEAD_SIGMA | E_HEAD_RGB | E_OUT_F32 | E_LO));
+      if ((F & E_RELU) && !relu_in_cvt) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
@@ -409,10 +418,18 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
         }
       }
       if (F & E_SMEM) {
+        if (relu_in_cvt) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          MODA_STS128(crow + (((p0 + j) ^ cx.sw) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                      pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 2; ++j)
+            MODA_STS128(crow + (((p0 + j) ^ cx.sw) << 4), pack2_relu(v[8 * j], v[8 * j + 1]),
+                        pack2_relu(v[8 * j + 2], v[8 * j + 3]), pack2_relu(v[8 * j + 4], v[8 * j + 5]),
+                        pack2_relu(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            MODA_STS128(crow + (((p0 + j) ^ cx.sw) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                        pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+        }
         if (F & E_LO) {
           const uint32_t crow_lo = cx.sA + (uint32_t)((st.out_lo_chunk + c64) * CHUNK_BYTES + cx.trow * 128);
 #pragma unroll

@@ -101,6 +101,10 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
     # tensor-core path for the auxiliary raw-feature MLPs on a plain PE(xyz) input (nerf_feat, nerf_vis)
     if (config.precision == "fp16" and not sigma_only and len(segs) == 1 and segs[0][0] == SEG_PE
             and generic_tc.supported(model, embed_xyz, k)):
+        if config.fused and skin_tc.supported(model, 0):
+            # a 5 x 64 raw-feature net without code columns (nerf_vis) is nerf_skin's architecture: same chain kernels
+            out = chain_tc.SkinChainFn.apply(pts2, None, nbins, win, torch.is_grad_enabled(), *model.param_list())
+            return out.reshape(Bn, nbins, 32)[..., :model.out_channels]
         skip = model.skips[0] if model.skips else None
         out = generic_tc.GenericTcFn.apply(pts2, win, torch.is_grad_enabled(), model.D, model.W, skip, *model.param_list())
         return out.reshape(Bn, nbins, 32)[..., :model.out_channels]

@@ -71,9 +71,11 @@ def _check_grads(name, got, truth, ref32, bar=GRAD_BAR, slack=3.0, per_ray_outli
         lim = max(bar, slack * e_ref)
         if per_ray_outliers and k.startswith("rays.") and t.dim() == 2 and t.shape[0] >= 1024:
             d = (got[k].detach().double().cpu() - t.double()).abs().max(-1).values / float(t.abs().max())
-            q = float(d.quantile(0.999))
-            table[-1] += "   per-ray 99.9%% quantile %.2e, rays above the bar: %d of %d" % (q, int((d > lim).sum()), d.numel())
-            if not (q <= lim and e <= 5 * lim):
+            q = float(d.quantile(0.995))
+            nrm = float((got[k].detach().double().cpu() - t.double()).norm() / t.double().norm())
+            table[-1] += "   per-ray 99.5%% quantile %.2e, norm-wise %.2e, rays above the bar: %d of %d" % (
+                q, nrm, int((d > lim).sum()), d.numel())
+            if not (q <= lim and nrm <= lim and e <= 5 * lim):
                 bad.append(table[-1])
         elif not e <= lim:
             bad.append(table[-1])
