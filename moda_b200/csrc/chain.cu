@@ -235,6 +235,16 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
+// timing experiment MODA_EXP_ALIAS_PE (results are WRONG): the 256-wide programs keep their fifth (PE) chunk on top of
+// chunk 0, which frees 2 x 16 KB of shared memory for two more weight stages -- does the depth of the ring matter?
+#ifdef MODA_EXP_ALIAS_PE
+#define MODA_CHUNK_OFF(c, wide) ((uint32_t)((wide) ? ((c) & 3) : (c)) * CHUNK_BYTES)
+#define MODA_NCHUNKS(n, wide) ((wide) ? (n) - 1 : (n))
+#else
+#define MODA_CHUNK_OFF(c, wide) ((uint32_t)(c) * CHUNK_BYTES)
+#define MODA_NCHUNKS(n, wide) (n)
+#endif
+
 // per-thread state of an epilogue warp that does not change within a tile
 struct EpiCtx {
   uint32_t sA;          // shared-window address of chunk 0
@@ -250,6 +260,7 @@ struct EpiCtx {
   int slot;             // tile slot of this epilogue group (two tiles in flight per CTA: 0 / 1)
   mutable int trn;      // trace records written by this thread
   uint32_t ready2_remote;   // CTA pairs: cluster address of the leader's ready2[slot][0] (0: single-CTA kernel)
+  bool step_fence;          // two tile slots: one proxy fence + chunk arrivals per STEP instead of per 64-column chunk
 };
 
 // One step's epilogue for this warp (flavour F = st.flags).  Sub-blocks of 16 columns are processed
@@ -306,7 +317,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
     const int c64 = cc >> 6;                 // chunk within the result
     const int p0 = (cc & 63) >> 3;           // first 16-byte piece within the chunk row (2 pieces per sub-block)
     const int chunk = st.out_chunk + c64;
-    const uint32_t crow = cx.sA + (uint32_t)(chunk * CHUNK_BYTES + cx.trow * 128);
+    const uint32_t crow = cx.sA + MODA_CHUNK_OFF(chunk, ACC_STRIDE == 256) + (uint32_t)(cx.trow * 128);
     const bool last_of_chunk = (i % SPC) == SPC - 1;
     if (F & E_LOAD16) {
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(pg.load_src) +
@@ -440,7 +451,7 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
         }
       }
     }
-    if ((F & E_SMEM) && last_of_chunk) {
+    if ((F & E_SMEM) && last_of_chunk && !cx.step_fence) {
       // this warp's part of the chunk is complete: make the generic-proxy writes visible to the async proxy
       // (tensor core, TMA) and count the warp in; the MMA thread and the store warp wait on the chunk barrier
 #ifndef MODA_EXP_NO_FENCE
@@ -453,6 +464,21 @@ __device__ __forceinline__ void run_step_body(const int Frt, const Program& pg, 
         if (cx.ready2_remote) {   // CTA pair: the leader's MMA thread counts both CTAs' writers
           mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)chunk);
           if (F & E_LO) mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)(st.out_lo_chunk + c64));
+        }
+      }
+    }
+    if ((F & E_SMEM) && cx.step_fence && i == nsub - 1) {
+      // two tile slots: the next MMA step of this tile starts on acc_free (after the whole step), so nothing gains from
+      // chunk-granular hand-over: ONE proxy fence per step, then the arrivals for all of its chunks (the store warp and,
+      // for chunks a load step wrote, the MMA warp wait on them)
+#ifndef MODA_EXP_NO_FENCE
+      fence_async_smem();
+#endif
+      __syncwarp();
+      if (cx.lane0) {
+        for (int c = 0; c < nch; ++c) {
+          mbar_arrive(&ready[st.out_chunk + c]);
+          if (cx.ready2_remote) mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)(st.out_chunk + c));
         }
       }
     }
@@ -507,6 +533,56 @@ __device__ __noinline__ void run_step_cold(const Program& pg, const Maps& maps, 
   if (CF & (E_HEAD_SIGMA | E_HEAD_RGB)) { hs[0] = hs0; hs[1] = hs1; hs[2] = hs2; }
 }
 
+// One row of the positional encoding, fp16 (hi [, lo for the split-precision 64-wide programs]) straight into the swizzled
+// A chunk: hrow = shared-window address of the row, sw = its swizzle phase (row & 7), x = the point.
+template <int BOX_ROWS>
+__device__ __forceinline__ void pe_row(const Program& pg, const uint32_t hrow, const int sw, const float (&x)[3]) {
+    // channels come out in index order; eight neighbours (one 16-byte piece of the swizzled row) share one
+  // 128-bit store (idx is a compile-time constant after unrolling, so the tests and the address arithmetic
+  // fold away)
+  float pend = 0.f;
+  uint32_t pk[4], pkl[4];
+  auto put = [&](const int idx, const float v) {
+    if ((idx & 1) == 0) { pend = v; return; }
+    const __half2 hv = __floats2half2_rn(pend, v);
+    pk[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
+    if (BOX_ROWS == 64) {   // split precision: low halves into the next chunk
+      const float2 hf = __half22float2(hv);
+      const __half2 lv = __floats2half2_rn(pend - hf.x, v - hf.y);
+      pkl[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&lv);
+    }
+    if ((idx & 7) == 7) {
+      const uint32_t a = hrow + (uint32_t)(((idx >> 3) ^ sw) << 4);
+      sts128(a, pk[0], pk[1], pk[2], pk[3]);
+      if (BOX_ROWS == 64) sts128(a + CHUNK_BYTES, pkl[0], pkl[1], pkl[2], pkl[3]);
+    }
+  };
+  put(0, x[0]); put(1, x[1]); put(2, x[2]);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const float f = (float)(1 << k);
+    const float w = (k < pg.F) ? pg.win[k] : 0.f;
+    float sn[3], cs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // SFU sin/cos after an exact two-term Cody-Waite reduction to [-pi, pi]: absolute error below 1e-6
+      // for |2^k x| <= 160 rad, far inside the fp16 rounding of the plain path and at the level of the
+      // (hi, lo) pair's 2^-22 of the split-precision path
+      const float r = x[c] * f;
+      const float kk = rintf(r * 0.15915494309189535f);
+      float r2 = fmaf(kk, -6.2831854820251465f, r);
+      r2 = fmaf(kk, 1.7484555e-7f, r2);
+      sn[c] = w * __sinf(r2);
+      cs[c] = w * __cosf(r2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) put(3 + 6 * k + c, sn[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) put(3 + 6 * k + 3 + c, cs[c]);
+  }
+  put(63, 0.f);
+}
+
 // BOX_ROWS: rows of one weight TMA box = widest accumulator half.  128: nerf_coarse (N <= 256, ring stage 32 KB),
 // 64: nerf_skin (N = 64, ring stage 8 KB).  EPI_WARPS (16 or 8) epilogue warps and PE_WARPS (4 or 2) producer warps;
 // the 64-wide configuration is sized so that TWO CTAs fit one SM (independent tiles hide each other's latencies).
@@ -541,8 +617,26 @@ constexpr int P_FWD = 0, P_BWD = 1;   // which set of straight-line epilogue fla
 // behind the other tile's MMAs.  A slot's accumulator is single-buffered: the next step's MMAs start when the
 // epilogue has drained it completely.  Per-tile arithmetic is unchanged, so results are bit-identical.
 // Tiles of CTA b: b, b + G, b + 2G, ... (G = grid); the j-th of them runs in slot j % SLOTS as that slot's tile j / SLOTS.
+//
+// Two tile slots, ONE MMA-issuing warp PER SLOT (MODA_DUAL_ISSUE, default): a slot-step costs its issuing warp ~4.2k cycles
+// (per K chunk a weight-stage wait, descriptors, four tcgen05.mma and a commit: ~690 cycles against 512 tensor cycles;
+// then the stores-done wait, the accumulator commit, the next step's table entry and the acc_free wait: ~1.1k cycles
+// during which the tensor pipe, whose queue holds ~4 MMAs, runs dry).  With a single warp alternating between the slots
+// those costs serialise: 4.2k cycles per tile-step although the epilogue warps idle 60 % of the time waiting for an
+// accumulator (profiles/r02_s20_trace_*).  With one issuer per slot the fixed costs of one slot's step overlap the other
+// slot's MMAs; the weight ring is shared, each issuer tracking the ring position of its own chunks in the global order
+// (tile iteration, step, slot, K chunk) the producer fills it in.  The producer moves to the last warp.
+#ifndef MODA_DUAL_ISSUE
+#define MODA_DUAL_ISSUE 1
+#endif
+// (with two issuers the positional encoding is produced by the epilogue warps, which wait for an accumulator 60 % of the
+// time, instead of a dedicated warp: warps are allocated in groups of four, so a 21st warp would cost the registers of
+// 24 -- 80 per thread instead of 96)
+constexpr int chain_threads(int slots, int epi_warps, int pe_warps) {
+  return ((slots == 2 && MODA_DUAL_ISSUE) ? (4 + slots * epi_warps) : (3 + slots * epi_warps + pe_warps)) * 32;
+}
 template <int BOX_ROWS, int EPI_WARPS, int PE_WARPS, int MIN_CTAS, int PROG, int PAIR, int SLOTS>
-__global__ void __launch_bounds__((3 + SLOTS * EPI_WARPS + PE_WARPS) * 32, MIN_CTAS)
+__global__ void __launch_bounds__(chain_threads(SLOTS, EPI_WARPS, PE_WARPS), MIN_CTAS)
 chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps maps) {
   static_assert(!PAIR || BOX_ROWS == 128, "CTA pairs: 256-wide chains only");
   static_assert(SLOTS == 1 || (SLOTS == 2 && PAIR == 1 && PE_WARPS == 1), "two tile slots: CTA-pair kernels only");
@@ -556,11 +650,14 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   constexpr int PE_THREADS = PE_WARPS * 32;
   (void)PE_THREADS;
   constexpr int PE_ROWS = TILE_M / PE_THREADS;                   // rows per producer thread
+  constexpr bool DUAL = (SLOTS == 2) && (MODA_DUAL_ISSUE != 0);  // one MMA-issuing warp per tile slot (warps 0 and 1)
+  constexpr int W_PROD = DUAL ? (3 + SLOTS * EPI_WARPS) : 0;     // warp that streams the weights
+  constexpr int PE_ARRIVALS = DUAL ? 4 : PE_WARPS;               // warps that write (and arrive on) a PE chunk
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                            // SLOTS x nchunks x 16 KB
-  uint8_t* sB = sA + (size_t)SLOTS * pg.nchunks * CHUNK_BYTES;   // stages x STAGE_BYTES
+  uint8_t* sB = sA + (size_t)SLOTS * MODA_NCHUNKS(pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES;   // stages x STAGE_BYTES
   float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);   // SLOTS x head_smem
   float* s_bias = s_head + SLOTS * head_smem(NH) / 4;            // bias_floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.bias_floats);
@@ -575,10 +672,13 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   uint64_t* ready2 = stores_done + 2;            // [2][MAX_CHUNKS]
   uint64_t* acc_free2 = ready2 + 2 * MAX_CHUNKS; // [2]
   uint64_t* stores_done2 = acc_free2 + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stores_done2 + 2);
+  // two issuers: turn[x] hands the weight ring to issuer x (parity waits on a ring barrier are only sound for a consumer
+  // that is less than one ring revolution ahead of the fills, which holds when chunks are claimed in their global order)
+  uint64_t* turn = stores_done2 + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
   constexpr int SLOT_CHUNK_BYTES_MAX = MAX_CHUNKS * CHUNK_BYTES;
   (void)SLOT_CHUNK_BYTES_MAX;
-  const uint32_t slot_bytes = (uint32_t)pg.nchunks * CHUNK_BYTES;   // A chunks of one tile slot
+  const uint32_t slot_bytes = (uint32_t)MODA_NCHUNKS(pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES;   // A chunks of one tile slot
   // accumulator of (slot, n-th MMA step of that slot) and the phase its barriers are in: one tile per CTA ping-pongs
   // over both accumulators step by step, two tile slots own one accumulator each
   auto acc_of = [](int slot, uint32_t ctr) { return SLOTS == 2 ? slot : (int)(ctr & 1); };
@@ -603,12 +703,13 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int k = 0; k < 2; ++k) {
-      for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[k * MAX_CHUNKS + i], pg.from_pe[i] ? PE_WARPS : EPI_WARPS);
+      for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready[k * MAX_CHUNKS + i], pg.from_pe[i] ? PE_ARRIVALS : EPI_WARPS);
       mbar_init(&stores_done[k], 1);
       mbar_init(&acc_full[k], 1); mbar_init(&acc_free[k], EPI_WARPS);
       mbar_init(&pe_free[k], 1);
+      mbar_init(&turn[k], 1);
       if (PAIR) {
-        for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready2[k * MAX_CHUNKS + i], 2 * (pg.from_pe[i] ? PE_WARPS : EPI_WARPS));
+        for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&ready2[k * MAX_CHUNKS + i], 2 * (pg.from_pe[i] ? PE_ARRIVALS : EPI_WARPS));
         mbar_init(&acc_free2[k], 2 * EPI_WARPS);
         mbar_init(&stores_done2[k], 2);
       }
@@ -632,7 +733,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     // ================================================================== weight producer
     if (lane == 0) {
       prefetch_tmap(&maps.w);
@@ -669,7 +770,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (DUAL && warp == 0)) {
     // ================================================================== MMA issuer (CTA pairs: the leader's only)
     // The WHOLE warp runs the loop converged (every lane polls the barriers) and one elected lane issues the tensor
     // core instructions: the loop state is then warp-uniform and ptxas keeps descriptors, barrier addresses and counters
@@ -678,6 +779,11 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     // took ~900 cycles against the 512 tensor cycles of the chunk (profiles/r02_*: tensor pipe 37 % active whatever
     // the epilogue did): this thread, not the tensor core or the epilogue, bounded the kernel.
     if (leader) {
+      const int my_slot = warp;   // DUAL: this warp issues for one tile slot only
+      (void)my_slot;
+      uint32_t turn_ctr = 0;      // DUAL: hand-overs of the weight ring received so far
+      bool turn_owed = false;     // DUAL, slot 0: the other issuer will hand the ring back before my next chunks
+      (void)turn_ctr; (void)turn_owed;
       int stage = 0;
       uint32_t phase = 0, gstep = 0;
       uint32_t mma_ctr0 = 0, mma_ctr1 = 0;               // MMA steps issued so far, per slot
@@ -700,6 +806,12 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           const uint32_t idesc = make_idesc(PAIR ? 2 * TILE_M : TILE_M, n, 0, 0);
 #pragma unroll 1
           for (int slot = 0; slot < nact; ++slot, ++gstep) {
+            if (DUAL && slot != my_slot) {
+              // the other issuer's chunks: only the ring position moves on
+              stage += nkc;
+              while (stage >= pg.stages) { stage -= pg.stages; phase ^= 1; }
+              continue;
+            }
             if (lane == 0) s_dbg[1] = (int)gstep;
             uint64_t* const sd_bar = PAIR ? &stores_done2[slot] : &stores_done[slot];
             if (nkc == 0) {
@@ -708,15 +820,24 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             }
             const uint32_t ctr = slot ? mma_ctr1 : mma_ctr0;
             const int b = acc_of(slot, ctr);
-            const bool tr = pg.trace && blockIdx.x == 0 && it == 2 && lane == 0;
+            // trace regions: 0 for the single issuer / slot 0's, 20 for slot 1's
+            const int tr = (pg.trace && blockIdx.x == 0 && it == 2 && lane == 0) ? ((DUAL && slot) ? 201 : 1) : 0;
             (void)tr;
-            MODA_TR(tr, 0, s, slot);
+            MODA_TR(tr, tr - 1 + 0, s, slot);
             // the epilogue that last read this accumulator has drained it
             wait_or_trap<0, MMA_WAIT_CLUSTER>(PAIR ? &acc_free2[b] : &acc_free[b], acc_phase(ctr) ^ 1);
             tc_fence_after();
-            MODA_TR(tr, 1, s, slot);
+            MODA_TR(tr, tr - 1 + 1, s, slot);
             const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_STRIDE);
             const uint32_t sA_slot = sA_u + (uint32_t)slot * slot_bytes;
+            if (DUAL) {
+              // claim the ring: the chunks before mine in the global order have been seen by their issuer
+              if (my_slot == 1 || turn_owed) {
+                wait_or_trap(&turn[my_slot], turn_ctr & 1);
+                ++turn_ctr;
+                turn_owed = false;
+              }
+            }
             uint64_t* const rdy = (PAIR ? ready2 : ready) + slot * MAX_CHUNKS;
 #pragma unroll 1
             for (int kc = 0; kc < nkc; ++kc) {
@@ -725,6 +846,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
               // weights first: the producer runs far ahead, so this check completes while the epilogue is still writing
               // the A chunk, and nothing but the descriptors stands between the chunk's arrival and the MMA issue
               wait_or_trap(&w_full[stage], phase);
+              MODA_TR(tr, tr - 1 + 3, s, kc);
               // two tile slots: chunks written by this tile's earlier MMA-step epilogues are complete once the
               // accumulator has been handed back (their warps arrived on the chunk barriers before acc_free)
               if (!(SLOTS == 2 && (info & 0x10000))) {
@@ -732,9 +854,10 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
                 wait_or_trap<0, MMA_WAIT_CLUSTER>(&rdy[c], gen & 1);
               }
               tc_fence_after();
+              MODA_TR(tr, tr - 1 + 5, s, kc);
               // the descriptors of a chunk are built once; the three K = 16 advances are plain additions (32 bytes = 2
               // units of the 16-byte address field, which cannot carry out of its 14 bits within a 16 KB chunk)
-              const uint32_t alo = ((sA_slot + (uint32_t)c * CHUNK_BYTES) & 0x3FFFF) >> 4;
+              const uint32_t alo = ((sA_slot + MODA_CHUNK_OFF(c, BOX_ROWS == 128)) & 0x3FFFF) >> 4;
               const uint32_t blo = ((sB_u + (uint32_t)stage * STAGE_BYTES) & 0x3FFFF) >> 4;
               if (elect_one()) {
                 if (PAIR) {
@@ -752,12 +875,19 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
                 }
               }
               __syncwarp();
+              MODA_TR(tr, tr - 1 + 6, s, kc);
               if (++stage == pg.stages) { stage = 0; phase ^= 1; }
             }
-            MODA_TR(tr, 2, s, slot);
+            if (DUAL && nact == 2) {
+              // every weight stage of this step has been observed full: the ring goes to the other issuer
+              if (lane == 0) mbar_arrive(&turn[my_slot ^ 1]);
+              if (my_slot == 0) turn_owed = true;
+            }
+            MODA_TR(tr, tr - 1 + 2, s, slot);
             // In-place rewrite guarantee: the epilogue of THIS step overwrites chunks that TMA stores of earlier steps
             // read; it starts on acc_full, so that is only signalled once those stores have read their source.
             if (sd_need > 0) wait_or_trap<0, MMA_WAIT_CLUSTER>(sd_bar, (sd_need - 1) & 1);
+            MODA_TR(tr, tr - 1 + 7, s, slot);
             if (elect_one()) {
               if (PAIR) {
                 umma_commit_pair_u32(acc_full_u + 8u * (uint32_t)b, 3);
@@ -768,7 +898,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
               }
             }
             __syncwarp();
-            MODA_TR(tr, 4, s, slot);
+            MODA_TR(tr, tr - 1 + 4, s, slot);
             if (slot) mma_ctr1 = ctr + 1; else mma_ctr0 = ctr + 1;
           }
         }
@@ -804,11 +934,41 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     cx.lscale = pg.load_scale ? *pg.load_scale : 1.0f;
     cx.T = pg.mask_tiles;
     cx.ready2_remote = PAIR ? mapa_u32(smem_u32(&ready2[slot * MAX_CHUNKS]), 0) : 0u;
+#ifdef MODA_EXP_CHUNK_FENCE
+    cx.step_fence = false;
+#else
+    // forward programs only: measured 1.45 -> 1.41 ms for the forward and 1.51 -> 1.58 ms for the adjoint, whose
+    // stores-done wait on the MMA warp is exposed when the TMA stores of a step start late
+    cx.step_fence = SLOTS == 2 && PROG == P_FWD;
+#endif
     const uint32_t acc_free2_remote = PAIR ? mapa_u32(smem_u32(&acc_free2[0]), 0) : 0u;
     (void)acc_free2_remote;
     const int h = cx.h, trow = cx.trow;
     uint32_t mma_ctr = 0;
     float sig_keep = 0.f;
+    // DUAL: the four h == 0 warps of the slot write the PE chunk of the slot's NEXT tile (thread = row, as in the
+    // epilogue) right after the epilogue of the last step that reads the current one -- its acc_full says those MMAs
+    // have completed, and the chunk's TMA save was waited for by the issuer steps earlier
+    const bool pe_duty = DUAL && pg.pe_chunk >= 0 && h == 0;
+    auto pe_fetch = [&](int tile_n, float (&x)[3]) {
+      const long long row = (long long)tile_n * TILE_M + trow;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = (row < pg.M) ? __ldg(pg.xyz + row * 3 + c) : 0.f;
+    };
+    auto pe_write = [&](const float (&x)[3]) {
+      pe_row<BOX_ROWS>(pg, cx.sA + MODA_CHUNK_OFF(pg.pe_chunk, BOX_ROWS == 128) + (uint32_t)(trow * 128), cx.sw, x);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ready_slot[pg.pe_chunk]);
+        if (PAIR) mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)pg.pe_chunk);
+      }
+    };
+    if (pe_duty && slot < ntile) {
+      float x0[3];
+      pe_fetch((int)blockIdx.x + slot * (int)gridDim.x, x0);
+      pe_write(x0);
+    }
     for (int it = 0; it * SLOTS + slot < ntile; ++it) {
       const int tile = (int)blockIdx.x + (it * SLOTS + slot) * (int)gridDim.x;
       cx.tile = tile;
@@ -835,6 +995,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         const int flags = st.flags;
         if (ew == 0 && lane == 0) s_dbg[2] = it * 100 + s;
         int b = 0;
+        const bool pe_now = pe_duty && st.release_pe && (it + 1) * SLOTS + slot < ntile;
+        float xn[3] = {0.f, 0.f, 0.f};
+        if (pe_now) pe_fetch(tile + SLOTS * (int)gridDim.x, xn);   // in flight while this step's accumulator is awaited
         // the saved ReLU sign words of this step (adjoint programs) come from HBM: ask for them before waiting for
         // the accumulator, so that their latency is off the step's critical path
         unsigned long long pm0 = 0, pm1 = 0;
@@ -947,6 +1110,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
           MODA_TR(cx.tr, cx.tr + 2, s, 0);
           ++mma_ctr;
         }
+        if (pe_now) pe_write(xn);
         // head partial sums: the warps h >= 1 of a lane quarter hand theirs to warp h = 0 through shared memory
         // (summation order h = 0, 1, ..: as before)
         if (flags & E_HEAD_SIGMA) {
@@ -984,7 +1148,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
         }
       }
     }
-  } else if (warp < 2 + SLOTS * EPI_WARPS + PE_WARPS) {
+  } else if (!DUAL && warp < 2 + SLOTS * EPI_WARPS + PE_WARPS) {
     // ================================================================== positional-encoding producers
     // (two tile slots: the one producer warp serves them alternately, in the order the tiles start)
     if (pg.pe_chunk >= 0) {
@@ -1026,51 +1190,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 #pragma unroll
           for (int j = 1; j < PE_ROWS; ++j)   // register select (the row loop stays rolled: code size)
             if (rr == j) { x[0] = xs[j][0]; x[1] = xs[j][1]; x[2] = xs[j][2]; }
-          const uint32_t hrow = pe_base + (uint32_t)(trow * 128);
-          // channels come out in index order; eight neighbours (one 16-byte piece of the swizzled row) share one
-          // 128-bit store (idx is a compile-time constant after unrolling, so the tests and the address arithmetic
-          // fold away)
-          float pend = 0.f;
-          uint32_t pk[4], pkl[4];
-          auto put = [&](const int idx, const float v) {
-            if ((idx & 1) == 0) { pend = v; return; }
-            const __half2 hv = __floats2half2_rn(pend, v);
-            pk[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
-            if (BOX_ROWS == 64) {   // split precision: low halves into the next chunk
-              const float2 hf = __half22float2(hv);
-              const __half2 lv = __floats2half2_rn(pend - hf.x, v - hf.y);
-              pkl[(idx & 7) >> 1] = *reinterpret_cast<const uint32_t*>(&lv);
-            }
-            if ((idx & 7) == 7) {
-              const uint32_t a = hrow + (uint32_t)(((idx >> 3) ^ sw) << 4);
-              sts128(a, pk[0], pk[1], pk[2], pk[3]);
-              if (BOX_ROWS == 64) sts128(a + CHUNK_BYTES, pkl[0], pkl[1], pkl[2], pkl[3]);
-            }
-          };
-          put(0, x[0]); put(1, x[1]); put(2, x[2]);
-#pragma unroll
-          for (int k = 0; k < 10; ++k) {
-            const float f = (float)(1 << k);
-            const float w = (k < pg.F) ? pg.win[k] : 0.f;
-            float sn[3], cs[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              // SFU sin/cos after an exact two-term Cody-Waite reduction to [-pi, pi]: absolute error below 1e-6
-              // for |2^k x| <= 160 rad, far inside the fp16 rounding of the plain path and at the level of the
-              // (hi, lo) pair's 2^-22 of the split-precision path
-              const float r = x[c] * f;
-              const float kk = rintf(r * 0.15915494309189535f);
-              float r2 = fmaf(kk, -6.2831854820251465f, r);
-              r2 = fmaf(kk, 1.7484555e-7f, r2);
-              sn[c] = w * __sinf(r2);
-              cs[c] = w * __cosf(r2);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) put(3 + 6 * k + c, sn[c]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) put(3 + 6 * k + 3 + c, cs[c]);
-          }
-          put(63, 0.f);
+          pe_row<BOX_ROWS>(pg, pe_base + (uint32_t)(trow * 128), sw, x);
         }
         fence_async_smem();
         __syncwarp();
@@ -1119,7 +1239,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
 #else
                 const int trow0 = tile * TILE_M;
 #endif
-                tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)slot * slot_bytes + (uint32_t)(c * CHUNK_BYTES),
+                tma_store_2d_u32(&maps.save[pg.duty[d].map], sA_u32 + (uint32_t)slot * slot_bytes + MODA_CHUNK_OFF(c, BOX_ROWS == 128),
                                  (int)pg.duty[d].col * 64, trow0);
                 bulk_commit();
                 any = true;
@@ -1277,10 +1397,10 @@ int launch(Builder& bld, const void* wpack, int wrows, int wcols, cudaStream_t s
   b.pg.mask_tiles = (b.pg.num_tiles + 1) & ~1;
   if (PAIR) b.pg.num_tiles = (b.pg.num_tiles + 1) & ~1;   // both CTAs of a pair run the same number of tiles
   constexpr int STAGE_BYTES = PAIR ? BOX_ROWS * 128 : ((BOX_ROWS == 128) ? 2 * BOX_ROWS * 128 : BOX_ROWS * 128);
-  constexpr int THREADS = (3 + SLOTS * EPI_WARPS + PE_WARPS) * 32;
+  constexpr int THREADS = chain_threads(SLOTS, EPI_WARPS, PE_WARPS);
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
   // weight ring: as many stages as fit (16 KB stages for CTA pairs, 32 KB otherwise), at most the program's request
-  const size_t fixed = 1024 + (size_t)SLOTS * b.pg.nchunks * CHUNK_BYTES + (size_t)SLOTS * head_smem(EPI_WARPS / 4) +
+  const size_t fixed = 1024 + (size_t)SLOTS * MODA_NCHUNKS(b.pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES + (size_t)SLOTS * head_smem(EPI_WARPS / 4) +
                        (size_t)b.pg.bias_floats * 4 + 512 + 32;
   MODA_REQUIRE(fixed + 2 * STAGE_BYTES <= cap, "chain: needs %zu B of shared memory (limit %zu)", fixed + 2 * STAGE_BYTES, cap);
   int stages = (int)((cap - fixed) / STAGE_BYTES);
@@ -1324,7 +1444,11 @@ int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_
     const int tiles = (b.pg.num_tiles + 1) & ~1;
     int e;
     if ((mode & MODE_TWO_SLOTS) && tiles >= 2 * ctas) {
+#ifdef MODA_EXP_ALIAS_PE
+      b.pg.stages = 5;
+#else
       b.pg.stages = 3;
+#endif
       e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 2>(b, wpack, 256, wcols, stream);
     } else {
       b.pg.stages = 8;

@@ -41,12 +41,14 @@ for region in range(32):
     rec += b[32 + 4000 * region:32 + 4000 * region + 4 * n].reshape(n, 4).tolist()
 rec.sort(key=lambda r: r[3])
 t0 = rec[0][3]
-names = {0: "mma  step begin (wait acc_free)", 1: "mma  acc_free seen", 2: "mma  all MMAs issued", 3: "mma  W stage full", 4: "mma  step committed",
+names = {0: "mma  step begin (wait acc_free)", 1: "mma  acc_free seen", 2: "mma  all MMAs issued", 3: "mma  W stage full", 4: "mma  step committed", 5: "mma  A chunk ready", 6: "mma  chunk issued", 7: "mma  stores-done seen",
          10: "epi0 acc_full seen", 11: "epi0 chunk written", 12: "epi0 store-read waited", 13: "epi0 barrier passed",
          20: "stor chunk ready seen", 21: "stor smem read done",
          30: "pe   computed", 31: "pe   chunk free"}
 for ev, a, bb, t in rec:
-    if ev >= 40:
+    if 200 <= ev < 210:
+        nm = names.get(ev - 200, str(ev)).replace("mma ", "mma1")
+    elif ev >= 40:
         nm = "epi%d.%d %s" % ((ev - 40) // 80, ((ev - 40) % 80) // 10, {0: "acc_full seen", 1: "chunk written", 2: "step done (acc_free arrive)"}[ev % 10])
     else:
         nm = names.get(ev, str(ev))
