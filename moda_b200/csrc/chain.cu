@@ -40,6 +40,8 @@ constexpr int MAX_SAVE_MAPS = 14;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_DUTY = 48;
 constexpr int head_smem(int nh) { return (nh > 1 ? nh - 1 : 1) * 128 * 4 * 4; }   // [warp-of-quarter - 1][row][4] floats (per tile slot)
+// the adjoint programs have no heads: their 2 x 2 KB go to the weight ring (a fourth 16 KB stage in two-slot mode)
+constexpr int head_bytes(int prog, int slots, int nh) { return prog == 0 ? slots * head_smem(nh) : 0; }
 
 // Epilogue flavour bits (tested at run time: every branch is uniform across the CTA).
 enum : int {
@@ -659,7 +661,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   uint8_t* sA = smem;                                            // SLOTS x nchunks x 16 KB
   uint8_t* sB = sA + (size_t)SLOTS * MODA_NCHUNKS(pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES;   // stages x STAGE_BYTES
   float* s_head = reinterpret_cast<float*>(sB + (size_t)pg.stages * STAGE_BYTES);   // SLOTS x head_smem
-  float* s_bias = s_head + SLOTS * head_smem(NH) / 4;            // bias_floats
+  float* s_bias = s_head + head_bytes(PROG, SLOTS, NH) / 4;      // bias_floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (size_t)pg.bias_floats);
   uint64_t* w_full = bars;                       // [MAX_STAGES]
   uint64_t* w_empty = w_full + MAX_STAGES;       // [MAX_STAGES]
@@ -1400,7 +1402,7 @@ int launch(Builder& bld, const void* wpack, int wrows, int wcols, cudaStream_t s
   constexpr int THREADS = chain_threads(SLOTS, EPI_WARPS, PE_WARPS);
   const size_t cap = 232448 / MIN_CTAS - (MIN_CTAS > 1 ? 1024 : 0);   // 1 KB per CTA is reserved by the system
   // weight ring: as many stages as fit (16 KB stages for CTA pairs, 32 KB otherwise), at most the program's request
-  const size_t fixed = 1024 + (size_t)SLOTS * MODA_NCHUNKS(b.pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES + (size_t)SLOTS * head_smem(EPI_WARPS / 4) +
+  const size_t fixed = 1024 + (size_t)SLOTS * MODA_NCHUNKS(b.pg.nchunks, BOX_ROWS == 128) * CHUNK_BYTES + (size_t)head_bytes(PROG, SLOTS, EPI_WARPS / 4) +
                        (size_t)b.pg.bias_floats * 4 + 512 + 32;
   MODA_REQUIRE(fixed + 2 * STAGE_BYTES <= cap, "chain: needs %zu B of shared memory (limit %zu)", fixed + 2 * STAGE_BYTES, cap);
   int stages = (int)((cap - fixed) / STAGE_BYTES);
@@ -1444,11 +1446,7 @@ int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_
     const int tiles = (b.pg.num_tiles + 1) & ~1;
     int e;
     if ((mode & MODE_TWO_SLOTS) && tiles >= 2 * ctas) {
-#ifdef MODA_EXP_ALIAS_PE
-      b.pg.stages = 5;
-#else
-      b.pg.stages = 3;
-#endif
+      b.pg.stages = 5;   // as many 16 KB stages as fit: 3 for the forward programs, 4 for the adjoint
       e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 2>(b, wpack, 256, wcols, stream);
     } else {
       b.pg.stages = 8;

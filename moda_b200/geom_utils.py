@@ -30,6 +30,20 @@ def _split_segments(segs, cx):
 
 def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=32 * 1024, xyz=None, code=None,
                  appearance_code=None, sigma_only=False, use_semantic=False, _pitched=False):
+    """geom_utils.py:19-57 plus the output stage of the flow-field heads (Transhead / SE3head override forward() in the
+    reference, nerf.py:200-237): a model with a ``post(raw, xyz)`` method gets it applied to the raw MLP output, with
+    ``xyz`` the sample points (the ``xyz=`` argument, or the points themselves when they are embedded here)."""
+    out = _evaluate_mlp(model, xyz_embedded, embed_xyz, dir_embedded, chunk, xyz, code, appearance_code, sigma_only,
+                        use_semantic, _pitched)
+    post = getattr(model, "post", None)
+    if post is not None and not sigma_only:
+        pts = xyz if xyz is not None else (xyz_embedded if embed_xyz is not None else None)
+        out = post(out, pts)
+    return out
+
+
+def _evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=32 * 1024, xyz=None, code=None,
+                  appearance_code=None, sigma_only=False, use_semantic=False, _pitched=False):
     """geom_utils.py:19-57.  xyz_embedded: (B,nbins,k) points (if ``embed_xyz`` is given) or features.
 
     The reference concatenates [PE | dir | code | appearance] per ray-chunk and calls the MLP; here the
@@ -116,10 +130,85 @@ def evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=3
 
 
 def bone_transform(bones_in, rts, neudbs=True, is_vec=False):
-    """geom_utils.py:59-111 (dual-quaternion branch): bones (...,B,10) moved by rts (...,B*8) -> (bs,B,10)."""
-    if not neudbs:
-        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
-    return BoneTransformFn.apply(bones_in, rts)
+    """geom_utils.py:59-111.  neudbs: bones (...,B,10) moved by dual quaternions rts (...,B*8) -> (bs,B,10) (CUDA kernel).
+    Otherwise (the LBS motion model, :87-107): rts are rigid transforms, (..,B,12) [R row-major | T] when ``is_vec`` else
+    (..,B,3,4); centre' = R c + T, orient' = standardize(quat(R) (x) orient).  O(rays x bones) device tensor algebra."""
+    if neudbs:
+        return BoneTransformFn.apply(bones_in, rts)
+    B = bones_in.shape[-2]
+    bones = bones_in.reshape(-1, B, 10)
+    if is_vec:
+        rts = rts.reshape(-1, B, 12)
+        Rmat, Tmat = rts[..., :9].reshape(-1, B, 3, 3), rts[..., 9:12]
+    else:
+        rts = rts.reshape(-1, B, 3, 4)
+        Rmat, Tmat = rts[..., :3], rts[..., 3]
+    center = (Rmat * bones[:, :, None, :3]).sum(-1) + Tmat
+    orient = quaternion_multiply(matrix_to_quaternion(Rmat), bones[:, :, 3:7].expand(Rmat.shape[0], B, 4))
+    scale = bones[:, :, 7:10].expand(Rmat.shape[0], B, 3)
+    return torch.cat([center, orient, scale], -1)
+
+
+def matrix_to_quaternion(matrix):
+    """pytorch3d 0.6.1 ``matrix_to_quaternion`` (third_party/pytorch3d/.../rotation_conversions.py:101-152): of the four
+    algebraically equal candidates (one per quaternion component used as the pivot) the one with the largest pivot is
+    returned; gradients flow through that candidate only, and a non-positive pivot radicand has zero subgradient."""
+    m = matrix.reshape(matrix.shape[:-2] + (9,))
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = m.unbind(-1)
+    rad = torch.stack([1 + m00 + m11 + m22, 1 + m00 - m11 - m22, 1 - m00 + m11 - m22, 1 - m00 - m11 + m22], -1)
+    pos = rad > 0
+    q_abs = torch.where(pos, torch.sqrt(torch.where(pos, rad, torch.ones_like(rad))), torch.zeros_like(rad))
+    sq = q_abs * q_abs
+    a, b, c = m21 - m12, m02 - m20, m10 - m01          # 4 r i, 4 r j, 4 r k
+    d, e, f = m10 + m01, m02 + m20, m12 + m21          # 4 i j, 4 i k, 4 j k
+    cand = torch.stack([torch.stack([sq[..., 0], a, b, c], -1), torch.stack([a, sq[..., 1], d, e], -1),
+                        torch.stack([b, d, sq[..., 2], f], -1), torch.stack([c, e, f, sq[..., 3]], -1)], -2)
+    cand = cand / (2.0 * q_abs.clamp_min(0.1))[..., None]
+    best = q_abs.argmax(-1)
+    return torch.gather(cand, -2, best[..., None, None].expand(best.shape + (1, 4))).squeeze(-2)
+
+
+def quaternion_multiply(a, b):
+    """pytorch3d ``quaternion_multiply`` (rotation_conversions.py:359-409): Hamilton product, real part made >= 0."""
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = b.unbind(-1)
+    ab = torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                      aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
+    return torch.where(ab[..., :1] < 0, -ab, ab)
+
+
+def rts_invert(rts_in):
+    """geom_utils.py:142-153: inverse of rigid transforms (...,3,4): [R^T | -R^T T]."""
+    rts = rts_in.reshape(-1, 3, 4)
+    Ri = rts[:, :, :3].transpose(1, 2)
+    Ti = -(Ri * rts[:, None, :, 3]).sum(-1)
+    return torch.cat([Ri, Ti[..., None]], -1).reshape(rts_in.shape)
+
+
+def blend_skinning(rts, skin, pts):
+    """geom_utils.py:304-348: linear blend skinning, x' = (sum_b w_b R_b) x + sum_b w_b T_b.  rts (bs,B,3,4), skin
+    (bs,N,B), pts (bs,N,3).  The blended 3x4 transform of every point is ONE batched (N,B) x (B,12) product per ray (the
+    reference materialises the (bs,N,B,3,3) broadcast product, 472 MB per 4096-ray chunk)."""
+    B = rts.shape[-3]
+    N = pts.shape[-2]
+    pts = pts.reshape(-1, N, 3)
+    rts = rts.reshape(-1, B, 12)
+    G = torch.bmm(skin.reshape(-1, N, B), rts).reshape(-1, N, 3, 4)
+    return (G[..., :3] * pts[:, :, None, :]).sum(-1) + G[..., 3]
+
+
+def lbs(bones, rts_fw, skin, xyz_in, backward=True):
+    """geom_utils.py:906-931: the LBS motion model (``--lbs``): rts_fw (bs,B*12) rigid transforms of the rest bones,
+    backward = blend of their inverses.  Returns (xyz, bones_dfm)."""
+    B = bones.shape[-2]
+    N = xyz_in.shape[-2]
+    bs = rts_fw.shape[0]
+    xyz_in = xyz_in.reshape(-1, N, 3)
+    v = rts_fw.reshape(-1, B, 12)
+    rts = torch.cat([v[..., :9].reshape(bs, B, 3, 3), v[..., 9:12, None]], -1)
+    bones_dfm = bone_transform(bones.reshape(-1, B, 10), rts, neudbs=False)
+    xyz = blend_skinning(rts_invert(rts) if backward else rts, skin, xyz_in)
+    return xyz, bones_dfm
 
 
 def quaternion_to_matrix(q):

@@ -171,8 +171,6 @@ def feat_match(nerf_feat, embedding_xyz, feats, bound, grid_size=20, use_corr=Tr
 
 def kp_reproj(pts_pred, models, embedding_xyz, rays, to_target=False, neudbs=True):
     """loss_utils.py:224-270: canonical points -> (forward warp of their frame) -> camera -> pixels.  (...,3) -> (N,1,2)."""
-    if not neudbs:
-        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
     N = pts_pred.reshape(-1, 3).shape[0]
     xyz = pts_pred.reshape(-1, 1, 3)
     rtk_vec = (rays["rtk_vec_target"] if to_target else rays["rtk_vec"]).reshape(N, -1)
@@ -180,8 +178,13 @@ def kp_reproj(pts_pred, models, embedding_xyz, rays, to_target=False, neudbs=Tru
         bone_rts_fw = (rays["bone_rts_target"] if to_target else rays["bone_rts"]).reshape(N, -1)
         bones = models["bones_rst"]
         rest_pose_code = models["rest_pose_code"](torch.zeros(1, dtype=torch.long, device=bones.device))
-        dskin = G.mlp_skinning(models.get("nerf_skin"), rest_pose_code, xyz, embed_xyz=embedding_xyz, _pitched=True)
-        xyz = G.warp_points(xyz, bones, bone_rts_fw, models["skin_aux"], dskin, backward=False)
+        if neudbs:
+            dskin = G.mlp_skinning(models.get("nerf_skin"), rest_pose_code, xyz, embed_xyz=embedding_xyz, _pitched=True)
+            xyz = G.warp_points(xyz, bones, bone_rts_fw, models["skin_aux"], dskin, backward=False)
+        else:   # the LBS motion model (loss_utils.py:255-257)
+            skin_fw = G.gauss_mlp_skinning(xyz, embedding_xyz, bones, rest_pose_code, models.get("nerf_skin"),
+                                           skin_aux=models["skin_aux"])
+            xyz, _ = G.lbs(bones, bone_rts_fw, skin_fw, xyz, backward=False)
     Rmat = rtk_vec[:, 0:9].reshape(N, 1, 3, 3)
     Tmat = rtk_vec[:, 9:12].reshape(N, 1, 3)
     Kinv = rtk_vec[:, 12:21].reshape(N, 1, 3, 3)

@@ -53,3 +53,25 @@ def parameters_of(models):
         if k in models and models[k].requires_grad:
             ps.append(models[k])
     return ps
+
+
+def build_motion_models(prob, device="cuda", requires_grad=True):
+    """models / embeddings / rays for ``synth.make_motion_problem`` (LBS: the core dict with rigid ``bone_rts``; flow
+    fields: ``coarse`` + ``flowbw`` / ``flowfw`` as nnutils/moda.py:285-299 constructs them)."""
+    from .nerf import SE3head, Transhead
+    if prob["motion"] == "lbs":
+        return build_models(prob, device, requires_grad)
+    coarse = NeRF(in_channels_xyz=63, in_channels_dir=27 + 64, init_beta=0.1)
+    coarse.load_state_dict(prob["coarse"])
+    arch, oc = (Transhead, 3) if prob["motion"] == "trans" else (SE3head, 9)
+    models = {"coarse": coarse.to(device)}
+    for k in ("flowbw", "flowfw"):
+        m = arch(in_channels_xyz=63 + 128, D=5, W=128, out_channels=oc, in_channels_dir=0, raw_feat=True)
+        m.load_state_dict(prob[k])
+        models[k] = m.to(device)
+    embeddings = {"xyz": Embedding(3, 10, alpha=10), "dir": Embedding(3, 4, alpha=10)}
+    rays = {k: v.clone().to(device) for k, v in prob["rays"].items()}
+    if requires_grad:
+        for k in ("time_embedded", "env_code", "rays_o", "rays_d"):
+            rays[k].requires_grad_(True)
+    return models, embeddings, rays

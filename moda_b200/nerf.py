@@ -128,10 +128,74 @@ class DQ_RTHead(NeRF):
 
 
 class Transhead(NeRF):
-    """Translation flow field (nnutils/nerf.py:200-210): 0.1 * MLP(x)."""
+    """Translation flow field (nnutils/nerf.py:200-210): 0.1 * MLP(x).  ``post`` is the output stage that
+    geom_utils.evaluate_mlp applies after running the MLP on the CUDA kernels."""
+
+    def post(self, raw, xyz=None):
+        return raw * 0.1
 
     def forward(self, x, xyz=None, sigma_only=False):
-        return super().forward(x, sigma_only=sigma_only) * 0.1
+        out = super().forward(x, sigma_only=sigma_only)
+        return out if sigma_only else self.post(out, xyz)
+
+
+def so3_exp_map(log_rot, eps=1e-4):
+    """pytorch3d ``so3_exponential_map`` (third_party/pytorch3d/.../so3.py:110-176): Rodrigues' formula with the squared
+    angle clamped at eps.  (n,3) -> (n,3,3)."""
+    x, y, z = log_rot.unbind(-1)
+    ang = (log_rot * log_rot).sum(-1).clamp_min(eps).sqrt()
+    f1 = ang.sin() / ang
+    f2 = (1.0 - ang.cos()) / (ang * ang)
+    o = torch.zeros_like(x)
+    K = torch.stack([o, -z, y, z, o, -x, -y, x, o], -1).reshape(-1, 3, 3)
+    eye = torch.eye(3, dtype=log_rot.dtype, device=log_rot.device)
+    return f1[:, None, None] * K + f2[:, None, None] * torch.bmm(K, K) + eye
+
+
+class SE3head(NeRF):
+    """Per-point rigid flow field (nnutils/nerf.py:212-237, after Nerfies): the MLP emits (rotation, pivot, translation);
+    flow = R (x + 0.1 pivot) - 0.1 pivot + 0.1 translation - x with R = exp(rotation)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.use_xyz = True
+
+    def post(self, raw, xyz):
+        shape = xyz.shape
+        r = raw.reshape(-1, 9)
+        pivot, trans = r[:, 3:6] * 0.1, r[:, 6:9] * 0.1
+        p = xyz.reshape(-1, 3)
+        w = (so3_exp_map(r[:, 0:3]) * (p + pivot)[:, None, :]).sum(-1) - pivot + trans
+        return w.reshape(shape) - xyz
+
+    def forward(self, x, xyz=None, sigma_only=False):
+        out = super().forward(x, sigma_only=sigma_only)
+        return out if sigma_only else self.post(out, xyz)
+
+
+class RTHead(NeRF):
+    """Pose MLP of the LBS motion model (nnutils/nerf.py:307-344): per bone [R (9, row-major) | 0.1 t]; R from a
+    quaternion (use_quat) or the exponential map of a delta rotation.  Evaluated once per frame (moda.py:307-311)."""
+
+    def __init__(self, use_quat, **kwargs):
+        super().__init__(**kwargs)
+        self.use_quat = use_quat
+        self.num_output = 7 if use_quat else 6
+        for m in self.modules():
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    def forward(self, x):
+        from .geom_utils import quaternion_to_matrix
+        x = super().forward(x)
+        bs = x.shape[0]
+        rts = x.reshape(-1, self.num_output)
+        tmat = rts[:, 0:3] * 0.1
+        if self.use_quat:
+            rmat = quaternion_to_matrix(torch.nn.functional.normalize(rts[:, 3:7], 2, -1))
+        else:
+            rmat = so3_exp_map(rts[:, 3:6])
+        return torch.cat([rmat.reshape(-1, 9), tmat], -1).reshape(bs, 1, -1)
 
 
 def fid_reindex(fid, num_vids, vid_offset):

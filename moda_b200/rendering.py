@@ -7,8 +7,10 @@ rest_pose_code}, ``rays`` keys {rays_o, rays_d, near, far, xys, time_embedded, b
 2, what MoDA's DEFAULT flags add to a training step (section 8(f) rank 1): ``nerf_feat`` feature rendering +
 ``feat_match_loss`` + key-point reprojection, the third warp to the paired frame with flow rendering
 (``rtk_vec_target`` / ``bone_rts_target`` / ``*_dentrg``), ``nerf_vis`` (``render_vis`` masking and ``vis_loss``),
-``nerf_dis`` residual fields, ``symm_shape`` and the per-ray loss terms.  Branches that remain out of scope (free-form
-flow fields, LBS, nerf_unc, appearance codes, s3im) raise NotImplementedError instead of silently doing something else.
+``nerf_dis`` residual fields, ``symm_shape`` and the per-ray loss terms; plus the two alternative motion models of
+section 8(f) rank 5: LBS (``opts.lbs``: rigid transforms per bone, linear blend) and the free-form flow fields
+(``flowbw`` / ``flowfw``: Transhead or SE3head).  Branches that remain out of scope (nerf_unc, appearance codes, s3im)
+raise NotImplementedError instead of silently doing something else.
 """
 import torch
 import torch.nn.functional as F
@@ -17,7 +19,7 @@ from . import geom_utils as G
 from . import loss_utils as L
 from .ops import CompositeFn, PointsFromDepthsFn, SampleRaysFn, SamplePdfFn, WeightedSumFn
 
-_UNSUPPORTED_MODELS = ("flowbw", "flowfw", "nerf_unc")
+_UNSUPPORTED_MODELS = ("nerf_unc",)
 _UNSUPPORTED_RAYS = ("appearance_code",)
 
 
@@ -30,8 +32,9 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     for k in _UNSUPPORTED_RAYS:
         if k in rays:
             raise NotImplementedError("rays['%s'] is outside the accelerated core path (SURVEY.md 8(f))" % k)
-    if opts is not None and (getattr(opts, "lbs", False) or not getattr(opts, "neudbs", True)) and "bones" in models:
-        raise NotImplementedError("only the dual-quaternion (neudbs) motion model is implemented")
+    if (opts is not None and "bones" in models and "flowbw" not in models
+            and not (getattr(opts, "lbs", False) or getattr(opts, "neudbs", True))):
+        raise ValueError("models['bones'] needs a motion model: opts.neudbs or opts.lbs (rendering.py:312-322)")
     if opts is not None and getattr(opts, "s3im_loss", False):
         raise NotImplementedError("opts.s3im_loss is off in every MoDA script (moda.py:170) and not implemented")
     if use_fine:
@@ -144,8 +147,48 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
     xyz_coarse_target = xyz_coarse_dentrg = xyz_coarse_sampled
     result = {}
     cyc_pair = None
-    has_bones = "bones" in models
-    if has_bones:
+    has_flow = "flowbw" in models
+    has_bones = "bones" in models and not has_flow   # rendering.py:257 / 289: the flow fields take precedence
+    use_lbs = has_bones and bool(getattr(opts, "lbs", False))
+    if has_flow:
+        # free-form deformation (rendering.py:257-286): backward flow to the canonical space, forward flow back
+        # (cycle term ||flow_bw + flow_fw||) and to the paired frames; nets: Transhead / SE3head (nerf.py:200-237)
+        code_of = lambda k: rays[k][:, None]
+        flow_bw = G.evaluate_mlp(models["flowbw"], xyz_coarse_sampled, embed_xyz=embedding_xyz, code=code_of("time_embedded"),
+                                 chunk=chunk // N_samples)
+        xyz_coarse_sampled = xyz_coarse_sampled + flow_bw
+        if fine_iter:
+            fw = lambda k: G.evaluate_mlp(models["flowfw"], xyz_coarse_sampled, embed_xyz=embedding_xyz, code=code_of(k),
+                                          chunk=chunk // N_samples)
+            cyc_pair = (flow_bw, -fw("time_embedded"))
+            if "time_embedded_target" in rays:
+                xyz_coarse_target = xyz_coarse_sampled + fw("time_embedded_target")
+            if "time_embedded_dentrg" in rays:
+                xyz_coarse_dentrg = xyz_coarse_sampled + fw("time_embedded_dentrg")
+    elif use_lbs:
+        # linear blend skinning (rendering.py:303-360 with opts.lbs; geom_utils.py:304-348, 906-931): Gaussian-bone
+        # weights from the skinning kernel, the blend as one batched (S,B) x (B,12) product per ray
+        bones_rst = models["bones_rst"]
+        bone_rts_fw = rays["bone_rts"]
+        skin_aux = models["skin_aux"]
+        rest_pose_code = models["rest_pose_code"](torch.zeros(1, dtype=torch.long, device=bones_rst.device))
+        nerf_skin = models.get("nerf_skin")
+        if "nerf_dis" in models:
+            raise NotImplementedError("nerf_dis with opts.lbs reads an undefined variable in the reference (rendering.py:324)")
+        bones_dfm = G.bone_transform(bones_rst, bone_rts_fw, False, is_vec=True)
+        skin_bw = G.gauss_mlp_skinning(xyz_coarse_sampled, embedding_xyz, bones_dfm, rays["time_embedded"], nerf_skin,
+                                       skin_aux=skin_aux)
+        xyz_coarse_sampled, _ = G.lbs(bones_rst, bone_rts_fw, skin_bw, xyz_coarse_sampled)
+        if fine_iter:
+            skin_fw = G.gauss_mlp_skinning(xyz_coarse_sampled, embedding_xyz, bones_rst, rest_pose_code, nerf_skin,
+                                           skin_aux=skin_aux)
+            fw = lambda rts: G.lbs(bones_rst, rts, skin_fw, xyz_coarse_sampled, backward=False)[0]
+            cyc_pair = (xyz_coarse_frame, fw(bone_rts_fw))
+            if dist_corresp and "bone_rts_target" in rays:
+                xyz_coarse_target = fw(rays["bone_rts_target"])
+            if dist_corresp and "bone_rts_dentrg" in rays:
+                xyz_coarse_dentrg = fw(rays["bone_rts_dentrg"])
+    elif has_bones:
         bones_rst = models["bones_rst"]
         bone_rts_fw = rays["bone_rts"]
         skin_aux = models["skin_aux"]
@@ -230,12 +273,12 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
         xyz_coarse_dentrg = _project(xyz_coarse_dentrg, rays["rtk_vec_dentrg"], N_rays)
 
     result["xyz_camera_vis"] = xyz_coarse_frame
-    if has_bones:
+    if has_bones or has_flow:
         result["xyz_canonical_vis"] = xyz_coarse_sampled
     if "feats_at_samp" in rays:
         result["pts_exp_vis"] = pts_exp
         result["pts_pred_vis"] = pts_pred
-    if has_bones:
+    if has_bones or has_flow:
         result["frame_cyc_dis"] = out[6]
     if is_training and "nerf_vis" in models:   # :475-477
         result["vis_loss"] = L.visibility_loss(models["nerf_vis"], embedding_xyz, xyz_coarse_sampled, vis_coarse,

@@ -204,3 +204,36 @@ def full_opts(**kw):
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+# ------------------------------------------------------------------------------------------------ motion models
+def make_motion_problem(n_rays, kind, seed=0, num_bones=NUM_BONES):
+    """The alternative motion models of SURVEY.md 8(f) rank 5 on the core problem.  kind = "lbs": ``rays['bone_rts']``
+    holds rigid transforms (N, B*12) = [R row-major | T] per bone (moda.py:301-311, opts.lbs); kind = "trans" / "se3": no
+    bones, free-form flow fields ``flowbw`` / ``flowfw`` (5x128 MLPs on [PE(xyz) | time code], 3 or 9 outputs:
+    Transhead / SE3head, moda.py:285-299)."""
+    p = make_problem(n_rays, seed=seed, num_bones=num_bones)
+    gen = torch.Generator().manual_seed(seed + 1000)
+    p["motion"] = kind
+    if kind == "lbs":
+        R = _small_rotation(gen, n_rays * num_bones, 0.2).reshape(n_rays, num_bones, 9)
+        T = 0.05 * torch.randn(n_rays, num_bones, 3, generator=gen, dtype=F32)
+        p["rays"]["bone_rts"] = torch.cat([R, T], -1).reshape(n_rays, num_bones * 12)
+        # softer Gaussians (skin_aux[0] = log scale of the sharpness, geom_utils.py:245-262): with the core problem's
+        # value the far samples get an exactly one-hot weight, their LBS cycle x -> R^-1 -> R returns x up to rounding,
+        # and d|x - x_cyc| there is a unit vector in the direction of that rounding noise -- in the reference as much as
+        # here, so no two implementations agree on it.  With several bones blending, |x - x_cyc| is far from zero.
+        p["skin_aux"] = torch.tensor([-4.0, 10.0], dtype=F32)
+        return p
+    if kind not in ("trans", "se3"):
+        raise ValueError(kind)
+    oc = 3 if kind == "trans" else 9
+    for k in ("flowbw", "flowfw"):
+        sd = nerf_state(gen, D=5, W=128, in_channels_xyz=PE_XYZ + T_EMBED, in_channels_dir=0, out_channels=oc, init_beta=0.01)
+        # default-init heads give flows of ~1e-3: scale the last layer so that the warp visibly moves the samples
+        sd["rgb.0.weight"] = sd["rgb.0.weight"] * 8.0
+        p[k] = sd
+    for k in ("bones_rst", "skin_aux", "nerf_skin", "rest_pose_code"):
+        p.pop(k)
+    p["rays"].pop("bone_rts")
+    return p

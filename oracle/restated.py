@@ -367,14 +367,105 @@ def sample_pdf(bins, weights, n_importance, det=False, eps=1e-5, u=None):
     return bins_g[..., 0] + (u - cdf_g[..., 0]) / denom * (bins_g[..., 1] - bins_g[..., 0])
 
 
+# ------------------------------------------------------------------------------------------------
+# alternative motion models: LBS and the free-form flow fields
+def matrix_to_quat(m):
+    """pytorch3d matrix_to_quaternion (rotation_conversions.py:101-152): candidate with the largest pivot."""
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = m.reshape(m.shape[:-2] + (9,)).unbind(-1)
+    t = torch.stack([1 + m00 + m11 + m22, 1 + m00 - m11 - m22, 1 - m00 + m11 - m22, 1 - m00 - m11 + m22], -1)
+    qa = torch.zeros_like(t)
+    qa[t > 0] = torch.sqrt(t[t > 0])
+    rows = [torch.stack([qa[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], -1),
+            torch.stack([m21 - m12, qa[..., 1] ** 2, m10 + m01, m02 + m20], -1),
+            torch.stack([m02 - m20, m10 + m01, qa[..., 2] ** 2, m12 + m21], -1),
+            torch.stack([m10 - m01, m20 + m02, m21 + m12, qa[..., 3] ** 2], -1)]
+    cands = torch.stack(rows, -2) / (2.0 * qa[..., None].clamp_min(0.1))
+    pick = F.one_hot(qa.argmax(-1), 4) > 0.5
+    return cands[pick, :].reshape(m.shape[:-2] + (4,))
+
+
+def bone_transform_rigid(bones, rts):
+    """geom_utils.py:87-107 (``neudbs=False``, is_vec): bones (B,10), rts (bs,B,12) [R | T] -> (bs,B,10)."""
+    B = bones.shape[-2]
+    rts = rts.reshape(-1, B, 12)
+    Rm, Tm = rts[..., :9].reshape(-1, B, 3, 3), rts[..., 9:]
+    b = bones.reshape(1, B, 10)
+    center = Rm.matmul(b[..., :3, None].expand(Rm.shape[0], B, 3, 1))[..., 0] + Tm
+    orient = quat_mul_std(matrix_to_quat(Rm), b[..., 3:7].expand(Rm.shape[0], B, 4))
+    return torch.cat([center, orient, b[..., 7:].expand(Rm.shape[0], B, 3)], -1)
+
+
+def rts_invert(rts):
+    """geom_utils.py:142-153."""
+    Ri = rts[..., :3].transpose(-1, -2)
+    return torch.cat([Ri, -Ri.matmul(rts[..., 3:])], -1)
+
+
+def blend_skinning(rts, skin, pts):
+    """geom_utils.py:304-326: rts (bs,B,3,4), skin (bs,N,B), pts (bs,N,3)."""
+    Rw = (skin[..., None, None] * rts[:, None, :, :, :3]).sum(2)
+    Tw = (skin[..., None] * rts[:, None, :, :, 3]).sum(2)
+    return Rw.matmul(pts[..., None])[..., 0] + Tw
+
+
+def lbs(bones, rts_fw, skin, xyz, backward=True):
+    """geom_utils.py:906-931."""
+    B = bones.shape[-2]
+    v = rts_fw.reshape(-1, B, 12)
+    rts = torch.cat([v[..., :9].reshape(-1, B, 3, 3), v[..., 9:, None]], -1)
+    return blend_skinning(rts_invert(rts) if backward else rts, skin, xyz)
+
+
+def so3_exp(w, eps=1e-4):
+    """pytorch3d so3_exponential_map (so3.py:148-176)."""
+    ang = (w * w).sum(-1).clamp(eps).sqrt()
+    K = torch.zeros(w.shape[0], 3, 3, dtype=w.dtype)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
+    return (ang.sin() / ang)[:, None, None] * K + ((1 - ang.cos()) / ang ** 2)[:, None, None] * K.bmm(K) + torch.eye(3, dtype=w.dtype)
+
+
+FLOW_SPEC = {"trans": NerfSpec(5, 128, 63 + 128, 0, 3, (4,), True), "se3": NerfSpec(5, 128, 63 + 128, 0, 9, (4,), True)}
+
+
+def flow_field(sd, kind, xyz, code, n_freqs, alpha):
+    """Transhead / SE3head on [PE(xyz) | code] (nerf.py:200-237; evaluate_mlp call sites rendering.py:262-283)."""
+    raw = evaluate_mlp(sd, FLOW_SPEC[kind], xyz, n_freqs, alpha, code=code, chunk=32768)
+    if kind == "trans":
+        return raw * 0.1
+    r = raw.reshape(-1, 9)
+    pivot, trans = r[:, 3:6] * 0.1, r[:, 6:9] * 0.1
+    p = xyz.reshape(-1, 3) + pivot
+    w = so3_exp(r[:, :3]).matmul(p[..., None])[..., 0] - pivot + trans
+    return w.reshape(xyz.shape) - xyz
+
+
 def _deform_and_render(prob, xyz, z_vals, dir_embedded, n_freqs, alpha, fine_iter, noise=None,
                        vis_sd=None, vis_spec=None, obj_bound=None):
-    """rendering.py:239-579 restricted to the core path."""
+    """rendering.py:239-579 restricted to the core path, plus the LBS / flow-field motion
+    models when ``prob['motion']`` names one (synth.make_motion_problem)."""
     rays = prob["rays"]
     R, S, _ = xyz.shape
     res = {}
     xyz_frame = xyz
-    if prob.get("bones_rst") is not None:
+    motion = prob.get("motion")
+    if motion in ("trans", "se3"):   # rendering.py:257-274
+        time_emb = rays["time_embedded"][:, None]
+        flow_bw = flow_field(prob["flowbw"], motion, xyz, time_emb, n_freqs, alpha)
+        xyz = xyz + flow_bw
+        if fine_iter:
+            cyc = (flow_bw + flow_field(prob["flowfw"], motion, xyz, time_emb, n_freqs, alpha)).norm(2, -1)
+    elif motion == "lbs":   # rendering.py:303-341 with opts.lbs
+        bones_rst, rts_fw, skin_aux = prob["bones_rst"], rays["bone_rts"], prob["skin_aux"]
+        spec = prob.get("skin_spec", SKIN_SPEC)
+        bones_dfm = bone_transform_rigid(bones_rst, rts_fw)
+        skin_bw = gauss_mlp_skinning(xyz, n_freqs, alpha, bones_dfm, rays["time_embedded"][:, None], prob["nerf_skin"],
+                                     spec, skin_aux)
+        xyz = lbs(bones_rst, rts_fw, skin_bw, xyz, backward=True)
+        if fine_iter:
+            skin_fw = gauss_mlp_skinning(xyz, n_freqs, alpha, bones_rst, prob["rest_pose_code"][0:1], prob["nerf_skin"],
+                                         spec, skin_aux)
+            cyc = (xyz_frame - lbs(bones_rst, rts_fw, skin_fw, xyz, backward=False)).norm(2, -1)
+    elif prob.get("bones_rst") is not None:
         bones_rst = prob["bones_rst"]
         rts_fw = rays["bone_rts"]
         skin_aux = prob["skin_aux"]
@@ -405,7 +496,7 @@ def _deform_and_render(prob, xyz, z_vals, dir_embedded, n_freqs, alpha, fine_ite
         res["vis_pred"] = (vis_pred * weights).sum(-1)
     if fine_iter:
         res["xyz_camera_vis"] = xyz_frame
-        if prob.get("bones_rst") is not None:
+        if prob.get("bones_rst") is not None or motion in ("trans", "se3"):
             res["xyz_canonical_vis"] = xyz
             res["frame_cyc_dis"] = (cyc * weights.detach()).sum(-1)
     return res, weights
@@ -491,15 +582,17 @@ GRAD_RAYS = ("bone_rts", "time_embedded", "env_code", "rays_o", "rays_d")
 def require_grads(prob):
     leaves = {}
     for k in GRAD_PARAMS:
-        prob[k].requires_grad_(True)
-        leaves[k] = prob[k]
-    for net in ("coarse", "nerf_skin"):
-        for k, v in prob[net].items():
+        if k in prob:
+            prob[k].requires_grad_(True)
+            leaves[k] = prob[k]
+    for net in ("coarse", "nerf_skin", "flowbw", "flowfw"):
+        for k, v in prob.get(net, {}).items():
             v.requires_grad_(True)
             leaves[net + "." + k] = v
     for k in GRAD_RAYS:
-        prob["rays"][k].requires_grad_(True)
-        leaves["rays." + k] = prob["rays"][k]
+        if k in prob["rays"]:
+            prob["rays"][k].requires_grad_(True)
+            leaves["rays." + k] = prob["rays"][k]
     return leaves
 
 
