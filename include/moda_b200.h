@@ -235,7 +235,9 @@ int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const flo
                         const void* wpack /* fp16 (64, 18*64): [Whi | Wlo] per layer */,
                         const float* const* biases /* rb1, b2, b3, b4, rb5, bfinal, bdir64, brgb64 */, void* A0,
                         void* H /* (5,P,64) */, void* fin, void* dfe, unsigned int* maskbits /* (6,tiles2,4,128), tiles2 as above */,
-                        float* y32 /* (P,32) delta skinning logits */, cudaStream_t stream);
+                        float* y32 /* (P,32) delta skinning logits */,
+                        int fold /* 1: xyz_encoding_final folded into dir_encoding, see MODA_CHAIN_FOLD_FINAL */,
+                        cudaStream_t stream);
 /* debug: device buffer (>= 16004 int64, zeroed) that subsequent chain launches fill with an event timeline of
  * block 0's third tile (tools/chain_trace.py); NULL switches tracing off */
 int moda_chain_set_trace(long long* buf);
@@ -249,10 +251,17 @@ int moda_chain_set_trace(long long* buf);
  * sized for an EVEN tile count in every mode. */
 #define MODA_CHAIN_PAIR 1
 #define MODA_CHAIN_TWO_SLOTS 2
+/*   MODA_CHAIN_FOLD_FINAL xyz_encoding_final (no activation, nerf.py:182) and dir_encoding (nerf.py:186-190) are two
+ *                         linear maps in a row: the caller passes their product W' = Wdir[:, :W] Wfinal in the packed
+ *                         weights (forward: in place of [Wfinal, Wdir]; adjoint: W'^T in place of [Wdir^T, Wfinal^T]) and
+ *                         bdir + Wdir[:, :W] bfinal in the bias, and every pass runs one step less; fin / d_fin are not
+ *                         produced (may be NULL).  The caller maps dW' back: dWdir = dW' Wfinal^T, dWfinal = Wdir^T dW'.
+ *                         The 64-wide programs take the same switch as their `fold` argument. */
+#define MODA_CHAIN_FOLD_FINAL 4
 int moda_chain_pair_available(void);
 int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (64, 9*64) */,
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
-                        void* dY /* (5,P,64) */, void* d_pe, cudaStream_t stream);
+                        void* dY /* (5,P,64) */, void* d_pe, int fold, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -201,12 +201,31 @@ def _loss_scale(g):
     return scale2[0:1], scale2[1:2]
 
 
+# ------------------------------------------------------------------------------- final layer folded into the dir layer
+def _fold(Wf, bf, Wd, bd, W):
+    """xyz_encoding_final (no activation) followed by dir_encoding on [final | rest] (nerf.py:182-190) is one linear map
+    of the last hidden activation: W' = Wd[:, :W] Wf and b' = bd + Wd[:, :W] bf (fp32; O(weights) work per call)."""
+    Wd1 = Wd[:, :W]
+    return Wd1 @ Wf, torch.addmv(bd, Wd1, bf)
+
+
+def _unfold_grads(gWp, dbp, Wf, bf, Wd, W, g_Wf, g_bf, g_Wd):
+    """Maps the gradient of the folded layer back to the parameters it was made of: with W' = Wd1 Wf and b' = bd + Wd1 bf,
+    dWf += Wd1^T dW', dbf += Wd1^T db', dWd1 += dW' Wf^T + db' bf^T (dbd = db' is accumulated by the caller)."""
+    Wd1 = Wd[:, :W]
+    g_Wf.addmm_(Wd1.t(), gWp)
+    g_bf.addmv_(Wd1.t(), dbp)
+    g_Wd[:, :W].addmm_(gWp, Wf.t())
+    g_Wd[:, :W].addr_(dbp, bf)
+
+
 # ------------------------------------------------------------------------------------------------ nerf_coarse
-def pack_trunk_fwd(params):
+def pack_trunk_fwd(params, fold=None):
     """(256, 38*64) fp16, chunk order documented at moda_chain_trunk_fwd (csrc/chain.cu)."""
     W = [params[2 * i] for i in range(8)]
     Wf, Wd = params[16], params[18]
-    out = torch.zeros(256, 38 * 64, device=W[0].device, dtype=HALF)
+    nchunk = 34 if fold is not None else 38   # fold: W' (128, 256) replaces [Wfinal, Wdir[:, :256]]
+    out = torch.zeros(256, nchunk * 64, device=W[0].device, dtype=HALF)
     pk = _Packer(out)
     _pack = lambda w, cols, col0, _o, out_col0, out_rows, width, tr: pk.add(w, cols, col0, out_col0, out_rows, width, tr)
     col = 0
@@ -218,22 +237,30 @@ def pack_trunk_fwd(params):
             _pack(W[4], 256, 63, out, col, 256, 256, False); col += 256
         else:
             _pack(W[i], 256, 0, out, col, 256, 256, False); col += 256
-    _pack(Wf, 256, 0, out, col, 256, 256, False); col += 256
-    _pack(Wd, 256, 0, out, col, 128, 256, False); col += 256
-    assert col == 38 * 64
+    if fold is not None:
+        _pack(fold, 256, 0, out, col, 128, 256, False); col += 256
+    else:
+        _pack(Wf, 256, 0, out, col, 256, 256, False); col += 256
+        _pack(Wd, 256, 0, out, col, 128, 256, False); col += 256
+    assert col == nchunk * 64
     return pk.run()
 
 
-def pack_trunk_bwd(params):
-    """(256, 42*64) fp16 transposed weights, chunk order documented at moda_chain_trunk_bwd."""
+def pack_trunk_bwd(params, fold=None):
+    """(256, 42*64) fp16 transposed weights, chunk order documented at moda_chain_trunk_bwd (fold: (256, 38*64), W'^T in
+    place of [Wdir^T, Wfinal^T])."""
     W = [params[2 * i] for i in range(8)]
     Wf, Wd = params[16], params[18]
-    out = torch.zeros(256, 42 * 64, device=W[0].device, dtype=HALF)
+    nchunk = 38 if fold is not None else 42
+    out = torch.zeros(256, nchunk * 64, device=W[0].device, dtype=HALF)
     pk = _Packer(out)
     _pack = lambda w, cols, col0, _o, out_col0, out_rows, width, tr: pk.add(w, cols, col0, out_col0, out_rows, width, tr)
     col = 0
-    _pack(Wd, 256, 0, out, col, 256, 128, True); col += 128
-    _pack(Wf, 256, 0, out, col, 256, 256, True); col += 256
+    if fold is not None:
+        _pack(fold, 256, 0, out, col, 256, 128, True); col += 128
+    else:
+        _pack(Wd, 256, 0, out, col, 256, 128, True); col += 128
+        _pack(Wf, 256, 0, out, col, 256, 256, True); col += 256
     for i in (7, 6, 5):
         _pack(W[i], 256, 0, out, col, 256, 256, True); col += 256
     _pack(W[4], 63, 0, out, col, 64, 256, True); col += 256
@@ -241,7 +268,7 @@ def pack_trunk_bwd(params):
     for i in (3, 2, 1):
         _pack(W[i], 256, 0, out, col, 256, 256, True); col += 256
     _pack(W[0], 63, 0, out, col, 64, 256, True); col += 256
-    assert col == 42 * 64
+    assert col == nchunk * 64
     return pk.run()
 
 
@@ -280,14 +307,21 @@ class TrunkChainFn(torch.autograd.Function):
         assert R * S == P and Wd.shape[1] == 256 + cc
         T = ((P + TILE - 1) // TILE + 1) & ~1   # even: the CTA-pair kernels run tiles two at a time
         wa, _ = _win_array(win)
-        rb = _small_linear(code, Wd, 256, bd, 128)
-        wpack = pack_trunk_fwd(params)
+        fold = config.fold_final
+        mode = config.chain_mode()
+        if fold:
+            Wp, bp = _fold(Wf, bf, Wd, bd, 256)
+            rb = _small_linear(code, Wd, 256, bp, 128)
+            wpack = pack_trunk_fwd(params, Wp)
+        else:
+            rb = _small_linear(code, Wd, 256, bd, 128)
+            wpack = pack_trunk_fwd(params)
         biases = (ctypes.c_void_p * 9)(*([ptr(params[2 * i + 1]) for i in range(8)] + [ptr(bf)]))
         raw = torch.empty(P, 4, device=dev, dtype=torch.float32)
         if need_bw:
             A0 = torch.empty(P, 64, device=dev, dtype=HALF)
             H = torch.empty(8, P, 256, device=dev, dtype=HALF)
-            fin = torch.empty(P, 256, device=dev, dtype=HALF)
+            fin = None if fold else torch.empty(P, 256, device=dev, dtype=HALF)
             dfe = torch.empty(P, 128, device=dev, dtype=HALF)
             bits = torch.empty(8, T, 4, TILE, device=dev, dtype=torch.int64)
         else:
@@ -295,11 +329,11 @@ class TrunkChainFn(torch.autograd.Function):
         call("moda_chain_trunk_fwd", ptr(xyz), P, S, len(win), wa, ptr(wpack), biases, ptr(rb), ptr(_al16(Ws)), ptr(bs),
              ptr(_al16(Wr)),
              ptr(br), ptr(A0), ptr(H), ptr(fin), ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(raw),
-             config.chain_mode(), stream())
+             mode, stream())
         if need_bw:
             ctx.save_for_backward(xyz, code, raw, *params)
             ctx.act = (A0, H, fin, dfe, bits)
-            ctx.meta = (S, win, dir_emb.shape[-1], env is not None, xyz_shape)
+            ctx.meta = (S, win, dir_emb.shape[-1], env is not None, xyz_shape, mode)
         return raw
 
     @staticmethod
@@ -307,7 +341,8 @@ class TrunkChainFn(torch.autograd.Function):
         xyz, code, raw = ctx.saved_tensors[:3]
         params = list(ctx.saved_tensors[3:])
         A0, H, fin, dfe, bits = ctx.act
-        S, win, cd, has_env, xyz_shape = ctx.meta
+        S, win, cd, has_env, xyz_shape, mode = ctx.meta
+        fold = bool(mode & 4)
         P, dev = xyz.shape[0], xyz.device
         R, cc = code.shape
         Wf, bf, Wd, bd, Ws, bs, Wr, br = params[16:24]
@@ -328,32 +363,43 @@ class TrunkChainFn(torch.autograd.Function):
         call("moda_linear_wgrad", R, 128, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(cc), _one(cc), _one(0), _one(1), None,
              0, ptr(grb), 128, ptr(g[18]), Wd.shape[1], 256, ptr(g[19]), stream())
         # the whole data-gradient chain in one kernel
-        wpackT = pack_trunk_bwd(params)
-        d_fin = torch.empty(P, 256, device=dev, dtype=HALF)
+        wpackT = pack_trunk_bwd(params, _fold(Wf, bf, Wd, bd, 256)[0] if fold else None)
+        d_fin = None if fold else torch.empty(P, 256, device=dev, dtype=HALF)
         dY = torch.empty(8, P, 256, device=dev, dtype=HALF)
         d_pe = torch.empty(P, 64, device=dev, dtype=HALF)
         call("moda_chain_trunk_bwd", ptr(d_dfe), ptr(gsig), ptr(_al16(Ws.reshape(-1))), ptr(sc), ptr(wpackT), bits.data_ptr(), P,
-             ptr(d_fin), ptr(dY), ptr(d_pe), config.chain_mode(), stream())
+             ptr(d_fin), ptr(dY), ptr(d_pe), mode, stream())
         # weight gradients (bias gradients ride along as column sums of the dY operand)
         gxyz = torch.empty(P, 3, device=dev, dtype=torch.float32)
         wa, _ = _win_array(win)
         # the eight 256 x 256 weight gradients (final layer, layers 8..6, the hidden part of layer 5, layers 4..2) in
         # ONE launch, the two PE-input ones (layers 5 and 1) in another
-        big = [(d_fin, H[7], g[16], 0, 256, 256, g[17])]
+        big = [] if fold else [(d_fin, H[7], g[16], 0, 256, 256, g[17])]
         for i in range(7, 0, -1):
             big.append((dY[i], H[i - 1], g[2 * i], 63 if i == 4 else 0, 256, 256, g[2 * i + 1]))
         pe_jobs = [(dY[4], A0, g[8], 0, 256, 63, None), (dY[0], A0, g[0], 0, 256, 63, g[1])]
         pe_bwd = lambda: call("moda_pe16_bwd", ptr(xyz), ptr(d_pe), None, 64, ptr(gxyz), P, len(win), wa, ptr(isc), 0, stream())
+        if fold:
+            # folded layer: dW' = d_dfe^T H8 and db' into scratch, then mapped back to dWdir / dWfinal / dbfinal
+            gWp = torch.zeros(128, 256, device=dev, dtype=torch.float32)
+            dbp = grb.sum(0)   # db' = column sums of d_dfe = sum of the per-ray sums
+
+            def dir_wgrad():
+                _wgrad(d_dfe, 128, H[7], 256, P, gWp, 0, 128, 256, isc)
+                _unfold_grads(gWp, dbp, Wf, bf, Wd, 256, g[16], g[17], g[18])
+        else:
+            gWp = dbp = None
+            dir_wgrad = lambda: _wgrad(d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
         q = _side_queue(dev, gret)
         if q is not None:   # weight gradients off the critical path: joined at the end of the backward pass
-            q.fork(d_dfe, fin, d_fin, H, dY, A0, isc, g)
+            q.fork(d_dfe, fin, d_fin, H, dY, A0, isc, g, gWp, dbp, params)
             q.run(_wgrad_multi, big, 256, 256, P, isc)
-            q.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+            q.run(dir_wgrad)
             q.run(_wgrad_multi, pe_jobs, 256, 64, P, isc)
             pe_bwd()
         else:
             with _Alternate(dev) as alt:   # the launches below are independent of each other
-                alt.run(_wgrad, d_dfe, 128, fin, 256, P, g[18], 0, 128, 256, isc)
+                alt.run(dir_wgrad)
                 alt.run(_wgrad_multi, big, 256, 256, P, isc)
                 alt.run(_wgrad_multi, pe_jobs, 256, 64, P, isc)
                 alt.run(pe_bwd)
@@ -367,26 +413,29 @@ class TrunkChainFn(torch.autograd.Function):
 WD = 64
 
 
-def pack_skin_fwd(params, nc):
-    """(64, 18*64) fp16: per layer [Whi | Wlo], order documented at moda_chain_skin_fwd."""
+def pack_skin_fwd(params, nc, fold=None):
+    """(64, 18*64) fp16: per layer [Whi | Wlo], order documented at moda_chain_skin_fwd (fold: (64, 16*64), W' (32, 64) in
+    place of [Wfinal, Wdir])."""
     W = [params[2 * i] for i in range(5)]
     Wf, Wd, Wr = params[10], params[12], params[16]
-    out = torch.zeros(64, 18 * 64, device=W[0].device, dtype=HALF)
-    blocks = [(W[0], 63, 0), (W[1], 64, 0), (W[2], 64, 0), (W[3], 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc),
-              (Wf, 64, 0), (Wd, 64, 0), (Wr, 32, 0)]
+    tail = [(fold, 64, 0)] if fold is not None else [(Wf, 64, 0), (Wd, 64, 0)]
+    blocks = [(W[0], 63, 0), (W[1], 64, 0), (W[2], 64, 0), (W[3], 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc)] + tail + [(Wr, 32, 0)]
+    out = torch.zeros(64, 2 * len(blocks) * 64, device=W[0].device, dtype=HALF)
     pk = _Packer(out)
     for i, (w, cols, col0) in enumerate(blocks):
         pk.add(w, cols, col0, 128 * i, 64, 64, False, lo_col0=128 * i + 64)
     return pk.run()
 
 
-def pack_skin_bwd(params, nc):
-    """(64, 9*64) fp16 transposed (hi) weights, order documented at moda_chain_skin_bwd."""
+def pack_skin_bwd(params, nc, fold=None):
+    """(64, 9*64) fp16 transposed (hi) weights, order documented at moda_chain_skin_bwd (fold: (64, 8*64), W'^T in place
+    of [Wdir^T, Wfinal^T])."""
     W = [params[2 * i] for i in range(5)]
     Wf, Wd, Wr = params[10], params[12], params[16]
-    out = torch.zeros(64, 9 * 64, device=W[0].device, dtype=HALF)
-    blocks = [(Wr, 32, 0), (Wd, 64, 0), (Wf, 64, 0), (W[4], 63, 0), (W[4], 64, 63 + nc), (W[3], 64, 0), (W[2], 64, 0),
-              (W[1], 64, 0), (W[0], 63, 0)]
+    head = [(fold, 64, 0)] if fold is not None else [(Wd, 64, 0), (Wf, 64, 0)]
+    blocks = [(Wr, 32, 0)] + head + [(W[4], 63, 0), (W[4], 64, 63 + nc), (W[3], 64, 0), (W[2], 64, 0), (W[1], 64, 0),
+                                     (W[0], 63, 0)]
+    out = torch.zeros(64, len(blocks) * 64, device=W[0].device, dtype=HALF)
     pk = _Packer(out)
     for i, (w, cols, col0) in enumerate(blocks):
         pk.add(w, cols, col0, 64 * i, 64, 64, True)
@@ -421,26 +470,28 @@ class SkinChainFn(torch.autograd.Function):
             rb5 = _small_linear(code, W[4], 63, b[4], 64)
         else:
             rb1, rb5 = _al16(b[0].reshape(1, 64)), _al16(b[4].reshape(1, 64))
+        fold = config.fold_final
+        Wp, bp = _fold(params[10], bf, params[12], bd, 64) if fold else (None, bd)
         pad = torch.zeros(2, 64, device=dev, dtype=torch.float32)
-        pad[0, :bd.shape[0]] = bd
+        pad[0, :bd.shape[0]] = bp
         pad[1, :oc] = br
-        wpack = pack_skin_fwd(params, nc)
+        wpack = pack_skin_fwd(params, nc, Wp)
         biases = (ctypes.c_void_p * 8)(ptr(rb1), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(rb5), ptr(bf), ptr(pad[0]), ptr(pad[1]))
         out = torch.empty(P, 32, device=dev, dtype=torch.float32)
         if need_bw:
             A0 = torch.empty(P, WD, device=dev, dtype=HALF)
             H = torch.empty(5, P, WD, device=dev, dtype=HALF)
-            fin = torch.empty(P, WD, device=dev, dtype=HALF)
+            fin = None if fold else torch.empty(P, WD, device=dev, dtype=HALF)
             dfe = torch.empty(P, WD, device=dev, dtype=HALF)
             bits = torch.empty(6, T, 2, TILE, device=dev, dtype=torch.int64)
         else:
             A0 = H = fin = dfe = bits = None
         call("moda_chain_skin_fwd", ptr(pts), P, rep, len(win), wa, ptr(wpack), biases, ptr(A0), ptr(H), ptr(fin),
-             ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(out), stream())
+             ptr(dfe), bits.data_ptr() if bits is not None else None, ptr(out), int(fold), stream())
         if need_bw:
             ctx.save_for_backward(pts, code, *params)
             ctx.act = (A0, H, fin, dfe, bits)
-            ctx.meta = (S, win, rep, pshape, oc)
+            ctx.meta = (S, win, rep, pshape, oc, fold)
         return out
 
     @staticmethod
@@ -448,19 +499,21 @@ class SkinChainFn(torch.autograd.Function):
         pts, code = ctx.saved_tensors[:2]
         params = list(ctx.saved_tensors[2:])
         A0, H, fin, dfe, bits = ctx.act
-        S, win, rep, pshape, oc = ctx.meta
+        S, win, rep, pshape, oc, fold = ctx.meta
         P, dev = pts.shape[0], pts.device
         Rc, nc = code.shape
         W = [params[2 * i] for i in range(5)]
         g, gret = _grad_targets(ctx.param_refs, params)
         gout = f32(gout).reshape(P, 32)
         sc, isc = _loss_scale(gout)
-        wpackT = pack_skin_bwd(params, nc)
+        Wf, bf, Wd, bd = params[10], params[11], params[12], params[13]
+        wpackT = pack_skin_bwd(params, nc, _fold(Wf, bf, Wd, bd, 64)[0] if fold else None)
         h16 = lambda: torch.empty(P, WD, device=dev, dtype=HALF)
-        G, d_dfe, d_fin, d_pe = h16(), h16(), h16(), h16()
+        G, d_dfe, d_pe = h16(), h16(), h16()
+        d_fin = None if fold else h16()
         dY = torch.empty(5, P, WD, device=dev, dtype=HALF)
         call("moda_chain_skin_bwd", ptr(gout), ptr(sc), ptr(wpackT), bits.data_ptr(), P, ptr(G), ptr(d_dfe), ptr(d_fin),
-             ptr(dY), ptr(d_pe), stream())
+             ptr(dY), ptr(d_pe), int(fold), stream())
         gcode = torch.zeros_like(code)
 
         def code_part(dYl, Wl, gW, gb, rbg=None):
@@ -485,10 +538,23 @@ class SkinChainFn(torch.autograd.Function):
         wa, _ = _win_array(win)
         # all nine 64 x 64 weight gradients of the evaluation in ONE launch (bias gradients ride along; for a single
         # shared pose-code row the column sums of dY[4] / dY[0] double as the code-part reductions)
+        if fold:
+            # folded layer: dW' = d_dfe^T H5 and db' into scratch, mapped back to dWdir / dWfinal / dbfinal after the launch
+            gWp = torch.zeros(32, 64, device=dev, dtype=torch.float32)
+            dbp = torch.zeros(32, device=dev, dtype=torch.float32)
+            mid = [(d_dfe, H[4], gWp, 0, 32, 64, dbp)]
+        else:
+            gWp = dbp = None
+            mid = [(d_dfe, fin, g[12], 0, 32, 64, g[13]), (d_fin, H[4], g[10], 0, 64, 64, g[11])]
         jobs = [(dY[4], A0, g[8], 0, 64, 63, rb4), (dY[0], A0, g[0], 0, 64, 63, rb0),
-                (G, dfe, g[16], 0, oc, 32, g[17]), (d_dfe, fin, g[12], 0, 32, 64, g[13]), (d_fin, H[4], g[10], 0, 64, 64, g[11]),
-                (dY[4], H[3], g[8], 63 + nc, 64, 64, None)]
+                (G, dfe, g[16], 0, oc, 32, g[17])] + mid + [(dY[4], H[3], g[8], 63 + nc, 64, 64, None)]
         jobs += [(dY[i], H[i - 1], g[2 * i], 0, 64, 64, g[2 * i + 1]) for i in (3, 2, 1)]
+
+        def rest_jobs(js):
+            _wgrad_multi(js, WD, WD, P, isc)
+            if fold:
+                _unfold_grads(gWp, dbp, Wf, bf, Wd, 64, g[10], g[11], g[12])
+                g[13].add_(dbp)
         want_pts = ctx.needs_input_grad[0]   # e.g. nerf_vis is evaluated on detached points (loss_utils.py:125-149)
         pe_bwd = lambda: want_pts and call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, WD, ptr(gpts), P, len(win), wa,
                                            ptr(isc), 0, stream())
@@ -498,13 +564,13 @@ class SkinChainFn(torch.autograd.Function):
             # the end of the backward pass
             if shared_row:
                 _wgrad_multi(jobs[:2], WD, WD, P, isc)
-            q.fork(G, dfe, d_dfe, fin, d_fin, H, dY, A0, isc, g)
-            q.run(_wgrad_multi, jobs[2:] if shared_row else jobs, WD, WD, P, isc)
+            q.fork(G, dfe, d_dfe, fin, d_fin, H, dY, A0, isc, g, gWp, dbp, params)
+            q.run(rest_jobs, jobs[2:] if shared_row else jobs)
             pe_bwd()
             code_part(dY[4], W[4], g[8], g[9], rb4)
             code_part(dY[0], W[0], g[0], g[1], rb0)
         else:
-            _wgrad_multi(jobs, WD, WD, P, isc)
+            rest_jobs(jobs)
             with _Alternate(dev) as alt:
                 alt.run(pe_bwd)
                 code_part(dY[4], W[4], g[8], g[9], rb4)

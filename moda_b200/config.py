@@ -52,6 +52,12 @@ def set_trunk_slots(n):
     trunk_slots = n
 
 
+# fold_final: the chains run xyz_encoding_final and dir_encoding (two linear maps in a row, nerf.py:182-190) as ONE layer
+# with the product weights W' = Wdir[:, :W] Wfinal: one step less per pass, one saved activation and one gradient less,
+# one weight-gradient job less; dW' is mapped back to dWdir / dWfinal with two small products.  MODA_B200_FOLD_FINAL=0: off.
+fold_final = os.environ.get("MODA_B200_FOLD_FINAL", "1") != "0"
+
+
 def chain_mode():
-    """The `mode` argument of moda_chain_trunk_*: bit 0 = CTA pairs, bit 1 = two tile slots."""
-    return (1 if trunk_pair else 0) | (2 if (trunk_pair and trunk_slots == 2) else 0)
+    """The `mode` argument of moda_chain_trunk_*: bit 0 = CTA pairs, bit 1 = two tile slots, bit 2 = final layer folded."""
+    return (1 if trunk_pair else 0) | (2 if (trunk_pair and trunk_slots == 2) else 0) | (4 if fold_final else 0)

@@ -654,7 +654,16 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   constexpr int PE_ROWS = TILE_M / PE_THREADS;                   // rows per producer thread
   constexpr bool DUAL = (SLOTS == 2) && (MODA_DUAL_ISSUE != 0);  // one MMA-issuing warp per tile slot (warps 0 and 1)
   constexpr int W_PROD = DUAL ? (3 + SLOTS * EPI_WARPS) : 0;     // warp that streams the weights
-  constexpr int PE_ARRIVALS = DUAL ? 4 : PE_WARPS;               // warps that write (and arrive on) a PE chunk
+  // EPI_PE: the positional encoding of a slot's next tile is written by its epilogue warps (one row per thread) instead
+  // of the PE warp.  Always with two issuers (no warp left for it); for the 64-wide forward program because its single
+  // PE warp needs ~19k cycles per tile (split hi/lo rows) and the PE chunk is single-buffered, so that time adds to the
+  // 20k cycles of the five steps that read the chunk: 39k cycles per tile and CTA (profiles/r02_s12_trace_skin_fwd.txt).
+  // Four warps write the same rows in a quarter of the time, right after the last step that reads the old chunk.
+#ifndef MODA_SKIN_EPI_PE
+#define MODA_SKIN_EPI_PE 1
+#endif
+  constexpr bool EPI_PE = DUAL || (BOX_ROWS == 64 && EPI_WARPS == 4 && MODA_SKIN_EPI_PE != 0);
+  constexpr int PE_ARRIVALS = EPI_PE ? 4 : PE_WARPS;             // warps that write (and arrive on) a PE chunk
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -951,7 +960,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
     // DUAL: the four h == 0 warps of the slot write the PE chunk of the slot's NEXT tile (thread = row, as in the
     // epilogue) right after the epilogue of the last step that reads the current one -- its acc_full says those MMAs
     // have completed, and the chunk's TMA save was waited for by the issuer steps earlier
-    const bool pe_duty = DUAL && pg.pe_chunk >= 0 && h == 0;
+    const bool pe_duty = EPI_PE && pg.pe_chunk >= 0 && h == 0;
     auto pe_fetch = [&](int tile_n, float (&x)[3]) {
       const long long row = (long long)tile_n * TILE_M + trow;
 #pragma unroll
@@ -963,6 +972,7 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&ready_slot[pg.pe_chunk]);
+        if (pg.pe_lo) mbar_arrive(&ready_slot[pg.pe_chunk + 1]);
         if (PAIR) mbar_arrive_remote(cx.ready2_remote + 8u * (uint32_t)pg.pe_chunk);
       }
     };
@@ -1153,7 +1163,8 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
   } else if (!DUAL && warp < 2 + SLOTS * EPI_WARPS + PE_WARPS) {
     // ================================================================== positional-encoding producers
     // (two tile slots: the one producer warp serves them alternately, in the order the tiles start)
-    if (pg.pe_chunk >= 0) {
+    // EPI_PE: the epilogue warps write the PE chunks; this warp only keeps the thread layout
+    if (pg.pe_chunk >= 0 && !EPI_PE) {
       const int pw = warp - 2 - SLOTS * EPI_WARPS;
       const bool lead = (pw == 0) && lane == 0;
       (void)lead;
@@ -1285,7 +1296,11 @@ using namespace moda::chain;
 // two tiles in flight per CTA (needs bit 0).  The only process-wide state is (a) a sticky flag that a cluster launch
 // failed once on this process's device/partition (then every later call uses the single-CTA kernels) and (b) the debug
 // trace hook below, both atomics.
-constexpr int MODE_PAIR = 1, MODE_TWO_SLOTS = 2;
+// bit 2 = xyz_encoding_final folded into dir_encoding: the reference applies final (no activation) and then the direction
+// layer to [final | dir | env] (nerf.py:182-190), i.e. two linear maps in a row; the caller hands in the product weights
+// W' = Wdir[:, :256] Wfinal (and the bias Wdir[:, :256] bfinal inside the per-ray bias), and the programs run one
+// 256-wide step less per pass (and save / re-read one (P,256) activation and one gradient less).
+constexpr int MODE_PAIR = 1, MODE_TWO_SLOTS = 2, MODE_FOLD_FINAL = 4;
 static std::atomic<int> g_pair_unavailable{0};
 static std::atomic<long long*> g_trace{nullptr};
 constexpr int PAIR_UNAVAILABLE = -77;   // launch<..., PAIR = 1> could not place the cluster: the caller relaunches single-CTA
@@ -1506,7 +1521,7 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     st.save_map = b.save(H ? (const char*)H + (size_t)l * P * 256 * 2 : nullptr, P, 256);
     b.out(st, 0, 4);
   }
-  {
+  if (!(mode & MODE_FOLD_FINAL)) {
     Step& st = b.add(256, 0);           // xyz_encoding_final (no activation)
     st.bias = biases[8];
     for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
@@ -1515,7 +1530,8 @@ extern "C" int moda_chain_trunk_fwd(const float* xyz, long long P, int rep, int 
     b.out(st, 0, 4);
   }
   {
-    Step& st = b.add(128, E_RELU | E_HEAD_RGB);   // dir_encoding on [fin | per-ray constant part as a bias]
+    // dir_encoding on [fin | per-ray constant part as a bias]; folded: on the layer-8 activations with W' (chunks 30-33)
+    Step& st = b.add(128, E_RELU | E_HEAD_RGB);
     st.rowbias = rowbias;
     for (int i = 0; i < 4; ++i) b.k(st, order[i], col + order[i]);
     col += 4;
@@ -1570,7 +1586,8 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
                                     const void* wpackT, const unsigned int* maskbits, long long P, void* d_fin,
                                     void* dY, void* d_pe, int mode, cudaStream_t stream) {
   if (P == 0) return 0;
-  MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && d_fin && dY && d_pe, "chain_trunk_bwd: null pointer");
+  const bool fold = (mode & MODE_FOLD_FINAL) != 0;   // wpackT: chunks 0-1 = W'^T, then W8^T ...: no d_fin step
+  MODA_REQUIRE(d_dfe && gsig && ws && wpackT && maskbits && (d_fin || fold) && dY && d_pe, "chain_trunk_bwd: null pointer");
   MODA_REQUIRE(al16(d_dfe) && al16(wpackT), "chain_trunk_bwd: d_dfe and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
@@ -1582,19 +1599,20 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
   const int order[4] = {0, 1, 2, 3};
   auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 256 * 2; };
   { Step& st = b.add(128, E_LOAD16); b.out(st, 0, 2); }
-  {
+  if (!fold) {
     Step& st = b.add(256, 0);                       // d_fin = d_dfe Wdir[:, :256]
     b.k(st, 0, 0); b.k(st, 1, 1);
     st.save_map = b.save(d_fin, P, 256);
     b.out(st, 0, 4);
   }
   {
-    Step& st = b.add(256, E_RANK1 | E_MASK_IN);     // dY[7] = (d_fin Wfinal + gsig ws) . [H8 > 0]
-    for (int i = 0; i < 4; ++i) b.k(st, order[i], 2 + order[i]);
+    Step& st = b.add(256, E_RANK1 | E_MASK_IN);     // dY[7] = (d_fin Wfinal + gsig ws) . [H8 > 0]; folded: d_dfe W'
+    if (fold) { b.k(st, 0, 0); b.k(st, 1, 1); }
+    else for (int i = 0; i < 4; ++i) b.k(st, order[i], 2 + order[i]);
     st.mask_slot = 7; st.save_map = b.save(dy(7), P, 256);
     b.out(st, 0, 4);
   }
-  int col = 6;
+  int col = fold ? 2 : 6;
   for (int l = 7; l >= 1; --l) {
     if (l == 4) {
       Step& sx = b.add(64, 0);                      // dPE partial = dY[4] W5[:, :63], parked in the SX chunk
@@ -1628,7 +1646,7 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
 // non-null: A0 (P,64), H (5,P,64), fin (P,64), dfe (P,64), maskbits (6, tiles, 2, 128): H1..H5, dfe.
 extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const float* win, const void* wpack,
                                    const float* const* biases, void* A0, void* H, void* fin, void* dfe,
-                                   unsigned int* maskbits, float* y32, cudaStream_t stream) {
+                                   unsigned int* maskbits, float* y32, int fold, cudaStream_t stream) {
   if (P == 0) return 0;
   MODA_REQUIRE(xyz && wpack && biases && y32 && rep > 0 && F >= 0 && F <= 10, "chain_skin_fwd: bad arguments");
   MODA_REQUIRE(al16(biases[0]) && al16(biases[4]) && al16(y32) && al16(wpack),
@@ -1651,11 +1669,17 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
     st.save_map = b.save(H ? (const char*)H + (size_t)l * P * 64 * 2 : nullptr, P, 64);
     b.out(st, AH, 1, AL);
   }
-  { Step& st = b.add(64, 0); st.bias = biases[5]; split(st, AH, AL, 12); st.save_map = b.save(fin, P, 64); b.out(st, AH, 1, AL); }
-  { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, 14);
+  // fold: xyz_encoding_final folded into dir_encoding (see MODE_FOLD_FINAL): wpack holds W' in place of Wfinal and
+  // Wdir (16 chunks), biases[5] is ignored and biases[6] = bdir + Wdir bfinal
+  int wc = 12;
+  if (!fold) {
+    Step& st = b.add(64, 0); st.bias = biases[5]; split(st, AH, AL, wc); wc += 2;
+    st.save_map = b.save(fin, P, 64); b.out(st, AH, 1, AL);
+  }
+  { Step& st = b.add(64, E_RELU | mo); st.mask_slot = 5; st.bias = biases[6]; split(st, AH, AL, wc); wc += 2;
     st.save_map = b.save(dfe, P, 64); b.out(st, AH, 1, AL); }
-  { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, 16); }
-  return launch<64, MODA_SKIN_EPI, 1, 2, P_FWD>(b, wpack, 64, 18 * 64, stream);
+  { Step& st = b.add(64, E_OUT_F32); st.bias = biases[7]; split(st, AH, AL, wc); wc += 2; }
+  return launch<64, MODA_SKIN_EPI, 1, 2, P_FWD>(b, wpack, 64, wc * 64, stream);
 }
 
 // Adjoint chain of nerf_skin on plain fp16 operands.  wpackT: fp16 (64, 9*64), rows = input channel, cols = output:
@@ -1665,9 +1689,10 @@ extern "C" int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F
 // Out (fp16, 64 columns): G = scale * gout, d_dfe, d_fin, dY (5,P,64), d_pe.
 extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const void* wpackT,
                                    const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
-                                   void* dY, void* d_pe, cudaStream_t stream) {
+                                   void* dY, void* d_pe, int fold, cudaStream_t stream) {
   if (P == 0) return 0;
-  MODA_REQUIRE(gout && wpackT && maskbits && G && d_dfe && d_fin && dY && d_pe, "chain_skin_bwd: null pointer");
+  // fold: wpackT = [Wrgb^T, W'^T, W5[:, :63]^T, ...] (8 chunks), no d_fin step (see MODE_FOLD_FINAL)
+  MODA_REQUIRE(gout && wpackT && maskbits && G && d_dfe && (d_fin || fold) && dY && d_pe, "chain_skin_bwd: null pointer");
   MODA_REQUIRE(al16(gout) && al16(wpackT), "chain_skin_bwd: gout and wpackT must be 16-byte aligned");
   Builder b;
   Program& pg = b.pg;
@@ -1678,15 +1703,16 @@ extern "C" int moda_chain_skin_bwd(const float* gout, const float* scale, const 
   auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 64 * 2; };
   { Step& st = b.add(64, E_LOAD32); st.save_map = b.save(G, P, 64); b.out(st, A, 1); }
   { Step& st = b.add(64, E_MASK_IN); b.k(st, A, 0); st.mask_slot = 5; st.save_map = b.save(d_dfe, P, 64); b.out(st, A, 1); }
-  { Step& st = b.add(64, 0); b.k(st, A, 1); st.save_map = b.save(d_fin, P, 64); b.out(st, A, 1); }
-  { Step& st = b.add(64, E_MASK_IN); b.k(st, A, 2); st.mask_slot = 4; st.save_map = b.save(dy(4), P, 64); b.out(st, A, 1); }
-  { Step& st = b.add(64, 0); b.k(st, A, 3); b.out(st, SX, 1); }
+  int wc = 1;
+  if (!fold) { Step& st = b.add(64, 0); b.k(st, A, wc++); st.save_map = b.save(d_fin, P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, E_MASK_IN); b.k(st, A, wc++); st.mask_slot = 4; st.save_map = b.save(dy(4), P, 64); b.out(st, A, 1); }
+  { Step& st = b.add(64, 0); b.k(st, A, wc++); b.out(st, SX, 1); }
   for (int l = 4; l >= 1; --l) {
     Step& st = b.add(64, E_MASK_IN);
-    b.k(st, A, 4 + (4 - l));
+    b.k(st, A, wc++);
     st.mask_slot = l - 1; st.save_map = b.save(dy(l - 1), P, 64);
     b.out(st, A, 1);
   }
-  { Step& st = b.add(64, E_ADD_SX); b.k(st, A, 8); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
-  return launch<64, MODA_SKIN_EPI, 1, MODA_SKIN_BWD_CTAS, P_BWD>(b, wpackT, 64, 9 * 64, stream);
+  { Step& st = b.add(64, E_ADD_SX); b.k(st, A, wc++); st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
+  return launch<64, MODA_SKIN_EPI, 1, MODA_SKIN_BWD_CTAS, P_BWD>(b, wpackT, 64, wc * 64, stream);
 }

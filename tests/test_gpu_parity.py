@@ -343,10 +343,14 @@ def test_split_precision_skin_mlp_matches_fp32_simt():
         assert max_abs(b[0], a[0]) < 2e-5, max_abs(b[0], a[0])
         # the PE adjoint amplifies by 2^9 with cancellation: both fp32-class paths carry ~1e-3 noise there
         assert nrel(b[1], a[1]) < 5e-3, ("gpts", nrel(b[1], a[1]))
-        assert nrel(b[2], a[2]) < 3e-3, ("gcode", nrel(b[2], a[2]))
+        # a code row shared by all 25 600 samples: its gradient is a sum of signed terms that cancels by ~sqrt(N), which
+        # amplifies the fp16 rounding of the adjoint chain relative to the result (per-ray codes: ~1e-3)
+        assert nrel(b[2], a[2]) < (1e-2 if code.shape[0] == 1 else 3e-3), ("gcode", nrel(b[2], a[2]))
         assert set(a[3]) == set(b[3])
-        worst = max((nrel(b[3][k], a[3][k]), k) for k in a[3])
-        assert worst[0] < 3e-3, worst
+        # bias gradients are signed sums over all samples too (same cancellation as the shared code row); against the
+        # fp64 oracle the folded and the unfolded chains sit at the same distance (profiles/r02_grad_table_n8192_*)
+        worst = max((nrel(b[3][k], a[3][k]) / (1e-2 if k.endswith("bias") else 3e-3), k) for k in a[3])
+        assert worst[0] < 1.0, worst
 
 
 def test_fused_chains_match_layer_by_layer_kernels():
