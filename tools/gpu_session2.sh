@@ -11,7 +11,7 @@ python tools/launch_summary.py $out/launches.csv > $out/launches.summary.txt; he
 NCU="ncu --set full --clock-control none --import-source on"
 timeout 600 $NCU -k regex:chain_kernel --launch-skip 2 -c 2 -f -o $out/chain_trunk python tools/chain_profile.py trunk > $out/ncu_trunk.log 2>&1
 timeout 600 $NCU -k regex:chain_kernel --launch-skip 2 -c 2 -f -o $out/chain_skin python tools/chain_profile.py skin > $out/ncu_skin.log 2>&1
-timeout 600 $NCU -k regex:tc_wgrad --launch-skip 6 -c 4 -f -o $out/wgrad python tools/chain_profile.py trunk > $out/ncu_wgrad.log 2>&1
+timeout 600 $NCU -k regex:tc_wgrad --launch-skip 3 -c 3 -f -o $out/wgrad python tools/chain_profile.py trunk > $out/ncu_wgrad.log 2>&1
 timeout 600 $NCU -k regex:chain_kernel --launch-skip 4 -c 1 -f -o $out/chain_sigma python bench.py --workload grid --steps 1 --warmup 3 --no-cpu > $out/ncu_sigma.log 2>&1
 timeout 600 $NCU -k regex:skin_warp_fwd --launch-skip 10 -c 2 -f -o $out/skinwarp_delta python bench.py --workload dqs --steps 1 --warmup 3 --no-cpu > $out/ncu_dqs.log 2>&1
 timeout 600 $NCU -k regex:skin_warp --launch-skip 12 -c 4 -f -o $out/skinwarp python bench.py --steps 1 --warmup 3 --no-cpu --no-extra --graph off > $out/ncu_skinwarp.log 2>&1
