@@ -81,6 +81,32 @@ def _traffic(entries):
     return sum(vals) / len(vals), d.get("source")
 
 
+def _step_dram(per_entry):
+    """DRAM bytes of one training step as far as the committed ncu captures cover it: per-launch bytes of profiles/traffic.json
+    x the launches per step counted here (the multi-job weight-gradient launches by their shape).  Returns (bytes, covered
+    kernels, C-ABI entries without a capture)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, [], []
+    k = json.load(open(p)).get("kernels", {})
+    n = lambda e: per_entry.get(e, (0, 0))[0]
+    # launches per step of each captured kernel: the trunk pass has one 256x256 multi-job weight-gradient launch, one
+    # 256x64 (PE inputs) and one single 128x256 (direction layer); each nerf_skin evaluation one 64x64 multi-job launch
+    plan = [("moda_chain_trunk_fwd", n("moda_chain_trunk_fwd")), ("moda_chain_trunk_bwd", n("moda_chain_trunk_bwd")),
+            ("moda_chain_skin_fwd", n("moda_chain_skin_fwd")), ("moda_chain_skin_bwd", n("moda_chain_skin_bwd")),
+            ("moda_tc_wgrad_multi<256,256>", n("moda_chain_trunk_bwd")), ("moda_tc_wgrad_multi<256,64>", n("moda_chain_trunk_bwd")),
+            ("moda_tc_wgrad<128,256>", n("moda_tc_wgrad")), ("moda_tc_wgrad_multi<64,64>", n("moda_chain_skin_bwd")),
+            ("moda_skin_warp_fwd", n("moda_skin_warp_fwd")), ("moda_skin_warp_bwd", n("moda_skin_warp_bwd"))]
+    tot, have, miss = 0.0, [], []
+    for key, cnt in plan:
+        if cnt and key in k:
+            tot += k[key]["dram_bytes_per_launch"] * cnt
+            have.append(key)
+        elif cnt:
+            miss.append(key)
+    return tot, have, miss
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU during the timed region (B200_PROFILING.md clocks line).
     NVML in a thread (a query takes well under a millisecond, so a 60 ms timed region still yields a dozen samples);
@@ -432,7 +458,17 @@ def run_ours(args):
                                    "achieved": round(agg, 3), "frac": round(agg / peak, 5),
                                    "share_of_step": round(lin_ms / tot_ms, 4)},
                 "all_kernels_ms_per_step": round(tot_ms, 3),
+                # the chains run xyz_encoding_final folded into dir_encoding: `achieved` keeps the
+                # ALGORITHMIC count of SURVEY 8(d) as its numerator, the tensor cores execute 65 536 MAC per sample less
+                "executed_flop_per_launch": 2.0 * (TRUNK_MAC_PER_SAMPLE - (65536 if _cfg.fold_final else 0)) * P,
                 "per_entry_ms": {k: round(ms, 3) for k, (n, ms) in sorted(per_entry.items(), key=lambda kv: -kv[1][1])}}
+        sd, sd_have, sd_miss = _step_dram({k: v for k, v in per_entry.items()})
+        if sd is not None:
+            hbm = peaks.get("hbm_gbs")
+            roof["step_dram_bytes"] = sd
+            roof["step_dram_note"] = ("ncu per-launch DRAM bytes x launches per step; captured: %s; not captured: %s%s"
+                                      % (", ".join(sd_have), ", ".join(sd_miss) or "-",
+                                         ("; = %.2f ms at the measured %.0f GB/s" % (sd / hbm / 1e6, hbm)) if hbm else ""))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_rays=args.cpu_rays, repeats=2)

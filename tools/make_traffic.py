@@ -18,6 +18,8 @@ NAMES = [(_chain(128, 0), "moda_chain_trunk_fwd"), (_chain(128, 1), "moda_chain_
          (r"tc_wgrad_kernel<%s256, %s256>" % (_T, _T), "moda_tc_wgrad<256,256>"),
          (r"tc_wgrad_multi_kernel<%s256, %s256>" % (_T, _T), "moda_tc_wgrad_multi<256,256>"),
          (r"tc_wgrad_multi_kernel<%s64, %s64>" % (_T, _T), "moda_tc_wgrad_multi<64,64>"),
+         (r"tc_wgrad_multi_kernel<%s256, %s64>" % (_T, _T), "moda_tc_wgrad_multi<256,64>"),
+         (r"tc_wgrad_kernel<%s128, %s256>" % (_T, _T), "moda_tc_wgrad<128,256>"),
          (r"skin_warp_fwd", "moda_skin_warp_fwd"), (r"skin_warp_bwd", "moda_skin_warp_bwd")]
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tag, reps = sys.argv[1], sys.argv[2:]
