@@ -1,0 +1,133 @@
+"""GPU tests of the second round-2 session: the multi-job weight-gradient kernel against an fp64 product, the folded
+final layer against the unfolded chain programs, and the deferred weight-gradient join against the in-Function join."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _nrel(x, y):
+    return float((x.double() - y.double()).norm() / (y.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (128, 128)])
+def test_wgrad_multi_against_fp64_product(N, K):
+    """dW[j] (first n_valid rows / k_valid columns, at a column offset of a wider matrix) += oscale dY[j]^T X[j] and
+    dbias[j] += oscale colsum(dY[j]) for several jobs of one shape in one launch; M not a multiple of the 64-row chunk,
+    fewer chunks than CTAs for the last job count."""
+    from moda_b200 import chain_tc
+    gen = torch.Generator().manual_seed(N * 1000 + K)
+    for M, njobs in ((4096 + 37, 3), (200, 9), (64 * 148 * 2 + 5, 2)):
+        osc = torch.tensor([0.25], device=DEV)
+        jobs, refs = [], []
+        for j in range(njobs):
+            dY = (torch.randn(M, N, generator=gen) * 0.5).to(DEV).half()
+            X = torch.randn(M, K, generator=gen).to(DEV).half()
+            n_valid = N if j % 2 == 0 else N - 7
+            k_valid = K if j % 3 == 0 else K - 1
+            col0 = 0 if j % 2 == 0 else 5
+            dW = torch.randn(N, K + 9, generator=gen).to(DEV)
+            db = torch.randn(N, generator=gen).to(DEV) if j % 2 == 0 else None
+            ref_w = dW.double().clone()
+            ref_w[:n_valid, col0:col0 + k_valid] += 0.25 * (dY.double().t() @ X.double())[:n_valid, :k_valid]
+            ref_b = None if db is None else db.double() + 0.25 * torch.cat([dY.double().sum(0)[:n_valid],
+                                                                              torch.zeros(N - n_valid, device=DEV, dtype=torch.float64)])
+            jobs.append((dY, X, dW, col0, n_valid, k_valid, db))
+            refs.append((ref_w, ref_b))
+        chain_tc._wgrad_multi(jobs, N, K, M, osc)
+        torch.cuda.synchronize()
+        for j, ((dY, X, dW, col0, n_valid, k_valid, db), (ref_w, ref_b)) in enumerate(zip(jobs, refs)):
+            scale = float((ref_w - dW.double()).abs().max() / ref_w.abs().max())
+            assert scale < 2e-6, (M, njobs, j, "dW", scale)
+            if db is not None:
+                e = float((ref_b - db.double()).abs().max() / ref_b.abs().max())
+                assert e < 2e-6, (M, njobs, j, "dbias", e)
+
+
+def _mlp_pass(model, emb, pts, code, dirs, w):
+    from moda_b200 import geom_utils as G
+    model.zero_grad()
+    p = pts.clone().requires_grad_(True)
+    c = code.clone().requires_grad_(True)
+    if dirs is not None:
+        d = dirs.clone().requires_grad_(True)
+        out = G.evaluate_mlp(model, p, embed_xyz=emb, dir_embedded=d, code=c)
+    else:
+        out = G.evaluate_mlp(model, p, embed_xyz=emb, code=c)
+    (out * w).sum().backward()
+    return out.detach(), p.grad, c.grad, {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}
+
+
+def test_folded_final_layer_matches_unfolded_chain_programs():
+    """xyz_encoding_final folded into dir_encoding (config.fold_final) is the same mathematics: both
+    chain programs agree to fp16-operand rounding on outputs and on every gradient, including those of the two layers that
+    were folded (their gradients are mapped back from dW')."""
+    from moda_b200 import config, synth, models as MM
+    config.set_precision("fp16")
+    prob = synth.make_problem(8, seed=0)
+    models, emb, _ = MM.build_models(prob, DEV)
+    gen = torch.Generator().manual_seed(11)
+    R, S = 300, 128   # 300 tiles: two waves of the CTA-pair kernels with a ragged tail
+    pts = (torch.rand(R, S, 3, generator=gen) * 0.6 - 0.3).to(DEV)
+    was = config.fold_final
+    try:
+        for name, code, dirs, wshape in (("coarse", (0.1 * torch.randn(R, 64, generator=gen)).to(DEV),
+                                          torch.randn(R, 27, generator=gen).to(DEV), 4),
+                                         ("nerf_skin", (0.1 * torch.randn(R, 128, generator=gen)).to(DEV), None, 25)):
+            w = (torch.randn(R, S, wshape, generator=gen) * 1e-3).to(DEV)
+            res = {}
+            for fold in (False, True):
+                config.fold_final = fold
+                res[fold] = _mlp_pass(models[name], emb["xyz"], pts, code, dirs, w)
+            a, b = res[False], res[True]
+            out_bar = 2e-3 if name == "coarse" else 2e-5
+            assert _nrel(b[0], a[0]) < out_bar, (name, "out", _nrel(b[0], a[0]))
+            assert _nrel(b[1], a[1]) < 5e-3, (name, "gpts", _nrel(b[1], a[1]))
+            # per-ray code gradients: a direction-layer ReLU unit within fp16 rounding of its kink flips between the two
+            # programs for a few rays (same effect as against the fp64 oracle, profiles/r02_diag_env_code.txt)
+            assert _nrel(b[2], a[2]) < 1e-2, (name, "gcode", _nrel(b[2], a[2]))
+            assert set(a[3]) == set(b[3])
+            for k in a[3]:
+                bar = 1e-2 if k.endswith("bias") else 5e-3
+                assert _nrel(b[3][k], a[3][k]) < bar, (name, k, _nrel(b[3][k], a[3][k]))
+            for k in ("xyz_encoding_final.weight", "xyz_encoding_final.bias", "dir_encoding.0.weight"):
+                assert float(b[3][k].abs().max()) > 0, (name, k, "no gradient mapped back")
+    finally:
+        config.fold_final = was
+
+
+def test_deferred_weight_gradient_join_gives_the_same_step():
+    """With FlatParams the weight-gradient kernels run on side streams joined at the end of backward()
+    (chain_tc._SideQueue).  Same kernels, same inputs: the flat gradient equals the one of the in-Function join up to the
+    order of the fp32 atomics, and a second step right behind the first (operands kept alive until the join, then freed)
+    reproduces it."""
+    from moda_b200 import config, synth, models as MM
+    from moda_b200.parallel import FlatParams
+    from moda_b200.rendering import render_rays
+    config.set_precision("fp16")
+    prob = synth.make_problem(512, seed=4)
+    was = config.defer_wgrad
+    grads = {}
+    try:
+        for defer in (False, True, True):
+            config.defer_wgrad = defer
+            models, emb, rays = MM.build_models(prob, DEV)
+            flat = FlatParams(MM.parameters_of(models))
+            for rep in range(2):
+                flat.zero_grad()
+                res = render_rays(models, emb, rays, N_samples=128, perturb=0, noise_std=0, opts=synth.default_opts(), img_size=512)
+                loss = ((res["img_coarse"] - 0.3) ** 2).mean() + ((res["sil_coarse"] - 0.5) ** 2).mean() + res["frame_cyc_dis"].mean()
+                loss.backward()
+                g = flat.grad.clone()
+                grads.setdefault(defer, []).append(g)
+                # churn the allocator: anything freed too early would be overwritten here
+                junk = [torch.full((1 << 20,), 7.0, device=DEV) for _ in range(8)]
+                del junk
+        torch.cuda.synchronize()
+    finally:
+        config.defer_wgrad = was
+    ref = grads[False][0]
+    assert float(ref.abs().max()) > 0
+    for g in grads[False][1:] + grads[True]:
+        assert float((g - ref).abs().max() / ref.abs().max()) < 1e-5
