@@ -349,7 +349,9 @@ def test_split_precision_skin_mlp_matches_fp32_simt():
         assert set(a[3]) == set(b[3])
         # bias gradients are signed sums over all samples too (same cancellation as the shared code row); against the
         # fp64 oracle the folded and the unfolded chains sit at the same distance (profiles/r02_grad_table_n8192_*)
-        worst = max((nrel(b[3][k], a[3][k]) / (1e-2 if k.endswith("bias") else 3e-3), k) for k in a[3])
+        # (with a shared code row the code columns of xyz_encoding_1 / _5 .weight are such sums as well)
+        wbar = 1e-2 if code.shape[0] == 1 else 3e-3
+        worst = max((nrel(b[3][k], a[3][k]) / (1e-2 if k.endswith("bias") else wbar), k) for k in a[3])
         assert worst[0] < 1.0, worst
 
 
