@@ -238,6 +238,16 @@ int moda_chain_skin_fwd(const float* xyz, long long P, int rep, int F, const flo
                         float* y32 /* (P,32) delta skinning logits */,
                         int fold /* 1: xyz_encoding_final folded into dir_encoding, see MODA_CHAIN_FOLD_FINAL */,
                         cudaStream_t stream);
+/* nerf_feat (nnutils/moda.py:447-449: NeRF(D=5, W=128, in 63, raw_feat=True, out 16), evaluated by rendering.py:174-178
+ * and loss_utils.py:318-320) as one chain kernel per pass on the 256-wide engine; the final layer is always folded into
+ * the direction layer (MODA_CHAIN_FOLD_FINAL).  Packed-weight chunk orders at the definitions (csrc/chain.cu). */
+int moda_chain_feat_fwd(const float* xyz, long long P, int F, const float* win, const void* wpack /* fp16 (128, 13*64) */,
+                        const float* const* biases /* b1..b5 (128), b' (64), brgb (64, zero padded) */, void* A0 /* (P,64) */,
+                        void* H /* (5,P,128) */, void* dfe /* (P,64) */, unsigned int* maskbits /* (6,tiles2,4,128) u64 */,
+                        float* y32 /* (P,32) */, int mode /* MODA_CHAIN_PAIR | MODA_CHAIN_TWO_SLOTS */, cudaStream_t stream);
+int moda_chain_feat_bwd(const float* gout /* (P,32) */, const float* scale, const void* wpackT /* fp16 (128, 14*64) */,
+                        const unsigned int* maskbits, long long P, void* G /* (P,64) */, void* d_dfe /* (P,64) */,
+                        void* dY /* (5,P,128) */, void* d_pe /* (P,64) */, int mode, cudaStream_t stream);
 /* debug: device buffer (>= 16004 int64, zeroed) that subsequent chain launches fill with an event timeline of
  * block 0's third tile (tools/chain_trace.py); NULL switches tracing off */
 int moda_chain_set_trace(long long* buf);

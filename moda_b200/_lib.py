@@ -67,6 +67,8 @@ SIGNATURES = {
     "moda_chain_trunk_sigma": [c_p, c_ll, c_i, c_fp, c_p, c_pp, c_p, c_p, c_p, c_i, c_p],
     "moda_chain_trunk_bwd": [c_p] * 6 + [c_ll] + [c_p] * 3 + [c_i, c_p],
     "moda_chain_skin_fwd": [c_p, c_ll, c_i, c_i, c_fp, c_p, c_pp] + [c_p] * 6 + [c_i, c_p],
+    "moda_chain_feat_fwd": [c_p, c_ll, c_i, c_fp, c_p, c_pp] + [c_p] * 5 + [c_i, c_p],
+    "moda_chain_feat_bwd": [c_p] * 4 + [c_ll] + [c_p] * 4 + [c_i, c_p],
     "moda_chain_skin_bwd": [c_p] * 4 + [c_ll] + [c_p] * 5 + [c_i, c_p],
     "moda_chain_set_trace": [c_p],
     "moda_chain_pair_available": [],

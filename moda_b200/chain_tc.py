@@ -578,3 +578,131 @@ class SkinChainFn(torch.autograd.Function):
         ctx.act = None
         gret[14] = gret[15] = None   # nerf_skin's sigma head is computed and discarded in the reference (nerf.py:178)
         return (gpts.reshape(pshape) if want_pts else None, gcode if nc else None, None, None, None) + tuple(gret)
+
+
+# ------------------------------------------------------------------------------------------ 5 x 128 raw-feature MLP
+FW = 128
+
+
+def feat_supported(model, embed_xyz, k):
+    """nerf_feat's architecture (nnutils/moda.py:447-449) on a plain PE(xyz) input."""
+    return (embed_xyz is not None and embed_xyz.N_freqs == 10 and k == 3 and model.raw_feat and model.in_channels_dir == 0
+            and model.in_channels_xyz == 63 and model.D == 5 and model.W == FW and list(model.skips) == [4]
+            and model.out_channels <= 32 and model.dir_encoding[0].weight.shape[0] == 64)
+
+
+def _pack_feat_fwd(params, Wp):
+    W = [params[2 * i] for i in range(5)]
+    Wr = params[16]
+    out = torch.zeros(FW, 13 * 64, device=W[0].device, dtype=HALF)
+    pk = _Packer(out)
+    col = 0
+    for w, cols, col0, rows, width in ((W[0], 63, 0, FW, 64), (W[1], FW, 0, FW, FW), (W[2], FW, 0, FW, FW), (W[3], FW, 0, FW, FW),
+                                       (W[4], 63, 0, FW, 64), (W[4], FW, 63, FW, FW), (Wp, FW, 0, 64, FW), (Wr, 64, 0, 64, 64)):
+        pk.add(w, cols, col0, col, rows, width, False)
+        col += width
+    assert col == 13 * 64
+    return pk.run()
+
+
+def _pack_feat_bwd(params, Wp):
+    W = [params[2 * i] for i in range(5)]
+    Wr = params[16]
+    out = torch.zeros(FW, 14 * 64, device=W[0].device, dtype=HALF)
+    pk = _Packer(out)
+    col = 0
+    # transposed blocks: rows = input channel of the layer, `width` columns = its output channels (zero padded)
+    for w, cols, col0, rows, width in ((Wr, 64, 0, 64, 64), (Wp, FW, 0, FW, 64), (W[4], 63, 0, 64, FW), (W[4], FW, 63, FW, FW),
+                                       (W[3], FW, 0, FW, FW), (W[2], FW, 0, FW, FW), (W[1], FW, 0, FW, FW), (W[0], 63, 0, 64, FW)):
+        pk.add(w, cols, col0, col, rows, width, True)
+        col += width
+    assert col == 14 * 64
+    return pk.run()
+
+
+class FeatChainFn(torch.autograd.Function):
+    """apply(pts (..,3), win, save, *params) -> (P, 32) fp32 raw features (columns >= out_channels zero): nerf_feat as ONE
+    chain kernel per pass (csrc/chain.cu: moda_chain_feat_fwd / _bwd) instead of one tensor-core kernel per layer
+    (generic_tc, which stays as the reference implementation this is tested against).  Same conventions as the other
+    chain Functions; xyz_encoding_final is always folded into dir_encoding."""
+
+    @staticmethod
+    def forward(ctx, pts, win, save, *params):
+        pshape = pts.shape
+        pts = f32(pts).reshape(-1, 3)
+        P, dev = pts.shape[0], pts.device
+        ctx.param_refs = params
+        params = [f32(p) for p in params]
+        need_bw = bool(save) and any(ctx.needs_input_grad)
+        b = [params[2 * i + 1] for i in range(5)]
+        Wf, bf, Wd, bd, Wr, br = params[10], params[11], params[12], params[13], params[16], params[17]
+        oc = br.shape[0]
+        Wp, bp = _fold(Wf, bf, Wd, bd, FW)
+        pad = torch.zeros(2, 64, device=dev, dtype=torch.float32)
+        pad[0] = bp
+        pad[1, :oc] = br
+        T = ((P + TILE - 1) // TILE + 1) & ~1
+        wa, _ = _win_array(win)
+        mode = config.chain_mode() & 3
+        wpack = _pack_feat_fwd(params, Wp)
+        biases = (ctypes.c_void_p * 7)(*([ptr(_al16(x)) for x in b] + [ptr(pad[0]), ptr(pad[1])]))
+        out = torch.empty(P, 32, device=dev, dtype=torch.float32)
+        if need_bw:
+            A0 = torch.empty(P, 64, device=dev, dtype=HALF)
+            H = torch.empty(5, P, FW, device=dev, dtype=HALF)
+            dfe = torch.empty(P, 64, device=dev, dtype=HALF)
+            bits = torch.empty(6, T, 4, TILE, device=dev, dtype=torch.int64)
+        else:
+            A0 = H = dfe = bits = None
+        call("moda_chain_feat_fwd", ptr(pts), P, len(win), wa, ptr(wpack), biases, ptr(A0), ptr(H), ptr(dfe),
+             bits.data_ptr() if bits is not None else None, ptr(out), mode, stream())
+        if need_bw:
+            ctx.save_for_backward(pts, *params)
+            ctx.act = (A0, H, dfe, bits)
+            ctx.meta = (win, pshape, oc, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pts = ctx.saved_tensors[0]
+        params = list(ctx.saved_tensors[1:])
+        A0, H, dfe, bits = ctx.act
+        win, pshape, oc, mode = ctx.meta
+        P, dev = pts.shape[0], pts.device
+        Wf, bf, Wd, bd = params[10], params[11], params[12], params[13]
+        g, gret = _grad_targets(ctx.param_refs, params)
+        gout = f32(gout).reshape(P, 32)
+        sc, isc = _loss_scale(gout)
+        wpackT = _pack_feat_bwd(params, _fold(Wf, bf, Wd, bd, FW)[0])
+        h16 = lambda n: torch.empty(P, n, device=dev, dtype=HALF)
+        G, d_dfe, d_pe = h16(64), h16(64), h16(64)
+        dY = torch.empty(5, P, FW, device=dev, dtype=HALF)
+        call("moda_chain_feat_bwd", ptr(gout), ptr(sc), ptr(wpackT), bits.data_ptr(), P, ptr(G), ptr(d_dfe), ptr(dY),
+             ptr(d_pe), mode, stream())
+        gWp = torch.zeros(64, FW, device=dev, dtype=torch.float32)
+        dbp = torch.zeros(64, device=dev, dtype=torch.float32)
+        hidden = [(dY[4], H[3], g[8], 63, FW, FW, g[9])] + [(dY[i], H[i - 1], g[2 * i], 0, FW, FW, g[2 * i + 1]) for i in (3, 2, 1)]
+        pe_jobs = [(dY[4], A0, g[8], 0, FW, 63, None), (dY[0], A0, g[0], 0, FW, 63, g[1])]
+        want_pts = ctx.needs_input_grad[0]
+        gpts = torch.empty(P, 3, device=dev, dtype=torch.float32) if want_pts else None
+        wa, _ = _win_array(win)
+
+        def wgrads():
+            _wgrad_multi(hidden, FW, FW, P, isc)
+            _wgrad_multi(pe_jobs, FW, 64, P, isc)
+            _wgrad_multi([(d_dfe, H[4], gWp, 0, 64, FW, dbp)], 64, FW, P, isc)
+            _wgrad_multi([(G, dfe, g[16], 0, oc, 64, g[17])], 64, 64, P, isc)
+            _unfold_grads(gWp, dbp, Wf, bf, Wd, FW, g[10], g[11], g[12])
+            g[13].add_(dbp)
+
+        q = _side_queue(dev, gret)
+        if q is not None:
+            q.fork(G, dfe, d_dfe, H, dY, A0, isc, g, gWp, dbp, params)
+            q.run(wgrads)
+        else:
+            wgrads()
+        if want_pts:
+            call("moda_pe16_bwd", ptr(pts), ptr(d_pe), None, 64, ptr(gpts), P, len(win), wa, ptr(isc), 0, stream())
+        ctx.act = None
+        gret[14] = gret[15] = None   # the sigma head is computed and discarded by the reference (nerf.py:178)
+        return (gpts.reshape(pshape) if want_pts else None, None, None) + tuple(gret)

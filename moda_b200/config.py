@@ -14,6 +14,23 @@ precision = os.environ.get("MODA_B200_PRECISION", "fp16")
 fused = os.environ.get("MODA_B200_FUSED", "1") != "0"
 
 
+class exact:
+    """``with config.exact():`` runs the enclosed MLP evaluations on the fp32 SIMT kernels whatever ``precision`` says
+    (for small, precision-critical evaluations such as the 8000-point feature lattice of feat_match, whose features go
+    through exp((f.v - 1) / 0.03))."""
+
+    def __enter__(self):
+        global precision
+        self.old = precision
+        precision = "fp32"
+        return self
+
+    def __exit__(self, *exc):
+        global precision
+        precision = self.old
+        return False
+
+
 def set_precision(p):
     global precision
     if p not in ("fp16", "fp32"):
@@ -56,6 +73,11 @@ def set_trunk_slots(n):
 # with the product weights W' = Wdir[:, :W] Wfinal: one step less per pass, one saved activation and one gradient less,
 # one weight-gradient job less; dW' is mapped back to dWdir / dWfinal with two small products.  MODA_B200_FOLD_FINAL=0: off.
 fold_final = os.environ.get("MODA_B200_FOLD_FINAL", "1") != "0"
+
+
+# feat_chain: nerf_feat (5 x 128 raw-feature MLP) as one chain kernel per pass (csrc/chain.cu: moda_chain_feat_*);
+# MODA_B200_FEAT_CHAIN=0 keeps the layer-by-layer tensor-core kernels (generic_tc).
+feat_chain = os.environ.get("MODA_B200_FEAT_CHAIN", "1") != "0"
 
 
 def chain_mode():

@@ -1060,6 +1060,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             MODA_FLAVOUR(E_BIAS | E_RELU | E_HEAD_SIGMA)                 // sigma-only program: last layer feeds the head only
             MODA_FLAVOUR(E_BIAS | E_SMEM)
             MODA_FLAVOUR_N(E_BIAS | E_RELU | E_HEAD_RGB | E_SMEM, 128)
+            MODA_FLAVOUR_N(HOT_FWD, 128)                                 // the 5 x 128 program (nerf_feat)
+            MODA_FLAVOUR_N(HOT_FWD, 64)
+            MODA_FLAVOUR_N(E_BIAS | E_OUT_F32, 64)
             run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           } else {
             MODA_FLAVOUR(E_BIAS | E_SMEM | E_LO)
@@ -1074,6 +1077,9 @@ chain_kernel(const __grid_constant__ Program pg, const __grid_constant__ Maps ma
             MODA_FLAVOUR_N(E_LOAD16 | E_SMEM, 128)
             MODA_FLAVOUR_N(E_SMEM, 64)
             MODA_FLAVOUR_N(E_ADD_SX | E_SMEM, 64)
+            MODA_FLAVOUR_N(HOT_BWD, 128)                                 // the 5 x 128 program (nerf_feat)
+            MODA_FLAVOUR_N(HOT_BWD, 64)
+            MODA_FLAVOUR_N(E_LOAD32 | E_SMEM, 64)
             run_step<-1, 0, NH, ACC_STRIDE, EPI_THREADS>(flags, pg, maps, st, cx, acc_col, ready_slot, hs0, hs1, hs2, pm0, pm1);
           } else {
             MODA_FLAVOUR(E_LOAD32 | E_SMEM)
@@ -1454,7 +1460,7 @@ int launch(Builder& bld, const void* wpack, int wrows, int wcols, cudaStream_t s
 // launches a 256-wide program in the requested mode (see MODE_*), falling back to the single-CTA kernel when a cluster
 // cannot be placed.  Two tile slots only pay when every CTA gets at least two tiles.
 template <int PROG>
-int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_t stream) {
+int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_t stream, int wrows = 256) {
   const bool pair = (mode & MODE_PAIR) && !g_pair_unavailable.load();
   if (pair) {
     const int ctas = sm_count() & ~1;
@@ -1462,15 +1468,15 @@ int launch_trunk(Builder& b, int mode, const void* wpack, int wcols, cudaStream_
     int e;
     if ((mode & MODE_TWO_SLOTS) && tiles >= 2 * ctas) {
       b.pg.stages = 5;   // as many 16 KB stages as fit: 3 for the forward programs, 4 for the adjoint
-      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 2>(b, wpack, 256, wcols, stream);
+      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 2>(b, wpack, wrows, wcols, stream);
     } else {
       b.pg.stages = 8;
-      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 1>(b, wpack, 256, wcols, stream);
+      e = launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 1, 1>(b, wpack, wrows, wcols, stream);
     }
     if (e != PAIR_UNAVAILABLE) return e;
   }
   b.pg.stages = 4;   // single-CTA weight ring: 4 stages of 32 KB
-  return launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 0, 1>(b, wpack, 256, wcols, stream);
+  return launch<128, MODA_TRUNK_EPI, 1, 1, PROG, 0, 1>(b, wpack, wrows, wcols, stream);
 }
 
 // the epilogue reads these operands with 128-bit loads
@@ -1634,6 +1640,78 @@ extern "C" int moda_chain_trunk_bwd(const void* d_dfe, const float* gsig, const 
     b.out(st, SX, 1);
   }
   return launch_trunk<P_BWD>(b, mode, wpackT, col * 64, stream);
+}
+
+// ------------------------------------------------------------------------------------------- 5 x 128 raw-feature MLP
+// nerf_feat (nnutils/moda.py:447-449: NeRF(D=5, W=128, in 63, raw_feat, out 16)) on a plain PE(xyz) input, on the
+// 256-wide engine (128-row weight boxes, CTA pairs / two tile slots as requested by `mode`), plain fp16 operands, the
+// final layer always folded into the direction layer (see MODE_FOLD_FINAL).
+// wpack fp16 (128, 13*64), 64-column chunks (rows = output channel, zero padded):
+//   0: W1[:, :63]   1-2: W2   3-4: W3   5-6: W4   7: W5[:, :63]   8-9: W5[:, 63:]   10-11: W' = Wdir Wfinal (64 rows)
+//   12: Wrgb (out_channels rows, K = 64)
+// biases: b1..b5 (128), b' = bdir + Wdir bfinal (64), brgb zero padded to 64.  y32 (P,32) fp32, columns >= out_channels 0.
+// Saved when non-null: A0 (P,64), H (5,P,128), dfe (P,64), maskbits (6, tiles2, 4, 128) u64.
+extern "C" int moda_chain_feat_fwd(const float* xyz, long long P, int F, const float* win, const void* wpack,
+                                   const float* const* biases, void* A0, void* H, void* dfe, unsigned int* maskbits,
+                                   float* y32, int mode, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(xyz && wpack && biases && y32 && F >= 0 && F <= 10, "chain_feat_fwd: bad arguments");
+  MODA_REQUIRE(al16(y32) && al16(wpack), "chain_feat_fwd: y32 and wpack must be 16-byte aligned");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 3;
+  pg.xyz = xyz; fill_win(pg, F, win);
+  pg.maskbits = maskbits; pg.y32 = y32; pg.ld_y32 = 32;
+  const int PE = 2;
+  const int mo = maskbits ? E_MASK_OUT : 0;
+  b.pe(PE, false, b.save(A0, P, 64));
+  int col = 0;
+  for (int l = 0; l < 5; ++l) {
+    Step& st = b.add(128, E_RELU | mo);
+    st.bias = biases[l]; st.mask_slot = l;
+    if (l == 0) { b.k(st, PE, col); col += 1; }
+    else {
+      if (l == 4) { b.k(st, PE, col); col += 1; st.release_pe = 1; }
+      b.k(st, 0, col); b.k(st, 1, col + 1); col += 2;
+    }
+    st.save_map = b.save(H ? (const char*)H + (size_t)l * P * 128 * 2 : nullptr, P, 128);
+    b.out(st, 0, 2);
+  }
+  { Step& st = b.add(64, E_RELU | mo); st.bias = biases[5]; st.mask_slot = 5; b.k(st, 0, col); b.k(st, 1, col + 1); col += 2;
+    st.save_map = b.save(dfe, P, 64); b.out(st, 0, 1); }
+  { Step& st = b.add(64, E_OUT_F32); st.bias = biases[6]; b.k(st, 0, col); col += 1; }
+  return launch_trunk<P_FWD>(b, mode, wpack, col * 64, stream, 128);
+}
+
+// Adjoint of the above.  wpackT fp16 (128, 14*64): 0: Wrgb^T (64 dfe rows, K = out_channels)   1: W'^T (128 rows, K = 64)
+//   2-3: W5[:, :63]^T (64 rows, K = 128)   4-5: W5[:, 63:]^T   6-7: W4^T   8-9: W3^T   10-11: W2^T   12-13: W1[:, :63]^T
+// In: gout (P,32) fp32, scale (device scalar), maskbits.  Out fp16: G (P,64) = scale gout, d_dfe (P,64), dY (5,P,128),
+// d_pe (P,64).
+extern "C" int moda_chain_feat_bwd(const float* gout, const float* scale, const void* wpackT, const unsigned int* maskbits,
+                                   long long P, void* G, void* d_dfe, void* dY, void* d_pe, int mode, cudaStream_t stream) {
+  if (P == 0) return 0;
+  MODA_REQUIRE(gout && wpackT && maskbits && G && d_dfe && dY && d_pe, "chain_feat_bwd: null pointer");
+  MODA_REQUIRE(al16(gout) && al16(wpackT), "chain_feat_bwd: gout and wpackT must be 16-byte aligned");
+  Builder b;
+  Program& pg = b.pg;
+  pg.M = P; pg.num_tiles = (int)((P + TILE_M - 1) / TILE_M); pg.rep = 1; pg.nchunks = 3;
+  pg.maskbits = const_cast<unsigned int*>(maskbits);
+  pg.load_src = gout; pg.load_ld = 32; pg.load_cols = 32; pg.load_scale = scale;
+  const int SX = 2;
+  auto dy = [&](int i) { return (const char*)dY + (size_t)i * P * 128 * 2; };
+  { Step& st = b.add(64, E_LOAD32); st.save_map = b.save(G, P, 64); b.out(st, 0, 1); }
+  { Step& st = b.add(64, E_MASK_IN); b.k(st, 0, 0); st.mask_slot = 5; st.save_map = b.save(d_dfe, P, 64); b.out(st, 0, 1); }
+  { Step& st = b.add(128, E_MASK_IN); b.k(st, 0, 1); st.mask_slot = 4; st.save_map = b.save(dy(4), P, 128); b.out(st, 0, 2); }
+  { Step& st = b.add(64, 0); b.k(st, 0, 2); b.k(st, 1, 3); b.out(st, SX, 1); }
+  int col = 4;
+  for (int l = 4; l >= 1; --l) {
+    Step& st = b.add(128, E_MASK_IN);
+    b.k(st, 0, col); b.k(st, 1, col + 1); col += 2;
+    st.mask_slot = l - 1; st.save_map = b.save(dy(l - 1), P, 128);
+    b.out(st, 0, 2);
+  }
+  { Step& st = b.add(64, E_ADD_SX); b.k(st, 0, col); b.k(st, 1, col + 1); col += 2; st.save_map = b.save(d_pe, P, 64); b.out(st, SX, 1); }
+  return launch_trunk<P_BWD>(b, mode, wpackT, col * 64, stream, 128);
 }
 
 // ------------------------------------------------------------------------------------------------ nerf_skin

@@ -119,6 +119,10 @@ def _evaluate_mlp(model, xyz_embedded, embed_xyz=None, dir_embedded=None, chunk=
             # a 5 x 64 raw-feature net without code columns (nerf_vis) is nerf_skin's architecture: same chain kernels
             out = chain_tc.SkinChainFn.apply(pts2, None, nbins, win, torch.is_grad_enabled(), *model.param_list())
             return out.reshape(Bn, nbins, 32)[..., :model.out_channels]
+        if config.fused and config.feat_chain and chain_tc.feat_supported(model, embed_xyz, k):
+            # nerf_feat (5 x 128): one chain kernel per pass
+            out = chain_tc.FeatChainFn.apply(pts2, win, torch.is_grad_enabled(), *model.param_list())
+            return out.reshape(Bn, nbins, 32)[..., :model.out_channels]
         skip = model.skips[0] if model.skips else None
         out = generic_tc.GenericTcFn.apply(pts2, win, torch.is_grad_enabled(), model.D, model.W, skip, *model.param_list())
         return out.reshape(Bn, nbins, 32)[..., :model.out_channels]

@@ -135,7 +135,12 @@ def feat_match(nerf_feat, embedding_xyz, feats, bound, grid_size=20, use_corr=Tr
         bound_t = torch.from_numpy(bound)[None, None].to(device)
         query_xyz = query_xyz + torch.randn_like(query_xyz) * bound_t * 0.05
     # canonical features on the lattice: one MLP evaluation over all grid_size^3 points (the reference chunks by 8192)
-    vol_feat = G.evaluate_mlp(nerf_feat, query_xyz[0][:, None], embed_xyz=embedding_xyz)[:, 0]
+    # on the fp32 kernels in every precision mode: 8000 points cost nothing, and these features enter
+    # exp((f.v - 1) / 0.03) -- an fp16-operand error of 3e-3 in v moves the matched points by ~2e-5, which the
+    # positional encoding of the reprojection path (kp_reproj evaluates nerf_skin AT the matched points) multiplies by 2^9
+    from . import config
+    with config.exact():
+        vol_feat = G.evaluate_mlp(nerf_feat, query_xyz[0][:, None], embed_xyz=embedding_xyz)[:, 0]
     vol_feat = F.normalize(vol_feat, 2, -1)
     if use_ot and not use_corr and not rt_entropy:
         return SinkhornMatchFn.apply(feats, vol_feat, query_xyz[0]), 0

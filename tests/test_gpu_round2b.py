@@ -131,3 +131,48 @@ def test_deferred_weight_gradient_join_gives_the_same_step():
     assert float(ref.abs().max()) > 0
     for g in grads[False][1:] + grads[True]:
         assert float((g - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_feat_chain_matches_layer_by_layer_kernels():
+    """nerf_feat (5 x 128) as one chain kernel per pass against the layer-by-layer tensor-core kernels (generic_tc) and the
+    fp32 SIMT kernels: outputs and every gradient, at a size with several waves and a ragged last tile, in inference mode
+    too (nothing saved)."""
+    from moda_b200 import config, synth, models as MM, geom_utils as G
+    prob = synth.make_full_problem(8, seed=1)
+    models, emb, _ = MM.build_full_models(prob, DEV)
+    feat = models["nerf_feat"]
+    gen = torch.Generator().manual_seed(21)
+    was = (config.precision, config.feat_chain)
+    try:
+        for R, S in ((331, 128), (16, 128), (63, 127), (1, 50)):
+            pts = (torch.rand(R, S, 3, generator=gen) * 0.4 - 0.2).to(DEV)
+            w = (torch.randn(R, S, 16, generator=gen) * 1e-3).to(DEV)
+            res = {}
+            for tag, prec, chain in (("simt", "fp32", False), ("layered", "fp16", False), ("chain", "fp16", True)):
+                config.set_precision(prec)
+                config.feat_chain = chain
+                feat.zero_grad()
+                p = pts.clone().requires_grad_(True)
+                out = G.evaluate_mlp(feat, p, embed_xyz=emb["xyz"])
+                assert out.shape == (R, S, 16)
+                (out * w).sum().backward()
+                res[tag] = (out.detach(), p.grad, {k: v.grad.clone() for k, v in feat.named_parameters() if v.grad is not None})
+                if tag == "chain":
+                    with torch.no_grad():
+                        out2 = G.evaluate_mlp(feat, pts, embed_xyz=emb["xyz"])
+                    assert torch.equal(out2, out.detach())
+            # outputs: both fp16 paths against the fp32 kernels; gradients: this random upstream gradient is a stress case
+            # (signed sums over all samples cancel by ~sqrt(N) and the PE adjoint multiplies the fp16 noise of d_pe by
+            # up to 2^9), so the bar for the chain is what the layer-by-layer fp16 kernels reach on the same input
+            sim, lay, cha = res["simt"], res["layered"], res["chain"]
+            assert _nrel(cha[0], sim[0]) < 3e-3, (R, "out", _nrel(cha[0], sim[0]))
+            assert _nrel(cha[0], lay[0]) < 3e-3, (R, "out vs layered", _nrel(cha[0], lay[0]))
+            assert set(sim[2]) == set(cha[2]) == set(lay[2])
+            pairs = [("gpts", lay[1], cha[1], sim[1])] + [(k, lay[2][k], cha[2][k], sim[2][k]) for k in sim[2]]
+            for k, l_, c_, s_ in pairs:
+                el, ec = _nrel(l_, s_), _nrel(c_, s_)
+                print("%4d x %3d  %-28s layered %.3e  chain %.3e" % (R, S, k, el, ec))
+                assert ec < max(1.3 * el, 5e-3), (R, k, "chain %.3e layered %.3e" % (ec, el))
+    finally:
+        config.set_precision(was[0])
+        config.feat_chain = was[1]
