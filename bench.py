@@ -229,7 +229,8 @@ def run_ours(args):
     models["nerf_skin"].train()
     opts = synth.default_opts()
     flat = FlatParams(MM.parameters_of(models))
-    optim = torch.optim.AdamW([flat.flat], lr=1e-4, fused=True, capturable=True)
+    # AdamW on the flat buffer (FlatParams.adamw_step -> moda_adamw_flat: torch.optim.AdamW's arithmetic and defaults,
+    # checked against it in tests/test_gpu_round2b.py; graph-capturable)
     ray_keys = ("rays_o", "rays_d", "near", "far", "time_embedded", "bone_rts", "env_code")
     host = {k: prob["rays"][k].pin_memory() for k in ray_keys}
     h2d_bytes = sum(v.numel() * 4 for v in host.values())
@@ -243,7 +244,7 @@ def run_ours(args):
         loss = _loss_of(res) * share
         loss.backward()
         flat.allreduce()
-        optim.step()
+        flat.adamw_step(lr=1e-4)
         return loss
 
     # end-to-end input pipeline: two device buffer sets; while step i computes, the host->device copy of step i+1's
@@ -731,7 +732,6 @@ def measure_full(args, dev, steps=None):
         models[k].train()
     opts = synth.full_opts()
     flat = FlatParams(MM.parameters_of(models))
-    optim = torch.optim.AdamW([flat.flat], lr=1e-4, fused=True)
     bound = prob["obj_bound"].numpy()
 
     def step():
@@ -743,7 +743,7 @@ def measure_full(args, dev, steps=None):
             loss = loss + res[k].mean()
         loss.backward()
         flat.allreduce()
-        optim.step()
+        flat.adamw_step(lr=1e-4)
         return loss
 
     sampler = ClockSampler(dev.index or 0)

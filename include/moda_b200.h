@@ -273,6 +273,13 @@ int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, cons
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, int fold, cudaStream_t stream);
 
+/* AdamW step (torch.optim.AdamW as the reference's training loop uses it, nnutils/train_utils.py:177-222) on the flat
+ * parameter / gradient buffers of the data-parallel path; m, v: moment buffers, state: 3 device floats {step count,
+ * lr / (1 - beta1^t), sqrt(1 - beta2^t)}, advanced on the device so that the call can be captured in a CUDA graph.
+ * n % 4 == 0, 16-byte aligned buffers. */
+int moda_adamw_flat(float* p, const float* g, float* m, float* v, long long n, float* state, float lr, float b1, float b2,
+                    float eps, float wd, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
