@@ -334,6 +334,7 @@ class TrunkChainFn(torch.autograd.Function):
             ctx.save_for_backward(xyz, code, raw, *params)
             ctx.act = (A0, H, fin, dfe, bits)
             ctx.meta = (S, win, dir_emb.shape[-1], env is not None, xyz_shape, mode)
+            ctx.Wp = Wp if fold else None   # the folded weights serve the adjoint too
         return raw
 
     @staticmethod
@@ -363,7 +364,7 @@ class TrunkChainFn(torch.autograd.Function):
         call("moda_linear_wgrad", R, 128, 1, (ctypes.c_void_p * 1)(ptr(code)), _one(cc), _one(cc), _one(0), _one(1), None,
              0, ptr(grb), 128, ptr(g[18]), Wd.shape[1], 256, ptr(g[19]), stream())
         # the whole data-gradient chain in one kernel
-        wpackT = pack_trunk_bwd(params, _fold(Wf, bf, Wd, bd, 256)[0] if fold else None)
+        wpackT = pack_trunk_bwd(params, ctx.Wp if fold else None)
         d_fin = None if fold else torch.empty(P, 256, device=dev, dtype=HALF)
         dY = torch.empty(8, P, 256, device=dev, dtype=HALF)
         d_pe = torch.empty(P, 64, device=dev, dtype=HALF)
@@ -492,6 +493,7 @@ class SkinChainFn(torch.autograd.Function):
             ctx.save_for_backward(pts, code, *params)
             ctx.act = (A0, H, fin, dfe, bits)
             ctx.meta = (S, win, rep, pshape, oc, fold)
+            ctx.Wp = Wp
         return out
 
     @staticmethod
@@ -507,7 +509,7 @@ class SkinChainFn(torch.autograd.Function):
         gout = f32(gout).reshape(P, 32)
         sc, isc = _loss_scale(gout)
         Wf, bf, Wd, bd = params[10], params[11], params[12], params[13]
-        wpackT = pack_skin_bwd(params, nc, _fold(Wf, bf, Wd, bd, 64)[0] if fold else None)
+        wpackT = pack_skin_bwd(params, nc, ctx.Wp if fold else None)
         h16 = lambda: torch.empty(P, WD, device=dev, dtype=HALF)
         G, d_dfe, d_pe = h16(), h16(), h16()
         d_fin = None if fold else h16()
@@ -660,6 +662,7 @@ class FeatChainFn(torch.autograd.Function):
             ctx.save_for_backward(pts, *params)
             ctx.act = (A0, H, dfe, bits)
             ctx.meta = (win, pshape, oc, mode)
+            ctx.Wp = Wp
         return out
 
     @staticmethod
@@ -673,7 +676,7 @@ class FeatChainFn(torch.autograd.Function):
         g, gret = _grad_targets(ctx.param_refs, params)
         gout = f32(gout).reshape(P, 32)
         sc, isc = _loss_scale(gout)
-        wpackT = _pack_feat_bwd(params, _fold(Wf, bf, Wd, bd, FW)[0])
+        wpackT = _pack_feat_bwd(params, ctx.Wp)
         h16 = lambda n: torch.empty(P, n, device=dev, dtype=HALF)
         G, d_dfe, d_pe = h16(64), h16(64), h16(64)
         dY = torch.empty(5, P, FW, device=dev, dtype=HALF)

@@ -375,7 +375,7 @@ extern "C" int moda_linear_wgrad(int M, int N, int nseg, const float* const* seg
   int splits = cdiv(148 * 4, tiles);
   int r_chunk = cdiv(M, splits);
   r_chunk = ((r_chunk + BR - 1) / BR) * BR;
-  if (r_chunk < 256) r_chunk = 256;
+  if (r_chunk < 64) r_chunk = 64;   // (256 left a 1024-ray problem on 16 CTAs: 17 us for 8 MFLOP)
   splits = cdiv(M, r_chunk);
   dim3 grid(cdiv(N, 64), cdiv(K, 64), splits);
   gemm_kernel<DenseT, ASrcT, EpiWgrad, 64, 64, false, false><<<grid, GEMM_THREADS, 0, stream>>>(p, a, ep, N, K, M, r_chunk);
