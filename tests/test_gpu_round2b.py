@@ -197,3 +197,37 @@ def test_flat_adamw_step_matches_torch_adamw():
             err = float((flat.flat.detach() - ref.detach()).abs().max() / ref.detach().abs().max())
             assert err < 2e-6, (kw, step, err)
         assert torch.equal(ts[0].data.reshape(-1), flat.flat.detach()[:256 * 63]), "parameters are views of the flat buffer"
+
+
+def test_edge_cases_of_the_new_entry_points():
+    """Empty inputs (P = 0) and a single sample through the chain Functions added this round (nerf_vis on the nerf_skin
+    chain, nerf_feat chain), an empty job list of the multi-job weight gradient, and an LBS warp with ONE bone (weights
+    exactly one: the blend is that bone's rigid transform and backward o forward is the identity)."""
+    from moda_b200 import chain_tc, config, synth, models as MM, geom_utils as G
+    config.set_precision("fp16")
+    prob = synth.make_full_problem(4, seed=2)
+    models, emb, _ = MM.build_full_models(prob, DEV)
+    for name, oc in (("nerf_vis", 1), ("nerf_feat", 16)):
+        net = models[name]
+        net.zero_grad()
+        out0 = G.evaluate_mlp(net, torch.zeros(0, 7, 3, device=DEV), embed_xyz=emb["xyz"])
+        assert out0.shape == (0, 7, oc)
+        p = (torch.rand(1, 1, 3, device=DEV) * 0.2).requires_grad_(True)
+        out1 = G.evaluate_mlp(net, p, embed_xyz=emb["xyz"])
+        assert out1.shape == (1, 1, oc) and torch.isfinite(out1).all()
+        out1.sum().backward()
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+        assert all(torch.isfinite(q.grad).all() for q in net.parameters() if q.grad is not None)
+    chain_tc._wgrad_multi([], 64, 64, 0, torch.ones(1, device=DEV))   # nothing to do: no launch, no error
+    # LBS with one bone
+    gen = torch.Generator().manual_seed(5)
+    R = synth._small_rotation(gen, 3, 0.3).reshape(3, 1, 9)
+    T = 0.05 * torch.randn(3, 1, 3, generator=gen)
+    rts = torch.cat([R, T], -1).reshape(3, 12).to(DEV)
+    bones = prob["bones_rst"][:1].to(DEV)
+    xyz = (torch.rand(3, 5, 3, generator=gen) - 0.5).to(DEV)
+    skin = torch.ones(3, 5, 1, device=DEV)
+    y, bd = G.lbs(bones, rts, skin, xyz, backward=True)
+    x2, _ = G.lbs(bones, rts, skin, y, backward=False)
+    assert float((x2 - xyz).abs().max()) < 1e-5
+    assert bd.shape == (3, 1, 10)
