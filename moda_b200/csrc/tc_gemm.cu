@@ -502,6 +502,14 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, int npair, int M, float* dW
 // block), which is what kept the weight gradients at ~33 us per launch however small the batch (profiles/r02: 1.22 ms
 // of a 2.1 ms step at 1024 rays per GPU).
 constexpr int WG_MAX_JOBS = 9;
+// ring depth of the multi-job kernel by shape: as many stages as ~192 KB hold, at most 8.  Three 16 KB stages of a 64 x 64
+// job keep 48 KB per SM in flight -- 7 MB over the machine, about what the HBM latency x bandwidth product needs and no
+// more: the 64 x 64 launch ran at 5.0 TB/s against 7.1 TB/s of the 256 x 256 one (three 64 KB stages).
+constexpr int wg_multi_stages(int nout, int kin) {
+  const int stage = (nout + kin) / 64 * WG_BOX_BYTES;
+  const int n = (192 * 1024) / stage;
+  return n < 3 ? 3 : (n > 8 ? 8 : n);
+}
 struct WgJob { CUtensorMap y, x; float* dW; float* dbias; int ldw, n_valid, k_valid, cta0, nctas, pad_; };
 struct WgJobs { int njobs; int pad_[15]; WgJob job[WG_MAX_JOBS]; };
 
@@ -522,23 +530,24 @@ tc_wgrad_multi_kernel(const __grid_constant__ WgJobs jobs, int M, const float* o
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int YB = NOUT / 64, XB = KIN / 64;       // boxes per operand per stage
   constexpr int STAGE_BYTES = (YB + XB) * WG_BOX_BYTES;
+  constexpr int NST = wg_multi_stages(NOUT, KIN);   // ring depth
   constexpr int MB = (NOUT + 127) / 128;             // 128-row blocks of the accumulator
   constexpr bool PAD_M = (NOUT == 64);
   constexpr int TCOLS = MB * KIN <= 32 ? 32 : (MB * KIN <= 64 ? 64 : (MB * KIN <= 128 ? 128 : (MB * KIN <= 256 ? 256 : 512)));
   static_assert(MB * KIN <= 512, "accumulator does not fit TMEM");
   static_assert(NOUT == 64 || NOUT % 128 == 0, "output channels: 64 or blocks of 128");
-  uint8_t* zero_blk = smem + WG_STAGES * STAGE_BYTES;  // 8 KB of zeros (only used when PAD_M)
+  uint8_t* zero_blk = smem + NST * STAGE_BYTES;  // 8 KB of zeros (only used when PAD_M)
   uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + WG_BOX_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + WG_STAGES;
-  uint64_t* done = bars + 2 * WG_STAGES;
+  uint64_t* empty = bars + NST;
+  uint64_t* done = bars + 2 * NST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_chunks = (M + WG_ROWS - 1) / WG_ROWS;
 
   if (threadIdx.x == 0) {
     // a stage is released by the MMA commit and, when bias gradients are wanted, by the 4 column-sum warps
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], dbias ? 5 : 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], dbias ? 5 : 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -568,7 +577,7 @@ tc_wgrad_multi_kernel(const __grid_constant__ WgJobs jobs, int M, const float* o
           for (int b = 0; b < YB; ++b) tma_load_2d(s + b * WG_BOX_BYTES, &J.y, &full[stage], b * 64, c * WG_ROWS);
           for (int b = 0; b < XB; ++b)
             tma_load_2d(s + (YB + b) * WG_BOX_BYTES, &J.x, &full[stage], b * 64, c * WG_ROWS);
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -598,7 +607,7 @@ tc_wgrad_multi_kernel(const __grid_constant__ WgJobs jobs, int M, const float* o
           }
           first = false;
           umma_commit(&empty[stage]);
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
       umma_commit(done);
@@ -634,7 +643,7 @@ tc_wgrad_multi_kernel(const __grid_constant__ WgJobs jobs, int M, const float* o
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[stage]);
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
       const int col = cp * 2;
@@ -858,7 +867,7 @@ extern "C" int moda_tc_wgrad_split(const void* dYhi, const void* dYlo, int ldy, 
 
 template <int NOUT, int KIN>
 static int launch_wgrad_multi(const tc::WgJobs& jobs, int grid, int M, const float* oscale, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)WG_STAGES * ((NOUT + KIN) / 64) * WG_BOX_BYTES + WG_BOX_BYTES + 256;
+  const size_t smem = 1024 + (size_t)tc::wg_multi_stages(NOUT, KIN) * ((NOUT + KIN) / 64) * WG_BOX_BYTES + WG_BOX_BYTES + 256;
   cudaFuncSetAttribute(tc_wgrad_multi_kernel<NOUT, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   tc_wgrad_multi_kernel<NOUT, KIN><<<grid, WG_THREADS, smem, stream>>>(jobs, M, oscale);
   return check_launch("tc_wgrad_multi");
