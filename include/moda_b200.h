@@ -273,6 +273,11 @@ int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, cons
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, int fold, cudaStream_t stream);
 
+/* One pass over the (n, m) Sinkhorn kernel matrix of feat_match (nnutils/loss_utils.py:347-386) serving both products of an
+ * iteration: y = K x (row sums), z = g(y) elementwise (mode 0: p / (y + delta); mode 1: -y u / (v + delta)), w += K^T z
+ * (column sums, w zeroed by the caller; NULL: row sums only).  K row-major fp32, m % 4 == 0, m <= 8192. */
+int moda_sinkhorn_pass(const float* K, int n, int m, const float* x, float* y, float* z, float* w, int mode, float p,
+                       float delta, const float* u, const float* v, cudaStream_t stream);
 /* AdamW step (torch.optim.AdamW as the reference's training loop uses it, nnutils/train_utils.py:177-222) on the flat
  * parameter / gradient buffers of the data-parallel path; m, v: moment buffers, state: 3 device floats {step count,
  * lr / (1 - beta1^t), sqrt(1 - beta2^t)}, advanced on the device so that the call can be captured in a CUDA graph.

@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from . import geom_utils as G
+from ._lib import call, ptr, stream
 
 
 def visibility_loss(mlp, embed, xyz_pos, w_pos, bound, chunk):
@@ -59,6 +60,11 @@ def feat_match_loss(nerf_feat, embedding_xyz, feats, pts, pts_prob, bound, use_c
     return pts_pred, pts_exp, feat_err, corr_err
 
 
+def _fused_pass_ok(K):
+    """moda_sinkhorn_pass takes fp32 CUDA matrices with m % 4 == 0 and m <= 8192 (the 20^3 lattice has 8000 points)."""
+    return K.is_cuda and K.dtype == torch.float32 and K.is_contiguous() and K.shape[1] % 4 == 0 and K.shape[1] <= 8192
+
+
 class SinkhornMatchFn(torch.autograd.Function):
     """pts_pred (N,3) = rownorm(a K b^T) Q with K = exp(-(1 - F V^T) / 0.03) and (a, b) from 20 Sinkhorn iterations on
     uniform marginals (loss_utils.py:347-386) -- with the ANALYTIC adjoint of the unrolled iterations instead of an
@@ -77,15 +83,28 @@ class SinkhornMatchFn(torch.autograd.Function):
         n, m = K.shape
         a = torch.full((n,), 1.0 / n, device=K.device, dtype=K.dtype)
         As, Bs, Cs, Ds = [a], [], [], []
-        for _ in range(SinkhornMatchFn.ITERS):
+        dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
+        if _fused_pass_ok(K):
+            # one pass over K per iteration (moda_sinkhorn_pass): d_i = K b_i, a_i = p1 / (d_i + delta) and, with the rows
+            # still on chip, c_{i+1} = K^T a_i -- instead of two matrix-vector products that each stream the matrix
             c = torch.mv(K.t(), a)
-            b = (1.0 / m) / (c + SinkhornMatchFn.DELTA)
-            d = torch.mv(K, b)
-            a = (1.0 / n) / (d + SinkhornMatchFn.DELTA)
-            As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
+            for i in range(it):
+                b = (1.0 / m) / (c + dl)
+                d, a = torch.empty_like(a), torch.empty_like(a)
+                c_next = torch.zeros_like(c) if i + 1 < it else None
+                call("moda_sinkhorn_pass", ptr(K), n, m, ptr(b), ptr(d), ptr(a), ptr(c_next), 0, 1.0 / n, dl, None, None, stream())
+                As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
+                c = c_next
+        else:
+            for _ in range(it):
+                c = torch.mv(K.t(), a)
+                b = (1.0 / m) / (c + dl)
+                d = torch.mv(K, b)
+                a = (1.0 / n) / (d + dl)
+                As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
         # T = a K b^T row-normalised: with the final a this is K b^T / rowsum; the reference normalises a K b^T whose row
         # sums are a_20 (K b_20): identical up to rounding
-        s = torch.mv(K, Bs[-1])
+        s = Ds[-1]
         pts = (K * Bs[-1][None]).matmul(query) / s[:, None]
         ctx.save_for_backward(feats, vol_feat, query, K, pts, s)
         ctx.hist = (As, Bs, Cs, Ds)
@@ -101,14 +120,22 @@ class SinkhornMatchFn(torch.autograd.Function):
         gb = (U * K).sum(0)
         gK = U * b20[None]
         left, right = [], []            # gK += sum_k left_k (x) right_k
+        fused = _fused_pass_ok(K)
+        n, m = K.shape
         for i in range(it, 0, -1):
             gc = -gb * Bs[i - 1] / (Cs[i - 1] + dl)
             left.append(As[i - 1]), right.append(gc)
-            ga = torch.mv(K, gc)
-            if i - 1 >= 1:
+            if i - 1 < 1:
+                break
+            if fused:   # ga = K gc, gd = -ga a / (d + delta), gb = K^T gd in one pass over K
+                gd, gb = torch.empty(n, device=K.device, dtype=K.dtype), torch.zeros(m, device=K.device, dtype=K.dtype)
+                call("moda_sinkhorn_pass", ptr(K), n, m, ptr(gc.contiguous()), None, ptr(gd), ptr(gb), 1, 0.0, dl,
+                     ptr(As[i - 1]), ptr(Ds[i - 2]), stream())
+            else:
+                ga = torch.mv(K, gc)
                 gd = -ga * As[i - 1] / (Ds[i - 2] + dl)
-                left.append(gd), right.append(Bs[i - 2])
                 gb = torch.mv(K.t(), gd)
+            left.append(gd), right.append(Bs[i - 2])
         gK.addmm_(torch.stack(left, 1), torch.stack(right, 0))
         gcost = gK.mul_(K).mul_(1.0 / SinkhornMatchFn.EPS)
         gq = None

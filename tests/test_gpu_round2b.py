@@ -231,3 +231,29 @@ def test_edge_cases_of_the_new_entry_points():
     x2, _ = G.lbs(bones, rts, skin, y, backward=False)
     assert float((x2 - xyz).abs().max()) < 1e-5
     assert bd.shape == (3, 1, 10)
+
+
+def test_sinkhorn_pass_against_matrix_vector_products():
+    """moda_sinkhorn_pass (one pass over K for y = K x, z = g(y), w = K^T z) against torch in fp64: both modes, a row
+    count that is not a multiple of the rows per trip, the 8000-column lattice size and a small one, row sums only."""
+    from moda_b200._lib import call, ptr, stream
+    gen = torch.Generator().manual_seed(9)
+    for n, m in ((8192 + 3, 8000), (37, 64), (1, 8192)):
+        K = torch.rand(n, m, generator=gen).to(DEV) * 0.01
+        x = torch.rand(m, generator=gen).to(DEV)
+        u = torch.rand(n, generator=gen).to(DEV) + 0.5
+        v = torch.rand(n, generator=gen).to(DEV) + 0.5
+        Kd, xd = K.double(), x.double()
+        for mode in (0, 1):
+            y, z = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+            w = torch.zeros(m, device=DEV)
+            call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y), ptr(z), ptr(w), mode, 1.0 / n, 1e-8, ptr(u), ptr(v), stream())
+            yd = Kd @ xd
+            zd = (1.0 / n) / (yd + 1e-8) if mode == 0 else -yd * u.double() / (v.double() + 1e-8)
+            wd = Kd.t() @ zd
+            for name, got, ref in (("y", y, yd), ("z", z, zd), ("w", w, wd)):
+                e = float((got.double() - ref).abs().max() / ref.abs().max())
+                assert e < 5e-6, (n, m, mode, name, e)
+        y2 = torch.empty(n, device=DEV)
+        call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y2), None, None, 0, 1.0, 0.0, None, None, stream())
+        assert float((y2.double() - Kd @ xd).abs().max() / (Kd @ xd).abs().max()) < 5e-6
