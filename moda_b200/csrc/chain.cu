@@ -2,24 +2,30 @@
 // activations living in shared memory (as the next layer's A operand) and TMEM (accumulators), never in HBM
 // except for what the other pass needs (fp16 copies for the weight gradients, ReLU sign bits for the adjoint).
 //
-//   nerf_coarse forward  : PE(xyz) -> 8 x (256, ReLU, skip at layer 5) -> final -> dir layer (+ per-ray bias) -> heads
-//                          (nnutils/nerf.py:147-198 on the input evaluate_mlp assembles, geom_utils.py:19-57)
-//   nerf_coarse adjoint  : d_dfe -> d_fin -> dY[7] ... dY[0] and dPE, ReLU masks from the saved sign bits
-//   nerf_skin forward    : the same engine at width 64 with split-precision (hi, lo) fp16 operands
+//   nerf_coarse forward  : PE(xyz) -> 8 x (256, ReLU, skip at layer 5) -> [final ->] dir layer (+ per-ray bias) -> heads
+//                          (nnutils/nerf.py:147-198 on the input evaluate_mlp assembles, geom_utils.py:19-57; the final
+//                          layer, a linear map without activation, is folded into the dir layer: MODE_FOLD_FINAL)
+//   nerf_coarse adjoint  : d_dfe -> [d_fin ->] dY[7] ... dY[0] and dPE, ReLU masks from the saved sign bits
+//   nerf_skin forward    : the same engine at width 64 with split-precision (hi, lo) fp16 operands (also nerf_vis)
 //   nerf_skin adjoint    : plain fp16 chain
+//   nerf_feat (5 x 128)  : forward and adjoint programs on the 256-wide engine (N = 128 / 64 steps)
 //
-// One engine, table driven ("Program": a list of Steps).  Per CTA (one per SM):
+// One engine, table driven ("Program": a list of Steps).  Warp roles of a CTA, one tile in flight (SLOTS = 1):
 //   warp 0       weight producer: streams the packed fp16 weight chunks (K = 64 columns each) of every step through
 //                a shared-memory ring with TMA; it depends on nothing but ring slots, so it runs far ahead.
 //   warp 1       MMA issuer: for every step, waits for the A chunks it needs (written by the previous step's
 //                epilogue or by the PE producers), issues tcgen05.mma into one of two TMEM accumulators.
-//   warps 2-9    epilogue: tcgen05.ld -> bias / per-ray bias / rank-1 term / ReLU / sign-bit mask -> fp16 ->
-//                (a) the 128-byte-swizzled shared-memory chunk that is the next step's A operand, written IN PLACE
-//                (the step that read it has completed), (b) a TMA store of that same chunk to HBM for the other
+//   warps 2..    epilogue (4 or 8 warps): tcgen05.ld -> bias / per-ray bias / rank-1 term / ReLU / sign-bit mask ->
+//                fp16 -> (a) the 128-byte-swizzled shared-memory chunk that is the next step's A operand, written IN
+//                PLACE (the step that read it has completed), (b) a TMA store of that same chunk to HBM for the other
 //                pass, (c) heads.  Chunk by chunk: the next step's MMAs start on chunk 0 while chunks 1-3 of the
-//                current step are still being drained, so the tensor core only idles for one chunk per layer.
-//   warps 10-13  positional-encoding producers (forward programs): sincosf in fp32, fp16 (hi[, lo]) rows written
-//                straight into the swizzled A chunk of the NEXT tile while the current tile is in flight.
+//                current step are still being drained.
+//   then         positional-encoding producer warp (forward programs): sincos in fp32, fp16 (hi[, lo]) rows written
+//                straight into the swizzled A chunk of the NEXT tile while the current tile is in flight; the last
+//                warp saves chunks with TMA stores.
+// Two tiles in flight (SLOTS = 2, the default of the 256-wide programs, launched as CTA pairs): warps 0 and 1 are the
+// MMA issuers of slot 0 and slot 1, warps 2-17 two groups of eight epilogue warps (which also write the PE chunk of
+// their slot's next tile), warp 18 the store warp, warp 19 the weight producer -- see the comment at chain_kernel.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
