@@ -88,10 +88,11 @@ class SinkhornMatchFn(torch.autograd.Function):
             # one pass over K per iteration (moda_sinkhorn_pass): d_i = K b_i, a_i = p1 / (d_i + delta) and, with the rows
             # still on chip, c_{i+1} = K^T a_i -- instead of two matrix-vector products that each stream the matrix
             c = torch.mv(K.t(), a)
+            acc = torch.zeros(it, m, device=K.device, dtype=K.dtype)   # the column sums of all passes: one fill
             for i in range(it):
                 b = (1.0 / m) / (c + dl)
                 d, a = torch.empty_like(a), torch.empty_like(a)
-                c_next = torch.zeros_like(c) if i + 1 < it else None
+                c_next = acc[i] if i + 1 < it else None
                 call("moda_sinkhorn_pass", ptr(K), n, m, ptr(b), ptr(d), ptr(a), ptr(c_next), 0, 1.0 / n, dl, None, None, stream())
                 As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
                 c = c_next
@@ -122,13 +123,14 @@ class SinkhornMatchFn(torch.autograd.Function):
         left, right = [], []            # gK += sum_k left_k (x) right_k
         fused = _fused_pass_ok(K)
         n, m = K.shape
+        acc = torch.zeros(it, m, device=K.device, dtype=K.dtype) if fused else None   # column sums of all passes
         for i in range(it, 0, -1):
             gc = -gb * Bs[i - 1] / (Cs[i - 1] + dl)
             left.append(As[i - 1]), right.append(gc)
             if i - 1 < 1:
                 break
             if fused:   # ga = K gc, gd = -ga a / (d + delta), gb = K^T gd in one pass over K
-                gd, gb = torch.empty(n, device=K.device, dtype=K.dtype), torch.zeros(m, device=K.device, dtype=K.dtype)
+                gd, gb = torch.empty(n, device=K.device, dtype=K.dtype), acc[i - 1]
                 call("moda_sinkhorn_pass", ptr(K), n, m, ptr(gc.contiguous()), None, ptr(gd), ptr(gb), 1, 0.0, dl,
                      ptr(As[i - 1]), ptr(Ds[i - 2]), stream())
             else:
