@@ -128,3 +128,53 @@ def test_motion_models_on_gpu_against_reference(kind, precision):
     dump_table("r02_motion_%s_%s" % (kind, precision), table)
     assert n >= 20, "too few gradients compared (%d)" % n
     assert not bad, "; ".join(bad)
+
+
+def test_lbs_and_flow_host_algebra_matches_the_oracle_on_cpu():
+    """The O(rays x bones) algebra of the alternative motion models is plain tensor code in the product (no kernel): on
+    the CPU it must agree with the oracle restatement, values and gradients -- bone_transform (rigid), matrix_to_quaternion
+    (incl. rotations whose largest quaternion component is not the real part), rts_invert, blend_skinning / lbs, the SO(3)
+    exponential map and the SE3head output stage."""
+    from moda_b200 import geom_utils as G
+    from moda_b200.nerf import so3_exp_map
+    gen = torch.Generator().manual_seed(2)
+    B, N, S = 7, 5, 9
+    # rotations by large angles about random axes: every pivot of matrix_to_quaternion gets used
+    w = torch.randn(N * B, 3, generator=gen) * 2.0
+    R = O.so3_exp(w)
+    assert max_abs(so3_exp_map(w), R) < 1e-6
+    q = G.matrix_to_quaternion(R)
+    assert max_abs(q, O.matrix_to_quat(R)) < 1e-6
+    assert len(set(O.matrix_to_quat(R).abs().argmax(-1).tolist())) >= 3, "fixture does not exercise several pivots"
+    T = 0.1 * torch.randn(N, B, 3, generator=gen)
+    bones = torch.cat([0.1 * torch.randn(B, 3, generator=gen), torch.nn.functional.normalize(torch.randn(B, 4, generator=gen), dim=-1),
+                       0.1 * torch.randn(B, 3, generator=gen)], -1)
+    skin = torch.softmax(torch.randn(N, S, B, generator=gen), -1)
+    xyz = torch.randn(N, S, 3, generator=gen)
+    up = torch.randn(N, S, 3, generator=gen)
+    ub = torch.randn(N, B, 10, generator=gen)
+    for backward in (True, False):
+        grads = []
+        for mod in ("product", "oracle"):
+            rts = torch.cat([R.reshape(N, B, 9), T], -1).reshape(N, B * 12).clone().requires_grad_(True)
+            b = bones.clone().requires_grad_(True)
+            sk = skin.clone().requires_grad_(True)
+            if mod == "product":
+                x, bd = G.lbs(b, rts, sk, xyz, backward=backward)
+            else:
+                x = O.lbs(b, rts, sk, xyz, backward=backward)
+                bd = O.bone_transform_rigid(b, rts)
+            ((x * up).sum() + (bd * ub).sum()).backward()
+            grads.append((x.detach(), bd.detach(), rts.grad, b.grad, sk.grad))
+        for a, c in zip(*grads):
+            assert rel_err(a, c) < 1e-5
+    rts3 = torch.cat([R.reshape(N, B, 3, 3), T[..., None]], -1)
+    assert max_abs(G.rts_invert(rts3), O.rts_invert(rts3)) < 1e-6
+    # SE3head output stage = the oracle's flow_field tail
+    from moda_b200.nerf import SE3head
+    raw = torch.randn(N, S, 9, generator=gen)
+    flow = SE3head.post(None, raw, xyz)
+    r = raw.reshape(-1, 9)
+    p = xyz.reshape(-1, 3) + 0.1 * r[:, 3:6]
+    ref = (O.so3_exp(r[:, :3]).matmul(p[..., None])[..., 0] - 0.1 * r[:, 3:6] + 0.1 * r[:, 6:9]).reshape(xyz.shape) - xyz
+    assert max_abs(flow, ref) < 1e-6
