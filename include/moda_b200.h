@@ -273,6 +273,14 @@ int moda_chain_skin_bwd(const float* gout /* (P,32) */, const float* scale, cons
                         const unsigned int* maskbits, long long P, void* G, void* d_dfe, void* d_fin,
                         void* dY /* (5,P,64) */, void* d_pe, int fold, cudaStream_t stream);
 
+/* xyz_encoding_final folded into dir_encoding (MODA_CHAIN_FOLD_FINAL): the product weights Wp (n, W) = Wd[:, :W] Wf and
+ * bias bp = bd + Wd[:, :W] bf, and the way back gWf += Wd1^T gWp, gbf += Wd1^T dbp, gWd[:, :W] += gWp Wf^T + dbp bf^T
+ * (nerf.py:182-190: two linear maps in a row).  O(weights) work, fp32. */
+int moda_fold_final(const float* Wd, int ldwd, const float* Wf, int ldwf, const float* bf, const float* bd, int n, int W,
+                    float* Wp, float* bp, cudaStream_t stream);
+int moda_unfold_final(const float* gWp, const float* dbp, const float* Wd, int ldwd, const float* Wf, int ldwf,
+                      const float* bf, int n, int W, float* gWf, int ldgf, float* gbf, float* gWd, int ldgd,
+                      cudaStream_t stream);
 /* One pass over the (n, m) Sinkhorn kernel matrix of feat_match (nnutils/loss_utils.py:347-386) serving both products of an
  * iteration: y = K x (row sums), z = g(y) elementwise (mode 0: p / (y + delta); mode 1: -y u / (v + delta)), w += K^T z
  * (column sums, w zeroed by the caller; NULL: row sums only).  K row-major fp32, m % 4 == 0, m <= 8192. */

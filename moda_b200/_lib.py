@@ -30,6 +30,8 @@ SIGNATURES = {
     "moda_embed_bwd": [c_p, c_i, c_p, c_i, c_p, c_i, c_ll, c_i, c_i, c_fp, c_i, c_p],
     "moda_sample_rays_fwd": [c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_i, c_i, c_p],
     "moda_points_from_depths": [c_p, c_p, c_p, c_p, c_i, c_i, c_p],
+    "moda_fold_final": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "moda_unfold_final": [c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     "moda_sinkhorn_pass": [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_p],
     "moda_adamw_flat": [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_p],
     "moda_sample_rays_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],

@@ -202,37 +202,22 @@ def _loss_scale(g):
 
 
 # ------------------------------------------------------------------------------- final layer folded into the dir layer
-def _dense1(t, width):
-    """One dense column segment (t (M, >= width), row pitch t.stride(0)) in the argument form of moda_linear_fwd / _wgrad."""
-    return 1, (ctypes.c_void_p * 1)(ptr(t)), _one(t.stride(0)), _one(width), _one(0), _one(1), None, 0
-
-
 def _fold(Wf, bf, Wd, bd, W):
     """xyz_encoding_final (no activation) followed by dir_encoding on [final | rest] (nerf.py:182-190) is one linear map
-    of the last hidden activation: W' = Wd[:, :W] Wf and b' = bd + Wd[:, :W] bf.  O(weights) work per call, on this
-    package's fp32 GEMM kernels (csrc/gemm.cu), like everything else on the step."""
+    of the last hidden activation: W' = Wd[:, :W] Wf and b' = bd + Wd[:, :W] bf.  O(weights) work per call, one launch
+    (moda_fold_final, csrc/gemm.cu)."""
     n, dev = Wd.shape[0], Wd.device
     Wp = torch.empty(n, W, device=dev, dtype=torch.float32)
-    # dA[M, K] = dY[M, N] W[N, K] with dY = Wd[:, :W], W = Wf
-    call("moda_linear_dgrad", n, W, W, ptr(Wd), Wd.stride(0), ptr(Wf), Wf.stride(0), 0, None, 0, 0, ptr(Wp), W, stream())
     bp = torch.empty(n, device=dev, dtype=torch.float32)
-    # Y[1, n] = bf[1, W] Wd[:, :W]^T + bd
-    call("moda_linear_fwd", 1, n, *_dense1(bf.reshape(1, W), W), ptr(Wd), Wd.stride(0), ptr(bd), 0, ptr(bp), n, stream())
+    call("moda_fold_final", ptr(Wd), Wd.stride(0), ptr(Wf), Wf.stride(0), ptr(bf), ptr(bd), n, W, ptr(Wp), ptr(bp), stream())
     return Wp, bp
 
 
 def _unfold_grads(gWp, dbp, Wf, bf, Wd, W, g_Wf, g_bf, g_Wd):
     """Maps the gradient of the folded layer back to the parameters it was made of: with W' = Wd1 Wf and b' = bd + Wd1 bf,
-    dWf += Wd1^T dW', dbf += Wd1^T db', dWd1 += dW' Wf^T + db' bf^T (dbd = db' is accumulated by the caller)."""
-    n = Wd.shape[0]
-    # dW[N, K] += dY[M, N]^T A[M, K]:  dWf (W, W) += Wd1^T gWp   and   dbf (W, 1) += Wd1^T db'
-    call("moda_linear_wgrad", n, W, *_dense1(gWp, W), ptr(Wd), Wd.stride(0), ptr(g_Wf), g_Wf.stride(0), 0, None, stream())
-    call("moda_linear_wgrad", n, W, *_dense1(dbp.reshape(n, 1), 1), ptr(Wd), Wd.stride(0), ptr(g_bf), 1, 0, None, stream())
-    # dA[M, K] += dY[M, N] W[N, K]:  dWd1 (n, W) += gWp Wf^T
-    WfT = Wf.t().contiguous()
-    call("moda_linear_dgrad", n, W, W, ptr(gWp), gWp.stride(0), ptr(WfT), W, 0, None, 0, 1, ptr(g_Wd), g_Wd.stride(0), stream())
-    # rank one: dWd1 (n, W) += db'^T bf   (M = 1 row)
-    call("moda_linear_wgrad", 1, n, *_dense1(bf.reshape(1, W), W), ptr(dbp), n, ptr(g_Wd), g_Wd.stride(0), 0, None, stream())
+    dWf += Wd1^T dW', dbf += Wd1^T db', dWd1 += dW' Wf^T + db' bf^T (dbd = db' is accumulated by the caller).  One launch."""
+    call("moda_unfold_final", ptr(gWp), ptr(dbp), ptr(Wd), Wd.stride(0), ptr(Wf), Wf.stride(0), ptr(bf), Wd.shape[0], W,
+         ptr(g_Wf), g_Wf.stride(0), ptr(g_bf), ptr(g_Wd), g_Wd.stride(0), stream())
 
 
 # ------------------------------------------------------------------------------------------------ nerf_coarse

@@ -416,3 +416,136 @@ extern "C" int moda_act_bwd(int kind, const float* y, int ldy, const float* g, i
   act_bwd_kernel<<<cdiv(M * N, 256), 256, 0, stream>>>(kind, y, ldy, g, ldg, out, ldo, M, N);
   return check_launch("act_bwd");
 }
+
+// ------------------------------------------------------------------------------ final layer folded into the direction layer
+// The chain programs run xyz_encoding_final (no activation) and dir_encoding as one layer (see MODA_CHAIN_FOLD_FINAL in
+// the header): W' (n, W) = Wd[:, :W] Wf, b' (n) = bd + Wd[:, :W] bf, and on the way back dWf (W, W) += Wd1^T dW', dbf (W) +=
+// Wd1^T db', dWd[:, :W] += dW' Wf^T + db' bf^T.  O(weights) work (n <= 128, W <= 256), one launch each way instead of
+// two / five launches of the general kernels above (which take ~10 us apiece on a 128 x 256 x 256 problem: 16 CTAs).
+namespace moda {
+constexpr int FOLD_THREADS = 256;
+constexpr int FT = 32;   // tile edge: a block makes 32 x 32 outputs, K walked in chunks of 32 through shared memory
+
+struct FoldArgs {
+  const float *Wd, *Wf, *bf, *bd, *gWp, *dbp;
+  float *Wp, *bp, *gWf, *gbf, *gWd;
+  int ldwd, ldwf, ldgf, ldgd, n, W;
+};
+
+// The three small products as one tiled routine C(m, c) (+)= sum_k A(m, k) B(k, c); the operand views (transposes, the
+// bias column / row riding along as one extra column or K index) are the only thing that differs:
+//   P = 0 fold      m = i < n,  c = j <= W, k < W      A = Wd[i][k]   B = Wf[k][j] | bf[k]        C = Wp[i][j] | bp[i] (+ bd)
+//   P = 1 unfold Wf m = k' < W, c = t <= W, k = i < n  A = Wd[i][k']  B = gWp[i][t] | dbp[i]      C = gWf[k'][t] | gbf[k']
+//   P = 2 unfold Wd m = i < n,  c = t < W,  k = j <= W A = gWp[i][j] | dbp[i]   B = Wf[t][j] | bf[t]   C = gWd[i][t]
+template <int P>
+struct FoldView {
+  static __device__ __forceinline__ int M(const FoldArgs& a) { return P == 1 ? a.W : a.n; }
+  static __device__ __forceinline__ int N(const FoldArgs& a) { return P == 2 ? a.W : a.W + 1; }
+  static __device__ __forceinline__ int K(const FoldArgs& a) { return P == 0 ? a.W : (P == 1 ? a.n : a.W + 1); }
+  static constexpr bool A_K_CONTIG = (P != 1);   // which index of the operand is contiguous in memory (picks the loader's
+  static constexpr bool B_K_CONTIG = (P == 2);   // thread mapping so that a warp reads whole cache lines)
+  static __device__ __forceinline__ float A(const FoldArgs& a, int m, int k) {
+    if (m >= M(a) || k >= K(a)) return 0.f;
+    if (P == 0) return __ldg(a.Wd + (size_t)m * a.ldwd + k);
+    if (P == 1) return __ldg(a.Wd + (size_t)k * a.ldwd + m);
+    return k < a.W ? __ldg(a.gWp + (size_t)m * a.W + k) : __ldg(a.dbp + m);
+  }
+  static __device__ __forceinline__ float B(const FoldArgs& a, int k, int c) {
+    if (c >= N(a) || k >= K(a)) return 0.f;
+    if (P == 0) return c < a.W ? __ldg(a.Wf + (size_t)k * a.ldwf + c) : __ldg(a.bf + k);
+    if (P == 1) return c < a.W ? __ldg(a.gWp + (size_t)k * a.W + c) : __ldg(a.dbp + k);
+    return k < a.W ? __ldg(a.Wf + (size_t)c * a.ldwf + k) : __ldg(a.bf + c);
+  }
+  static __device__ __forceinline__ void C(const FoldArgs& a, int m, int c, float v) {
+    if (m >= M(a) || c >= N(a)) return;
+    if (P == 0) {
+      if (c < a.W) a.Wp[(size_t)m * a.W + c] = v; else a.bp[m] = v + __ldg(a.bd + m);
+    } else if (P == 1) {
+      // atomic adds: the two evaluations of nerf_skin unfold into the same gradient buffers from different streams
+      atomicAdd(c < a.W ? a.gWf + (size_t)m * a.ldgf + c : a.gbf + m, v);
+    } else {
+      atomicAdd(a.gWd + (size_t)m * a.ldgd + c, v);
+    }
+  }
+};
+
+template <int P>
+__device__ __forceinline__ void fold_tile(const FoldArgs& a, int tm, int tn, float (*As)[FT + 1], float (*Bs)[FT + 1]) {
+  using V = FoldView<P>;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;   // 8 warps: warp wp owns rows 4 wp .. 4 wp + 3, lane = column
+  const int m0 = tm * FT, c0 = tn * FT, K = V::K(a);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float ra[4], rb[4];
+  // element u of this thread in a 32 x 32 operand tile: (x = wp + 8 u, y = lane), y along the contiguous index
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = wp + 8 * u;
+      ra[u] = V::A_K_CONTIG ? V::A(a, m0 + x, k0 + lane) : V::A(a, m0 + lane, k0 + x);
+      rb[u] = V::B_K_CONTIG ? V::B(a, k0 + lane, c0 + x) : V::B(a, k0 + x, c0 + lane);
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += FT) {
+    __syncthreads();   // the previous chunk has been consumed
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = wp + 8 * u;
+      if (V::A_K_CONTIG) As[lane][x] = ra[u]; else As[x][lane] = ra[u];      // As[k][m]
+      if (V::B_K_CONTIG) Bs[lane][x] = rb[u]; else Bs[x][lane] = rb[u];      // Bs[k][c]
+    }
+    __syncthreads();
+    if (k0 + FT < K) fetch(k0 + FT);   // the next chunk is in flight while this one is multiplied
+#pragma unroll
+    for (int k = 0; k < FT; ++k) {
+      const float b = Bs[k][lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(As[k][4 * wp + u], b, acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) V::C(a, m0 + 4 * wp + u, c0 + lane, acc[u]);
+}
+
+// blockIdx.x enumerates the tiles of product P0 first, then (unfold) those of P1
+template <int P0, int P1>
+__global__ void __launch_bounds__(FOLD_THREADS) fold_final_kernel(FoldArgs a, int tiles_n0, int ntiles0, int tiles_n1) {
+  __shared__ float As[FT][FT + 1];
+  __shared__ float Bs[FT][FT + 1];
+  int t = blockIdx.x;
+  if (t < ntiles0) {
+    fold_tile<P0>(a, t / tiles_n0, t % tiles_n0, As, Bs);
+  } else {
+    t -= ntiles0;
+    fold_tile<P1>(a, t / tiles_n1, t % tiles_n1, As, Bs);
+  }
+}
+}  // namespace moda
+
+// Wp (n, W) = Wd[:, :W] Wf,  bp (n) = bd + Wd[:, :W] bf      (Wd (n, >= W) with row pitch ldwd, Wf (W, W) pitch ldwf)
+extern "C" int moda_fold_final(const float* Wd, int ldwd, const float* Wf, int ldwf, const float* bf, const float* bd, int n,
+                               int W, float* Wp, float* bp, cudaStream_t stream) {
+  using namespace moda;
+  MODA_REQUIRE(Wd && Wf && bf && bd && Wp && bp && n > 0 && W > 0 && ldwd >= W && ldwf >= W, "fold_final: bad arguments");
+  FoldArgs a{};
+  a.Wd = Wd; a.Wf = Wf; a.bf = bf; a.bd = bd; a.Wp = Wp; a.bp = bp; a.ldwd = ldwd; a.ldwf = ldwf; a.n = n; a.W = W;
+  const int tm = cdiv(n, FT), tn = cdiv(W + 1, FT);
+  fold_final_kernel<0, 0><<<tm * tn, FOLD_THREADS, 0, stream>>>(a, tn, tm * tn, 1);
+  return check_launch("fold_final");
+}
+
+// gWf (W, W) += Wd1^T gWp,  gbf (W) += Wd1^T dbp,  gWd[:, :W] (n, W) += gWp Wf^T + dbp bf^T   (atomic adds)
+extern "C" int moda_unfold_final(const float* gWp, const float* dbp, const float* Wd, int ldwd, const float* Wf, int ldwf,
+                                 const float* bf, int n, int W, float* gWf, int ldgf, float* gbf, float* gWd, int ldgd,
+                                 cudaStream_t stream) {
+  using namespace moda;
+  MODA_REQUIRE(gWp && dbp && Wd && Wf && bf && gWf && gbf && gWd && n > 0 && W > 0 && ldwd >= W && ldwf >= W && ldgf >= W &&
+                   ldgd >= W, "unfold_final: bad arguments");
+  FoldArgs a{};
+  a.gWp = gWp; a.dbp = dbp; a.Wd = Wd; a.Wf = Wf; a.bf = bf; a.gWf = gWf; a.gbf = gbf; a.gWd = gWd;
+  a.ldwd = ldwd; a.ldwf = ldwf; a.ldgf = ldgf; a.ldgd = ldgd; a.n = n; a.W = W;
+  const int tn1 = cdiv(W + 1, FT), nt1 = cdiv(W, FT) * tn1;      // gWf | gbf
+  const int tn2 = cdiv(W, FT), nt2 = cdiv(n, FT) * tn2;          // gWd[:, :W]
+  fold_final_kernel<1, 2><<<nt1 + nt2, FOLD_THREADS, 0, stream>>>(a, tn1, nt1, tn2);
+  return check_launch("unfold_final");
+}
