@@ -344,14 +344,16 @@ __global__ void amax_kernel(const float* __restrict__ g, long long n, unsigned i
   float m = 0.f;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-    // 128-bit loads, two per trip in flight
+    // 128-bit loads, four per trip in flight (at two the 134 MB delta-logit gradient streamed at 2.9 TB/s)
     const float4* g4 = reinterpret_cast<const float4*>(g);
     const long long n4 = n >> 2;
     long long i = tid;
-    for (; i + nth < n4; i += 2 * nth) {
-      const float4 a = __ldg(g4 + i), b = __ldg(g4 + i + nth);
+    for (; i + 3 * nth < n4; i += 4 * nth) {
+      const float4 a = __ldcs(g4 + i), b = __ldcs(g4 + i + nth), c = __ldcs(g4 + i + 2 * nth), d = __ldcs(g4 + i + 3 * nth);
       m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
       m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
     }
     for (; i < n4; i += nth) {
       const float4 a = __ldg(g4 + i);
@@ -513,7 +515,7 @@ extern "C" int moda_loss_scale(const float* g, long long n, float target, unsign
                                cudaStream_t stream) {
   MODA_REQUIRE(g && work && scale2 && target > 0.f, "loss_scale: bad arguments");
   cudaMemsetAsync(work, 0, sizeof(unsigned int), stream);
-  if (n > 0) amax_kernel<<<148 * 2, 256, 0, stream>>>(g, n, work);
+  if (n > 0) amax_kernel<<<148 * 4, 256, 0, stream>>>(g, n, work);
   scale_from_amax_kernel<<<1, 1, 0, stream>>>(work, target, scale2);
   return check_launch("loss_scale");
 }

@@ -6,6 +6,7 @@ rendering.py and is built from these.
 """
 import ctypes
 
+import functools
 import torch
 
 from . import _lib
@@ -24,17 +25,21 @@ def _win_array(win):
 
 
 def pe_window(n_freqs, alpha):
-    """nerf.py:63-66, evaluated in fp32 exactly like the reference does (torch ops on a CPU tensor)."""
-    import math
+    """nerf.py:63-66, evaluated in fp32 exactly like the reference does (torch ops on a CPU tensor).  A pure function of two
+    numbers asked for several times per step: memoised."""
     if n_freqs <= 0:
         return []
-    if alpha is None:
-        alpha = n_freqs
+    return list(_pe_window(int(n_freqs), float(n_freqs if alpha is None else alpha)))
+
+
+@functools.lru_cache(maxsize=64)
+def _pe_window(n_freqs, alpha):
+    import math
     a = torch.as_tensor(alpha, dtype=torch.float32).cpu()
     w = a - torch.arange(n_freqs, dtype=torch.float32)
     w = torch.clamp(w, 0.0, 1.0)
     w = 0.5 * (1 + torch.cos(math.pi * w + math.pi))
-    return [float(x) for x in w]
+    return tuple(float(x) for x in w)
 
 
 class _P:
