@@ -283,9 +283,25 @@ int moda_unfold_final(const float* gWp, const float* dbp, const float* Wd, int l
                       cudaStream_t stream);
 /* One pass over the (n, m) Sinkhorn kernel matrix of feat_match (nnutils/loss_utils.py:347-386) serving both products of an
  * iteration: y = K x (row sums), z = g(y) elementwise (mode 0: p / (y + delta); mode 1: -y u / (v + delta)), w += K^T z
- * (column sums, w zeroed by the caller; NULL: row sums only).  K row-major fp32, m % 4 == 0, m <= 8192. */
+ * (column sums, w zeroed by the caller; NULL: row sums only).  K row-major fp32, m % 4 == 0, m <= 8192.
+ * The input vector is either given (xmode 0: x) or formed while it is staged and written to xout (when non-null):
+ * xmode 1: x = xp / (xc + delta) (b_i of loss_utils.py:372 from the column sums), xmode 2: x = -xg xb / (xc + delta) (the
+ * adjoint's gc_i). */
 int moda_sinkhorn_pass(const float* K, int n, int m, const float* x, float* y, float* z, float* w, int mode, float p,
-                       float delta, const float* u, const float* v, cudaStream_t stream);
+                       float delta, const float* u, const float* v, int xmode, const float* xc, const float* xg,
+                       const float* xb, float xp, float* xout, cudaStream_t stream);
+/* The kernel matrix itself, K (n, m) = exp((F V^T - 1) / eps) from unit features F (n, d), V (m, d), d = 16
+ * (loss_utils.py:325-332, 359); c_out (m, zeroed by the caller, may be NULL) += cs_scale x column sums of K. */
+int moda_sinkhorn_matrix(const float* F, const float* V, int n, int m, int d, float eps, float cs_scale, float* K,
+                         float* c_out, cudaStream_t stream);
+/* out (n, 4) = K X, X (m, 4): the soft-argmax numerator and row sum of loss_utils.py:383-386 in one pass over K. */
+int moda_sinkhorn_rows4(const float* K, int n, int m, const float* X, float* out, cudaStream_t stream);
+/* out (m, 4, zeroed by the caller) += K^T Wt, Wt (n, 4): the direct term of the adjoint in one pass over K. */
+int moda_sinkhorn_cols4(const float* K, int n, int m, const float* Wt, float* out, cudaStream_t stream);
+/* gF (n, d) += gcost V, gV (m, d) += gcost^T F with gcost = K / eps * (L Rm) never materialised: L (n, R), Rm (R, m) are the
+ * low-rank factors of dLoss/dK (R = 44: 4 direct + 39 sweep terms + 1 zero), d = 16. */
+int moda_sinkhorn_gcost(const float* K, int n, int m, const float* L, const float* Rm, int R, const float* F, const float* V,
+                        int d, float eps, float* gF, float* gV, cudaStream_t stream);
 /* AdamW step (torch.optim.AdamW as the reference's training loop uses it, nnutils/train_utils.py:177-222) on the flat
  * parameter / gradient buffers of the data-parallel path; m, v: moment buffers, state: 3 device floats {step count,
  * lr / (1 - beta1^t), sqrt(1 - beta2^t)}, advanced on the device so that the call can be captured in a CUDA graph.

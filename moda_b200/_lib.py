@@ -32,7 +32,11 @@ SIGNATURES = {
     "moda_points_from_depths": [c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "moda_fold_final": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "moda_unfold_final": [c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
-    "moda_sinkhorn_pass": [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_p],
+    "moda_sinkhorn_pass": [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_f, c_p, c_p],
+    "moda_sinkhorn_matrix": [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "moda_sinkhorn_rows4": [c_p, c_i, c_i, c_p, c_p, c_p],
+    "moda_sinkhorn_cols4": [c_p, c_i, c_i, c_p, c_p, c_p],
+    "moda_sinkhorn_gcost": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_p],
     "moda_adamw_flat": [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_p],
     "moda_sample_rays_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "moda_dq_unary_fwd": [c_i, c_p, c_p, c_ll, c_p],

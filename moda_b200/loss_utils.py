@@ -60,9 +60,12 @@ def feat_match_loss(nerf_feat, embedding_xyz, feats, pts, pts_prob, bound, use_c
     return pts_pred, pts_exp, feat_err, corr_err
 
 
-def _fused_pass_ok(K):
-    """moda_sinkhorn_pass takes fp32 CUDA matrices with m % 4 == 0 and m <= 8192 (the 20^3 lattice has 8000 points)."""
-    return K.is_cuda and K.dtype == torch.float32 and K.is_contiguous() and K.shape[1] % 4 == 0 and K.shape[1] <= 8192
+def _fused_ok(feats, vol_feat):
+    """The one-pass Sinkhorn kernels (csrc/sinkhorn.cu) take 16-channel fp32 CUDA features and a lattice of m % 4 == 0, m <=
+    8192 points; anything else (the CPU oracle tests, other feature widths) runs the same algebra as torch ops."""
+    m = vol_feat.shape[0]
+    return (feats.is_cuda and feats.dtype == torch.float32 and vol_feat.dtype == torch.float32 and feats.shape[1] == 16 and
+            vol_feat.shape[1] == 16 and m % 4 == 0 and m <= 8192 and feats.shape[0] > 0)
 
 
 class SinkhornMatchFn(torch.autograd.Function):
@@ -79,40 +82,66 @@ class SinkhornMatchFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, vol_feat, query):
+        if _fused_ok(feats, vol_feat):
+            return SinkhornMatchFn._forward_fused(ctx, feats, vol_feat, query)
         K = torch.exp((feats.matmul(vol_feat.t()) - 1.0) / SinkhornMatchFn.EPS)
         n, m = K.shape
         a = torch.full((n,), 1.0 / n, device=K.device, dtype=K.dtype)
         As, Bs, Cs, Ds = [a], [], [], []
         dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
-        if _fused_pass_ok(K):
-            # one pass over K per iteration (moda_sinkhorn_pass): d_i = K b_i, a_i = p1 / (d_i + delta) and, with the rows
-            # still on chip, c_{i+1} = K^T a_i -- instead of two matrix-vector products that each stream the matrix
+        for _ in range(it):
             c = torch.mv(K.t(), a)
-            acc = torch.zeros(it, m, device=K.device, dtype=K.dtype)   # the column sums of all passes: one fill
-            for i in range(it):
-                b = (1.0 / m) / (c + dl)
-                d, a = torch.empty_like(a), torch.empty_like(a)
-                c_next = acc[i] if i + 1 < it else None
-                call("moda_sinkhorn_pass", ptr(K), n, m, ptr(b), ptr(d), ptr(a), ptr(c_next), 0, 1.0 / n, dl, None, None, stream())
-                As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
-                c = c_next
-        else:
-            for _ in range(it):
-                c = torch.mv(K.t(), a)
-                b = (1.0 / m) / (c + dl)
-                d = torch.mv(K, b)
-                a = (1.0 / n) / (d + dl)
-                As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
+            b = (1.0 / m) / (c + dl)
+            d = torch.mv(K, b)
+            a = (1.0 / n) / (d + dl)
+            As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
         # T = a K b^T row-normalised: with the final a this is K b^T / rowsum; the reference normalises a K b^T whose row
         # sums are a_20 (K b_20): identical up to rounding
         s = Ds[-1]
         pts = (K * Bs[-1][None]).matmul(query) / s[:, None]
+        ctx.fused = False
+        ctx.save_for_backward(feats, vol_feat, query, K, pts, s)
+        ctx.hist = (As, Bs, Cs, Ds)
+        return pts
+
+    @staticmethod
+    def _forward_fused(ctx, feats, vol_feat, query):
+        """The same iteration with every (n x m)-sized operation as one pass over K (csrc/sinkhorn.cu): the matrix is written
+        once together with the first column sums (moda_sinkhorn_matrix); each iteration is ONE pass (moda_sinkhorn_pass: b_i
+        from c_i while it is staged, d_i = K b_i, a_i = p1 / (d_i + delta) and, with the rows still on chip, c_{i+1} = K^T
+        a_i); the soft-argmax is one pass with four vectors (moda_sinkhorn_rows4)."""
+        feats, vol_feat, query = feats.contiguous(), vol_feat.contiguous(), query.contiguous()
+        n, m, dev = feats.shape[0], vol_feat.shape[0], feats.device
+        dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        K = new(n, m)
+        acc = torch.zeros(it, m, device=dev, dtype=torch.float32)     # the column sums c_1 .. c_20: one fill
+        call("moda_sinkhorn_matrix", ptr(feats), ptr(vol_feat), n, m, feats.shape[1], SinkhornMatchFn.EPS, 1.0 / n, ptr(K),
+             ptr(acc[0]), stream())
+        As, Bs, Cs, Ds = [torch.full((n,), 1.0 / n, device=dev, dtype=torch.float32)], [], [], []
+        hist = new(it, m)                                                  # b_1 .. b_20
+        rows = new(2 * it, n)                                              # d_i, a_i
+        for i in range(it):
+            c, b, d, a = acc[i], hist[i], rows[2 * i], rows[2 * i + 1]
+            c_next = acc[i + 1] if i + 1 < it else None
+            call("moda_sinkhorn_pass", ptr(K), n, m, None, ptr(d), ptr(a), ptr(c_next), 0, 1.0 / n, dl, None, None,
+                 1, ptr(c), None, None, 1.0 / m, ptr(b), stream())
+            As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
+        # pts = (K b) Q / rowsum: X = b (x) [Qx Qy Qz 1]; the fourth product is the row sum d_20 again
+        X = torch.cat([query, torch.ones_like(query[:, :1])], 1) * Bs[-1][:, None]
+        out4 = new(n, 4)
+        call("moda_sinkhorn_rows4", ptr(K), n, m, ptr(X), ptr(out4), stream())
+        s = Ds[-1]
+        pts = out4[:, :3] / s[:, None]
+        ctx.fused = True
         ctx.save_for_backward(feats, vol_feat, query, K, pts, s)
         ctx.hist = (As, Bs, Cs, Ds)
         return pts
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.fused:
+            return SinkhornMatchFn._backward_fused(ctx, g)
         feats, vol_feat, query, K, pts, s = ctx.saved_tensors
         As, Bs, Cs, Ds = ctx.hist
         dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
@@ -121,22 +150,14 @@ class SinkhornMatchFn(torch.autograd.Function):
         gb = (U * K).sum(0)
         gK = U * b20[None]
         left, right = [], []            # gK += sum_k left_k (x) right_k
-        fused = _fused_pass_ok(K)
-        n, m = K.shape
-        acc = torch.zeros(it, m, device=K.device, dtype=K.dtype) if fused else None   # column sums of all passes
         for i in range(it, 0, -1):
             gc = -gb * Bs[i - 1] / (Cs[i - 1] + dl)
             left.append(As[i - 1]), right.append(gc)
             if i - 1 < 1:
                 break
-            if fused:   # ga = K gc, gd = -ga a / (d + delta), gb = K^T gd in one pass over K
-                gd, gb = torch.empty(n, device=K.device, dtype=K.dtype), acc[i - 1]
-                call("moda_sinkhorn_pass", ptr(K), n, m, ptr(gc.contiguous()), None, ptr(gd), ptr(gb), 1, 0.0, dl,
-                     ptr(As[i - 1]), ptr(Ds[i - 2]), stream())
-            else:
-                ga = torch.mv(K, gc)
-                gd = -ga * As[i - 1] / (Ds[i - 2] + dl)
-                gb = torch.mv(K.t(), gd)
+            ga = torch.mv(K, gc)
+            gd = -ga * As[i - 1] / (Ds[i - 2] + dl)
+            gb = torch.mv(K.t(), gd)
             left.append(gd), right.append(Bs[i - 2])
         gK.addmm_(torch.stack(left, 1), torch.stack(right, 0))
         gcost = gK.mul_(K).mul_(1.0 / SinkhornMatchFn.EPS)
@@ -144,6 +165,53 @@ class SinkhornMatchFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             gq = (K * b20[None] / s[:, None]).t().matmul(g)
         return gcost.matmul(vol_feat), gcost.t().matmul(feats), gq
+
+    @staticmethod
+    def _backward_fused(ctx, g):
+        """The reverse sweep with one pass over K per iteration, and dLoss/dK kept in factored form: the direct term
+        U (.) b_20 with U[r][j] = (g_r . Q_j - g_r . pts_r) / s_r has rank 4 and the sweep adds 39 outer products, so
+        gcost = K / eps * (L Rm) with L (n, 44), Rm (44, m) is consumed tile by tile (moda_sinkhorn_gcost) and never
+        written."""
+        feats, vol_feat, query, K, pts, s = ctx.saved_tensors
+        As, Bs, Cs, Ds = ctx.hist
+        dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
+        n, m, dev = K.shape[0], K.shape[1], K.device
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        g = g.contiguous().float()
+        b20 = Bs[-1]
+        RANK = 44                       # 4 (direct term) + 20 (a_{i-1} (x) gc_i) + 19 (gd_{i-1} (x) b_{i-1}) + 1 zero
+        L, Rm = torch.zeros(n, RANK, device=dev, dtype=torch.float32), torch.zeros(RANK, m, device=dev, dtype=torch.float32)
+        # direct term: U = alpha . Q^T - beta with alpha = g / s, beta = (g . pts) / s
+        L[:, 0:3] = g / s[:, None]
+        L[:, 3] = -(g * pts).sum(-1) / s
+        Rm[0:3] = query.t() * b20[None]
+        Rm[3] = b20
+        # gb_20 = sum_r K[r][j] U[r][j] = Q_j . (K^T alpha)_j - (K^T beta)_j: one pass with four row-weight vectors
+        cols = torch.zeros(m, 4, device=dev, dtype=torch.float32)
+        call("moda_sinkhorn_cols4", ptr(K), n, m, ptr(L[:, 0:4].contiguous()), ptr(cols), stream())
+        gb = ((cols[:, 0:3] * query).sum(-1) + cols[:, 3]).contiguous()
+        acc = torch.zeros(it, m, device=dev, dtype=torch.float32)       # gb_{i-1}: column sums of the passes
+        gds = new(it - 1, n)
+        # factor columns 4, 6, .. 42: a_{i-1} (x) gc_i for i = 20 .. 1; columns 5, 7, .. 41: gd_{i-1} (x) b_{i-1} for i = 20 .. 2
+        for q, i in enumerate(range(it, 1, -1)):
+            # gc_i = -gb_i b_i / (c_i + delta) formed while staged (and written to its row of Rm), ga = K gc_i,
+            # gd = -ga a_{i-1} / (d_{i-1} + delta), gb_{i-1} = K^T gd: one pass over K
+            gb_next = acc[i - 1]
+            call("moda_sinkhorn_pass", ptr(K), n, m, None, None, ptr(gds[q]), ptr(gb_next), 1, 0.0, dl, ptr(As[i - 1]),
+                 ptr(Ds[i - 2]), 2, ptr(Cs[i - 1]), ptr(gb), ptr(Bs[i - 1]), 0.0, ptr(Rm[4 + 2 * q]), stream())
+            gb = gb_next
+        Rm[4 + 2 * (it - 1)] = -gb * Bs[0] / (Cs[0] + dl)
+        L[:, 4:4 + 2 * it:2] = torch.stack([As[i - 1] for i in range(it, 0, -1)], 1)
+        L[:, 5:5 + 2 * (it - 1):2] = gds.t()
+        Rm[5:5 + 2 * (it - 1):2] = torch.stack([Bs[i - 2] for i in range(it, 1, -1)], 0)
+        gF = torch.zeros_like(feats)
+        gV = torch.zeros_like(vol_feat)
+        call("moda_sinkhorn_gcost", ptr(K), n, m, ptr(L), ptr(Rm), RANK, ptr(feats), ptr(vol_feat), feats.shape[1],
+             SinkhornMatchFn.EPS, ptr(gF), ptr(gV), stream())
+        gq = None
+        if ctx.needs_input_grad[2]:
+            gq = (K * b20[None] / s[:, None]).t().matmul(g)
+        return gF, gV, gq
 
 
 def feat_match(nerf_feat, embedding_xyz, feats, bound, grid_size=20, use_corr=True, use_ot=False, is_training=True,

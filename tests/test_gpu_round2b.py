@@ -247,7 +247,8 @@ def test_sinkhorn_pass_against_matrix_vector_products():
         for mode in (0, 1):
             y, z = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
             w = torch.zeros(m, device=DEV)
-            call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y), ptr(z), ptr(w), mode, 1.0 / n, 1e-8, ptr(u), ptr(v), stream())
+            call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y), ptr(z), ptr(w), mode, 1.0 / n, 1e-8, ptr(u), ptr(v),
+                 0, None, None, None, 0.0, None, stream())
             yd = Kd @ xd
             zd = (1.0 / n) / (yd + 1e-8) if mode == 0 else -yd * u.double() / (v.double() + 1e-8)
             wd = Kd.t() @ zd
@@ -255,5 +256,84 @@ def test_sinkhorn_pass_against_matrix_vector_products():
                 e = float((got.double() - ref).abs().max() / ref.abs().max())
                 assert e < 5e-6, (n, m, mode, name, e)
         y2 = torch.empty(n, device=DEV)
-        call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y2), None, None, 0, 1.0, 0.0, None, None, stream())
+        call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x), ptr(y2), None, None, 0, 1.0, 0.0, None, None,
+             0, None, None, None, 0.0, None, stream())
         assert float((y2.double() - Kd @ xd).abs().max() / (Kd @ xd).abs().max()) < 5e-6
+        # input vector formed while staged: xmode 1 (b = p2 / (c + delta)) and xmode 2 (gc = -gb b / (c + delta))
+        c = torch.rand(m, generator=gen).to(DEV) + 0.1
+        gbv = torch.randn(m, generator=gen).to(DEV)
+        for xmode, xref in ((1, (1.0 / m) / (c.double() + 1e-8)), (2, -gbv.double() * x.double() / (c.double() + 1e-8))):
+            y3, xo = torch.empty(n, device=DEV), torch.empty(m, device=DEV)
+            call("moda_sinkhorn_pass", ptr(K), n, m, None, ptr(y3), None, None, 0, 1.0, 0.0, None, None,
+                 xmode, ptr(c), ptr(gbv), ptr(x), 1.0 / m, ptr(xo), stream())
+            assert float((xo.double() - xref).abs().max() / xref.abs().max()) < 1e-6, (n, m, xmode)
+            assert float((y3.double() - Kd @ xref).abs().max() / (Kd @ xref).abs().max()) < 5e-6, (n, m, xmode)
+
+
+def test_sinkhorn_matrix_rows_cols_gcost_against_fp64():
+    """The other one-pass kernels of the feature matching (csrc/sinkhorn.cu) against torch in fp64: the matrix exp((F V^T -
+    1) / eps) with its first column sums, the four-vector row and column products, and gF / gV from the factored cost
+    gradient; ragged sizes (rows not a multiple of the row blocks, columns not a multiple of 256)."""
+    from moda_b200._lib import call, ptr, stream
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(10)
+    for n, m in ((1000 + 3, 8000), (37, 64), (1, 260)):
+        f = F.normalize(torch.randn(n, 16, generator=gen), 2, -1).to(DEV)
+        v = F.normalize(torch.randn(m, 16, generator=gen), 2, -1).to(DEV)
+        K = torch.empty(n, m, device=DEV)
+        c = torch.zeros(m, device=DEV)
+        call("moda_sinkhorn_matrix", ptr(f), ptr(v), n, m, 16, 0.03, 1.0 / n, ptr(K), ptr(c), stream())
+        Kd = torch.exp((f.double() @ v.double().t() - 1.0) / 0.03)
+        # the exponent is (f.v - 1) / 0.03: one fp32 rounding of f.v (6e-8) is a relative 2e-6 in K
+        assert float(((K.double() - Kd).abs() / Kd).max()) < 2e-5, (n, m)
+        assert float((c.double() - Kd.sum(0) / n).abs().max() / (Kd.sum(0) / n).abs().max()) < 1e-5
+        X = torch.randn(m, 4, generator=gen).to(DEV)
+        out = torch.empty(n, 4, device=DEV)
+        call("moda_sinkhorn_rows4", ptr(K), n, m, ptr(X), ptr(out), stream())
+        ref = K.double() @ X.double()
+        assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6, (n, m)
+        Wt = torch.randn(n, 4, generator=gen).to(DEV)
+        oc = torch.zeros(m, 4, device=DEV)
+        call("moda_sinkhorn_cols4", ptr(K), n, m, ptr(Wt), ptr(oc), stream())
+        ref = K.double().t() @ Wt.double()
+        assert float((oc.double() - ref).abs().max() / ref.abs().max()) < 5e-6, (n, m)
+        L = torch.randn(n, 44, generator=gen).to(DEV)
+        Rm = torch.randn(44, m, generator=gen).to(DEV)
+        gF, gV = torch.zeros(n, 16, device=DEV), torch.zeros(m, 16, device=DEV)
+        call("moda_sinkhorn_gcost", ptr(K), n, m, ptr(L), ptr(Rm), 44, ptr(f), ptr(v), 16, 0.03, ptr(gF), ptr(gV), stream())
+        gc = K.double() * (L.double() @ Rm.double()) / 0.03
+        for name, got, ref in (("gF", gF, gc @ v.double()), ("gV", gV, gc.t() @ f.double())):
+            assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-5, (n, m, name)
+
+
+def test_sinkhorn_match_fused_against_torch_ops_and_fp64():
+    """SinkhornMatchFn on the one-pass kernels against the same algebra as torch ops (the path the CPU oracle test pins
+    against autograd through the reference's loop) in fp64: matched points and the gradients of both feature sets."""
+    from moda_b200 import loss_utils as LU
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(11)
+    n, m = 300, 512
+    f0 = torch.randn(n, 16, generator=gen)
+    v0 = torch.randn(m, 16, generator=gen)
+    q = (torch.rand(m, 3, generator=gen) - 0.5).to(DEV)
+    gout = torch.randn(n, 3, generator=gen).to(DEV)
+
+    def run(dtype, fused):
+        f = f0.to(DEV, dtype).requires_grad_(True)
+        v = v0.to(DEV, dtype).requires_grad_(True)
+        ok = LU._fused_ok
+        LU._fused_ok = (lambda a, b: ok(a, b)) if fused else (lambda a, b: False)
+        try:
+            pts = LU.SinkhornMatchFn.apply(F.normalize(f, 2, -1), F.normalize(v, 2, -1), q.to(dtype))
+            (pts * gout.to(dtype)).sum().backward()
+        finally:
+            LU._fused_ok = ok
+        return pts.detach().double(), f.grad.double(), v.grad.double()
+
+    ref = run(torch.float64, False)
+    plain = run(torch.float32, False)
+    fused = run(torch.float32, True)
+    for name, r, p, g in zip(("pts", "d feats", "d lattice feats"), ref, plain, fused):
+        scale = float(r.abs().max())
+        e_plain, e_fused = float((p - r).abs().max()) / scale, float((g - r).abs().max()) / scale
+        assert e_fused < max(2e-5, 3 * e_plain), (name, e_fused, e_plain)
