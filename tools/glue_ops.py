@@ -1,5 +1,5 @@
 """Which python lines launch the ATen glue kernels of a step (a TorchDispatchMode logging op, source line and output size):
-python tools/glue_stacks.py [rays] [full]"""
+python tools/glue_ops.py [rays] [full]"""
 import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
