@@ -302,6 +302,16 @@ int moda_sinkhorn_cols4(const float* K, int n, int m, const float* Wt, float* ou
  * low-rank factors of dLoss/dK (R = 44: 4 direct + 39 sweep terms + 1 zero), d = 16. */
 int moda_sinkhorn_gcost(const float* K, int n, int m, const float* L, const float* Rm, int R, const float* F, const float* V,
                         int d, float eps, float* gF, float* gV, cudaStream_t stream);
+/* Flow rendering of the third warp (rendering.py:434-459, 480-499: obj_to_cam, pinhole_cam, vrender_flo of
+ * geom_utils.py:567-581, 654-672, 1704-1743) for one paired frame: the warped samples xyz (N, S, 3) are projected with the
+ * ray's camera R (N, 9 row-major), T (N, 3), K (N, 4) = (fx, fy, px, py) and flo (N, 2) = sum_s w'_s / (1e-9 + sum w') (xy'_s -
+ * xys) * 2 / img_size over the valid samples (z >= 1e-5 and |xy| <= 2 img_size), valid (N) = 1 when every sample is.  The
+ * backward entry recomputes the projection and overwrites gxyz (N, S, 3), gR (N, 9), gT (N, 3), gK (N, 4), gw (N, S). */
+int moda_flow_render_fwd(const float* xyz, const float* R, const float* T, const float* K, const float* w, const float* xys,
+                         int N, int S, float img_size, float* flo, float* valid, cudaStream_t stream);
+int moda_flow_render_bwd(const float* xyz, const float* R, const float* T, const float* K, const float* w, const float* xys,
+                         const float* gflo, int N, int S, float img_size, float* gxyz, float* gR, float* gT, float* gK,
+                         float* gw, cudaStream_t stream);
 /* AdamW step (torch.optim.AdamW as the reference's training loop uses it, nnutils/train_utils.py:177-222) on the flat
  * parameter / gradient buffers of the data-parallel path; m, v: moment buffers, state: 3 device floats {step count,
  * lr / (1 - beta1^t), sqrt(1 - beta2^t)}, advanced on the device so that the call can be captured in a CUDA graph.

@@ -37,6 +37,8 @@ SIGNATURES = {
     "moda_sinkhorn_rows4": [c_p, c_i, c_i, c_p, c_p, c_p],
     "moda_sinkhorn_cols4": [c_p, c_i, c_i, c_p, c_p, c_p],
     "moda_sinkhorn_gcost": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_p],
+    "moda_flow_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p],
+    "moda_flow_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "moda_adamw_flat": [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_f, c_p],
     "moda_sample_rays_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "moda_dq_unary_fwd": [c_i, c_p, c_p, c_ll, c_p],

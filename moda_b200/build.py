@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoda_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "skin.cu", "composite.cu", "gemm.cu", "sample_pdf.cu", "raysum.cu", "sinkhorn.cu", "tc_gemm.cu", "tc_support.cu", "chain.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "skin.cu", "composite.cu", "gemm.cu", "sample_pdf.cu", "raysum.cu", "sinkhorn.cu", "flow.cu", "tc_gemm.cu", "tc_support.cu", "chain.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -376,6 +376,50 @@ def vrender_flo(weights_coarse, xyz_coarse_target, xys, img_size):
     return flo, valid
 
 
+class FlowRenderFn(torch.autograd.Function):
+    """``vrender_flo(weights, pinhole_cam(obj_to_cam(xyz, R, T), K), xys, img_size)`` as one kernel each way
+    (csrc/flow.cu): xyz (N,S,3) root-frame samples of a paired frame, R (N,9), T (N,3), K (N,4), weights (N,S), xys (N,2)."""
+
+    @staticmethod
+    def forward(ctx, xyz, R, T, K, weights, xys, img_size):
+        from ._lib import call, ptr, stream, f32
+        xyz, R, T, K, weights, xys = (f32(t).contiguous() for t in (xyz, R, T, K, weights, xys))
+        N, S = weights.shape
+        flo = torch.empty(N, 2, device=xyz.device, dtype=torch.float32)
+        valid = torch.empty(N, 1, device=xyz.device, dtype=torch.float32)
+        call("moda_flow_render_fwd", ptr(xyz), ptr(R), ptr(T), ptr(K), ptr(weights), ptr(xys), N, S, float(img_size), ptr(flo),
+             ptr(valid), stream())
+        ctx.save_for_backward(xyz, R, T, K, weights, xys)
+        ctx.img_size = float(img_size)
+        ctx.mark_non_differentiable(valid)
+        return flo, valid
+
+    @staticmethod
+    def backward(ctx, gflo, _gvalid):
+        from ._lib import call, ptr, stream, f32
+        xyz, R, T, K, weights, xys = ctx.saved_tensors
+        N, S = weights.shape
+        new = lambda *shape: torch.empty(*shape, device=xyz.device, dtype=torch.float32)
+        gxyz, gR, gT, gK, gw = new(N, S, 3), new(N, 9), new(N, 3), new(N, 4), new(N, S)
+        call("moda_flow_render_bwd", ptr(xyz), ptr(R), ptr(T), ptr(K), ptr(weights), ptr(xys), ptr(f32(gflo).contiguous()), N, S,
+             ctx.img_size, ptr(gxyz), ptr(gR), ptr(gT), ptr(gK), ptr(gw), stream())
+        return gxyz, gR, gT, gK, gw, None, None
+
+
+def project_render_flo(weights_coarse, xyz_root, rtk_vec, xys, img_size, N_rays):
+    """rendering.py:434-459 + 480-499 for one paired frame: project the warped samples (N,S,3) with the frame's camera
+    (rtk_vec (N,21) = R | T | K^-1) and render their expected 2-D motion.  On CUDA tensors this is one fused kernel each
+    way; the per-ray camera algebra (K from K^-1) stays as tensor ops so that its gradient reaches rtk_vec."""
+    Rmat = rtk_vec[:, 0:9].reshape(N_rays, 1, 3, 3)
+    Tmat = rtk_vec[:, 9:12].reshape(N_rays, 1, 3)
+    K = mat2K(Kmatinv(rtk_vec[:, 12:21].reshape(N_rays, 1, 3, 3)))
+    S = weights_coarse.shape[-1]
+    if xyz_root.is_cuda and weights_coarse.dim() == 2 and weights_coarse.shape[0] == N_rays:
+        return FlowRenderFn.apply(xyz_root.reshape(N_rays, S, 3), Rmat.reshape(N_rays, 9), Tmat.reshape(N_rays, 3),
+                                  K.reshape(N_rays, 4), weights_coarse, xys.reshape(N_rays, 2), img_size)
+    return vrender_flo(weights_coarse, pinhole_cam(obj_to_cam(xyz_root, Rmat, Tmat), K), xys, img_size)
+
+
 def diff_flo(pts_target, xys, img_size):
     """geom_utils.py:1745-1757."""
     return (pts_target.reshape(xys.shape) - xys) / img_size * 2

@@ -126,15 +126,6 @@ def inference(models, embedding_xyz, xyz_, dir_, dir_embedded, z_vals, N_rays, N
     return rgb, feat, depth, weights, vis, sil
 
 
-def _project(xyz, rtk_vec, N_rays):
-    """rendering.py:428-449: root-frame points (N,S,3) -> pixels of the view described by rtk_vec (N,21)."""
-    Rmat = rtk_vec[:, 0:9].reshape(N_rays, 1, 3, 3)
-    Tmat = rtk_vec[:, 9:12].reshape(N_rays, 1, 3)
-    Kinv = rtk_vec[:, 12:21].reshape(N_rays, 1, 3, 3)
-    K = G.mat2K(G.Kmatinv(Kinv))
-    return G.pinhole_cam(G.obj_to_cam(xyz, Rmat, Tmat), K)
-
-
 def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays, embedding_xyz, rays_d, noise_std,
                      obj_bound, dir_embedded, z_vals, img_size, progress, opts, fine_iter=True, render_vis=False):
     """rendering.py:239-579: backward warp, cycle forward warp (+ the warps to the paired frames), trunk + feature +
@@ -267,10 +258,7 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
         if getattr(opts, "use_corr", False):
             result["corr_err"] = corr_err
         result["proj_err"] = proj_err / img_size * 2
-    if dist_corresp and "rtk_vec_target" in rays:   # :434-446
-        xyz_coarse_target = _project(xyz_coarse_target, rays["rtk_vec_target"], N_rays)
-    if dist_corresp and "rtk_vec_dentrg" in rays:   # :448-459
-        xyz_coarse_dentrg = _project(xyz_coarse_dentrg, rays["rtk_vec_dentrg"], N_rays)
+    # (the projections of the warped samples into the paired views, :434-459, happen together with the flow rendering below)
 
     result["xyz_camera_vis"] = xyz_coarse_frame
     if has_bones or has_flow:
@@ -286,7 +274,8 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
     flo_coarse = flo_valid = None
     if "rtk_vec_target" in rays:   # :480-489
         if dist_corresp:
-            flo_coarse, flo_valid = G.vrender_flo(weights_coarse, xyz_coarse_target, xys, img_size)
+            flo_coarse, flo_valid = G.project_render_flo(weights_coarse, xyz_coarse_target, rays["rtk_vec_target"], xys,
+                                                         img_size, N_rays)
         else:
             if pts_target is None:
                 raise RuntimeError("rtk_vec_target without dist_corresp needs opts.use_corresp (rendering.py:407-411)")
@@ -297,7 +286,8 @@ def inference_deform(xyz_coarse_sampled, rays, models, chunk, N_samples, N_rays,
         if not dist_corresp:
             raise NotImplementedError("rtk_vec_dentrg without dist_corresp reads an undefined variable in the reference "
                                       "(rendering.py:496)")
-        result["fdp_coarse"], result["fdp_valid"] = G.vrender_flo(weights_coarse, xyz_coarse_dentrg, xys, img_size)
+        result["fdp_coarse"], result["fdp_valid"] = G.project_render_flo(weights_coarse, xyz_coarse_dentrg,
+                                                                         rays["rtk_vec_dentrg"], xys, img_size, N_rays)
     if "img_at_samp" in rays:
         _per_ray_losses(result, rays, rgb_coarse, sil_coarse, is_training, flo_coarse, flo_valid)
     if "feats_at_samp" in rays:   # :572-578

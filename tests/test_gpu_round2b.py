@@ -337,3 +337,46 @@ def test_sinkhorn_match_fused_against_torch_ops_and_fp64():
         scale = float(r.abs().max())
         e_plain, e_fused = float((p - r).abs().max()) / scale, float((g - r).abs().max()) / scale
         assert e_fused < max(2e-5, 3 * e_plain), (name, e_fused, e_plain)
+
+
+def test_fused_flow_rendering_against_tensor_ops_fp64():
+    """project_render_flo on the fused kernels (csrc/flow.cu) against the tensor-op composition obj_to_cam -> pinhole_cam ->
+    vrender_flo in fp64: flow, validity flags and the gradients of points, weights and the camera vector; samples behind
+    the camera and far outside the image are in the batch (they must drop out of the sums and get no gradient); ragged
+    sample count and a ray count that is not a multiple of the warps per CTA."""
+    from moda_b200 import geom_utils as G
+    gen = torch.Generator().manual_seed(12)
+    N, S, img = 37, 45, 64.0
+    xyz0 = torch.randn(N, S, 3, generator=gen) * 0.3
+    xyz0[:, :, 2] += 3.0
+    xyz0[3, 5, 2] = -4.0            # behind the camera
+    xyz0[7, :, 0] += 40.0           # a whole ray far outside the image
+    xyz0[9, 11, 1] = 25.0
+    w0 = torch.rand(N, S, generator=gen)
+    A = torch.linalg.qr(torch.randn(N, 3, 3, generator=gen))[0]
+    T = torch.randn(N, 3, generator=gen) * 0.1
+    Kinv = torch.zeros(N, 3, 3)
+    fx = 60.0 + torch.rand(N, generator=gen) * 5
+    fy = 62.0 + torch.rand(N, generator=gen) * 5
+    Kinv[:, 0, 0], Kinv[:, 1, 1], Kinv[:, 2, 2] = 1 / fx, 1 / fy, 1.0
+    Kinv[:, 0, 2], Kinv[:, 1, 2] = -32.0 / fx, -30.0 / fy
+    rtk0 = torch.cat([A.reshape(N, 9), T, Kinv.reshape(N, 9)], -1)
+    xys = (torch.rand(N, 2, generator=gen) * img)
+    gout = torch.randn(N, 2, generator=gen)
+
+    def run(dtype, dev):
+        xyz = xyz0.to(dev, dtype).requires_grad_(True)
+        w = w0.to(dev, dtype).requires_grad_(True)
+        rtk = rtk0.to(dev, dtype).requires_grad_(True)
+        flo, valid = G.project_render_flo(w, xyz, rtk, xys.to(dev, dtype), img, N)
+        (flo * gout.to(dev, dtype)).sum().backward()
+        return [t.detach().double().cpu() for t in (flo, valid, xyz.grad, w.grad, rtk.grad)]
+
+    ref = run(torch.float64, "cpu")      # tensor-op composition
+    got = run(torch.float32, DEV)        # fused kernels
+    assert torch.equal(ref[1].reshape(-1), got[1].reshape(-1))
+    assert float(ref[1].sum()) < N       # the batch does contain rays with dropped samples
+    for name, r, g in zip(("flo", "valid", "d xyz", "d weights", "d rtk_vec"), ref, got):
+        scale = float(r.abs().max()) + 1e-30
+        assert float((g.reshape(r.shape) - r).abs().max()) / scale < 2e-5, name
+    assert float(got[2][3, 5].abs().max()) == 0.0 and float(got[3][7].abs().max()) == 0.0

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p gpurun_variants/obj_$name
-for f in api elementwise skin composite gemm sample_pdf raysum sinkhorn tc_gemm tc_support chain; do
+for f in api elementwise skin composite gemm sample_pdf raysum sinkhorn flow tc_gemm tc_support chain; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
     "$@" -I moda_b200/csrc -c moda_b200/csrc/$f.cu -o gpurun_variants/obj_$name/$f.o &
 done
