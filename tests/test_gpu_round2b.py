@@ -380,3 +380,27 @@ def test_fused_flow_rendering_against_tensor_ops_fp64():
         scale = float(r.abs().max()) + 1e-30
         assert float((g.reshape(r.shape) - r).abs().max()) / scale < 2e-5, name
     assert float(got[2][3, 5].abs().max()) == 0.0 and float(got[3][7].abs().max()) == 0.0
+
+
+def test_dense_target_flow_branch_equals_target_branch_on_the_same_frame():
+    """rendering.py:448-459, 491-499: the `dentrg` pair (bone_rts_dentrg / rtk_vec_dentrg -> fdp_coarse, fdp_valid) runs the
+    same third warp + projection + flow rendering as the target pair; fed the target frame's pose and camera it must
+    reproduce flo_coarse / flo_valid, and the result carries both key pairs."""
+    from moda_b200 import config, synth, models as MM
+    from moda_b200.rendering import render_rays
+    config.set_precision("fp16")
+    prob = synth.make_full_problem(16, seed=4)
+    models, emb, rays = MM.build_full_models(prob, DEV)
+    rays = dict(rays)
+    rays["bone_rts_dentrg"] = rays["bone_rts_target"].detach().clone()
+    rays["rtk_vec_dentrg"] = rays["rtk_vec_target"].detach().clone()
+    for m in ("coarse", "nerf_skin", "nerf_vis", "nerf_feat"):
+        models[m].train()
+    res = render_rays(models, emb, rays, N_samples=128, perturb=0, noise_std=0, chunk=32768,
+                      obj_bound=prob["obj_bound"].numpy(), img_size=prob["img_size"], opts=synth.full_opts())
+    assert res["fdp_coarse"].shape == res["flo_coarse"].shape and res["fdp_valid"].shape == res["flo_valid"].shape
+    assert torch.equal(res["fdp_valid"], res["flo_valid"])
+    d = (res["fdp_coarse"] - res["flo_coarse"]).detach().abs().max()
+    assert float(d) <= 1e-6 * float(res["flo_coarse"].detach().abs().max() + 1.0)
+    res["fdp_coarse"].sum().backward()      # the branch is differentiable down to the bones
+    assert models["bones_rst"].grad is not None and torch.isfinite(models["bones_rst"].grad).all()
