@@ -474,7 +474,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_rays=args.cpu_rays, repeats=2)
     # secondary figures of BASELINE.json's metric, folded into the same line so that the driver's BENCH / SCALE files
-    # carry them: the DQ-skinning microbench (configs[3], one GPU) and the density grid (configs[4], sharded over the ranks)
+    # carry them: the DQ-skinning microbench (configs[3], one GPU), the density grid (configs[4], sharded over the ranks) and
+    # the default-flag MoDA step (one GPU)
     extra = {}
     if not args.no_extra:
         torch.cuda.empty_cache()
@@ -483,6 +484,11 @@ def run_ours(args):
             extra["grid"] = g
         if world == 1:
             extra["dqs"] = measure_dqs(args, dev, with_cpu=False, steps=3)
+            try:   # the default-flag MoDA step (`--workload full` is the stand-alone form)
+                torch.cuda.empty_cache()
+                extra["full"] = measure_full(args, dev, steps=5)
+            except Exception as e:   # a secondary figure must not take the headline line down with it
+                extra["full"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         rays_s = R * world / (ms_step * 1e-3)
         out = {"metric": "train rays/s (128 samp/ray)", "value": round(rays_s, 1), "unit": "rays/s",
