@@ -65,6 +65,38 @@ def _stub_model(g, dev, with_dis):
     return m
 
 
+def test_project_render_flo_tensor_path_against_oracle():
+    """project_render_flo (rendering.py:434-459 + 480-499 for one paired frame) on CPU tensors -- the tensor-op path the
+    fused CUDA kernels are tested against on the GPU -- against the oracle's restatement of obj_to_cam / pinhole_cam /
+    vrender_flo, values and gradients, with samples behind the camera and outside the image in the batch."""
+    from moda_b200 import geom_utils as G
+    from oracle import restated as O
+    gen = torch.Generator().manual_seed(21)
+    N, S, img = 9, 17, 64.0
+    xyz0 = torch.randn(N, S, 3, generator=gen, dtype=torch.float64) * 0.3
+    xyz0[:, :, 2] += 3.0
+    xyz0[2, 4, 2] = -2.0
+    xyz0[5, :, 1] += 30.0
+    w0 = torch.rand(N, S, generator=gen, dtype=torch.float64)
+    Rm = torch.linalg.qr(torch.randn(N, 3, 3, generator=gen, dtype=torch.float64))[0]
+    Tm = torch.randn(N, 3, generator=gen, dtype=torch.float64) * 0.1
+    Kinv = torch.zeros(N, 3, 3, dtype=torch.float64)
+    Kinv[:, 0, 0], Kinv[:, 1, 1], Kinv[:, 2, 2], Kinv[:, 0, 2], Kinv[:, 1, 2] = 1 / 60.0, 1 / 62.0, 1.0, -32 / 60.0, -30 / 62.0
+    rtk0 = torch.cat([Rm.reshape(N, 9), Tm, Kinv.reshape(N, 9)], -1)
+    xys = torch.rand(N, 2, generator=gen, dtype=torch.float64) * img
+    gout = torch.randn(N, 2, generator=gen, dtype=torch.float64)
+    outs = []
+    for fn in (lambda w, x, r: G.project_render_flo(w, x, r, xys, img, N),
+               lambda w, x, r: O.vrender_flo(w, O.project(x, r), xys, img)):
+        xyz, w, rtk = (t.clone().requires_grad_(True) for t in (xyz0, w0, rtk0))
+        flo, valid = fn(w, xyz, rtk)
+        (flo * gout).sum().backward()
+        outs.append((flo.detach(), valid.detach().reshape(-1), xyz.grad, w.grad, rtk.grad))
+    assert float(outs[0][1].sum()) < N
+    for a, b in zip(*outs):
+        assert max_abs(a, b.numpy()) < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["fp32", "fp16"])
 def test_pose_head_rest_pose_correction_and_mesh_warps_against_reference(mode):
