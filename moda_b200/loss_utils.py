@@ -60,12 +60,85 @@ def feat_match_loss(nerf_feat, embedding_xyz, feats, pts, pts_prob, bound, use_c
     return pts_pred, pts_exp, feat_err, corr_err
 
 
-def _fused_ok(feats, vol_feat):
-    """The one-pass Sinkhorn kernels (csrc/sinkhorn.cu) take 16-channel fp32 CUDA features and a lattice of m % 4 == 0, m <=
-    8192 points; anything else (the CPU oracle tests, other feature widths) runs the same algebra as torch ops."""
+# ---------------------------------------------------------------------------------------- Sinkhorn feature matching
+# Every (rays x lattice)-sized operation of the matching is one of five primitives.  On 16-channel fp32 CUDA features they
+# are the one-pass kernels of csrc/sinkhorn.cu; on anything else (CPU tensors of the oracle tests, fp64, other feature
+# widths) the same primitive is a tensor op, so the algebra of SinkhornMatchFn below exists once and is pinned on the CPU
+# against autograd through the reference's loop (tests/test_oracle.py) and on the GPU against itself in fp64.
+_USE_KERNELS = True   # tests switch the kernels off to compare them with the tensor-op primitives on the same device
+
+
+def _sk_use_kernels(feats, vol_feat):
     m = vol_feat.shape[0]
-    return (feats.is_cuda and feats.dtype == torch.float32 and vol_feat.dtype == torch.float32 and feats.shape[1] == 16 and
-            vol_feat.shape[1] == 16 and m % 4 == 0 and m <= 8192 and feats.shape[0] > 0)
+    return (_USE_KERNELS and feats.is_cuda and feats.dtype == torch.float32 and vol_feat.dtype == torch.float32 and
+            feats.shape[1] == 16 and vol_feat.shape[1] == 16 and m % 4 == 0 and m <= 8192 and feats.shape[0] > 0)
+
+
+def _sk_matrix(feats, vol_feat, eps, use, c_out=None):
+    """K = exp((F V^T - 1) / eps) and the first column sums c_1 = K^T a_0 with a_0 = 1/n (moda_sinkhorn_matrix)."""
+    n, m = feats.shape[0], vol_feat.shape[0]
+    if use:
+        K = torch.empty(n, m, device=feats.device, dtype=torch.float32)
+        c = c_out if c_out is not None else torch.zeros(m, device=feats.device, dtype=torch.float32)
+        call("moda_sinkhorn_matrix", ptr(feats), ptr(vol_feat), n, m, feats.shape[1], eps, 1.0 / n, ptr(K), ptr(c), stream())
+        return K, c
+    K = torch.exp((feats.matmul(vol_feat.t()) - 1.0) / eps)
+    return K, K.sum(0) / n
+
+
+def _sk_pass(K, use, mode, p, delta, u=None, v=None, xmode=0, x=None, xc=None, xg=None, xb=None, xp=0.0, want_y=True,
+             want_w=True, w_out=None):
+    """One pass over K (moda_sinkhorn_pass): the input vector x (given, or xp / (xc + delta), or -xg xb / (xc + delta)),
+    y = K x, z = p / (y + delta) (mode 0) or -y u / (v + delta) (mode 1), w = K^T z.  Returns (x, y, z, w)."""
+    n, m = K.shape
+    if use:
+        new = lambda k: torch.empty(k, device=K.device, dtype=torch.float32)
+        xo = x if xmode == 0 else new(m)
+        y = new(n) if want_y else None
+        z = new(n)
+        w = None
+        if want_w:
+            w = w_out if w_out is not None else torch.zeros(m, device=K.device, dtype=torch.float32)
+        call("moda_sinkhorn_pass", ptr(K), n, m, ptr(x) if xmode == 0 else None, ptr(y), ptr(z), ptr(w), mode, p, delta,
+             ptr(u), ptr(v), xmode, ptr(xc), ptr(xg), ptr(xb), xp, ptr(xo) if xmode else None, stream())
+        return xo, y, z, w
+    if xmode == 1:
+        x = xp / (xc + delta)
+    elif xmode == 2:
+        x = -xg * xb / (xc + delta)
+    y = torch.mv(K, x)
+    z = p / (y + delta) if mode == 0 else -y * u / (v + delta)
+    return x, y, z, (torch.mv(K.t(), z) if want_w else None)
+
+
+def _sk_rows4(K, X, use):
+    """K X for X (m, 4) (moda_sinkhorn_rows4)."""
+    if use:
+        out = torch.empty(K.shape[0], 4, device=K.device, dtype=torch.float32)
+        call("moda_sinkhorn_rows4", ptr(K), K.shape[0], K.shape[1], ptr(X.contiguous()), ptr(out), stream())
+        return out
+    return K.matmul(X)
+
+
+def _sk_cols4(K, Wt, use):
+    """K^T Wt for Wt (n, 4) (moda_sinkhorn_cols4)."""
+    if use:
+        out = torch.zeros(K.shape[1], 4, device=K.device, dtype=torch.float32)
+        call("moda_sinkhorn_cols4", ptr(K), K.shape[0], K.shape[1], ptr(Wt.contiguous()), ptr(out), stream())
+        return out
+    return K.t().matmul(Wt)
+
+
+def _sk_gcost(K, L, Rm, feats, vol_feat, eps, use):
+    """gF = gcost V and gV = gcost^T F for gcost = K / eps * (L Rm), never materialised on the kernel path
+    (moda_sinkhorn_gcost, factor rank 44)."""
+    if use and L.shape[1] == 44:
+        gF, gV = torch.zeros_like(feats), torch.zeros_like(vol_feat)
+        call("moda_sinkhorn_gcost", ptr(K), K.shape[0], K.shape[1], ptr(L.contiguous()), ptr(Rm.contiguous()), 44, ptr(feats),
+             ptr(vol_feat), feats.shape[1], eps, ptr(gF), ptr(gV), stream())
+        return gF, gV
+    gcost = K * L.matmul(Rm) / eps
+    return gcost.matmul(vol_feat), gcost.t().matmul(feats)
 
 
 class SinkhornMatchFn(torch.autograd.Function):
@@ -76,138 +149,68 @@ class SinkhornMatchFn(torch.autograd.Function):
     with c_i = K^T a_{i-1}, b_i = p2 / (c_i + d), d_i = K b_i, a_i = p1 / (d_i + d) the reverse sweep is
         gc_i = -gb_i b_i / (c_i + d);  gK += a_{i-1} (x) gc_i;  ga_{i-1} = K gc_i;
         gd_{i-1} = -ga_{i-1} a_{i-1} / (d_{i-1} + d);  gK += gd_{i-1} (x) b_{i-1};  gb_{i-1} = K^T gd_{i-1}
-    so gK is a rank-40 sum plus the direct term, formed once.  Verified against autograd through the reference's loop
-    to 1e-15 in fp64 (tests/test_oracle.py)."""
+    so dLoss/dK is a sum of 39 outer products plus the direct term U (.) b_20, U[r][j] = (g_r . Q_j - g_r . pts_r) / s_r, which
+    has rank 4: it is kept as factors L (N, 44), Rm (44, M) and consumed as gcost = K / eps * (L Rm) by one kernel that never
+    writes it.  One pass over K per iteration (b_i from c_i while staged, d_i, a_i and c_{i+1} with the rows still on chip),
+    one for the matrix itself, one for the soft-argmax, one for the direct term of the adjoint.  Verified against autograd
+    through the reference's loop to 1e-12 in fp64 (tests/test_oracle.py)."""
     EPS, DELTA, ITERS = 0.03, 1e-8, 20
 
     @staticmethod
     def forward(ctx, feats, vol_feat, query):
-        if _fused_ok(feats, vol_feat):
-            return SinkhornMatchFn._forward_fused(ctx, feats, vol_feat, query)
-        K = torch.exp((feats.matmul(vol_feat.t()) - 1.0) / SinkhornMatchFn.EPS)
-        n, m = K.shape
-        a = torch.full((n,), 1.0 / n, device=K.device, dtype=K.dtype)
-        As, Bs, Cs, Ds = [a], [], [], []
-        dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
-        for _ in range(it):
-            c = torch.mv(K.t(), a)
-            b = (1.0 / m) / (c + dl)
-            d = torch.mv(K, b)
-            a = (1.0 / n) / (d + dl)
-            As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
-        # T = a K b^T row-normalised: with the final a this is K b^T / rowsum; the reference normalises a K b^T whose row
-        # sums are a_20 (K b_20): identical up to rounding
-        s = Ds[-1]
-        pts = (K * Bs[-1][None]).matmul(query) / s[:, None]
-        ctx.fused = False
-        ctx.save_for_backward(feats, vol_feat, query, K, pts, s)
-        ctx.hist = (As, Bs, Cs, Ds)
-        return pts
-
-    @staticmethod
-    def _forward_fused(ctx, feats, vol_feat, query):
-        """The same iteration with every (n x m)-sized operation as one pass over K (csrc/sinkhorn.cu): the matrix is written
-        once together with the first column sums (moda_sinkhorn_matrix); each iteration is ONE pass (moda_sinkhorn_pass: b_i
-        from c_i while it is staged, d_i = K b_i, a_i = p1 / (d_i + delta) and, with the rows still on chip, c_{i+1} = K^T
-        a_i); the soft-argmax is one pass with four vectors (moda_sinkhorn_rows4)."""
         feats, vol_feat, query = feats.contiguous(), vol_feat.contiguous(), query.contiguous()
+        use = _sk_use_kernels(feats, vol_feat)
         n, m, dev = feats.shape[0], vol_feat.shape[0], feats.device
         dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
-        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
-        K = new(n, m)
-        acc = torch.zeros(it, m, device=dev, dtype=torch.float32)     # the column sums c_1 .. c_20: one fill
-        call("moda_sinkhorn_matrix", ptr(feats), ptr(vol_feat), n, m, feats.shape[1], SinkhornMatchFn.EPS, 1.0 / n, ptr(K),
-             ptr(acc[0]), stream())
-        As, Bs, Cs, Ds = [torch.full((n,), 1.0 / n, device=dev, dtype=torch.float32)], [], [], []
-        hist = new(it, m)                                                  # b_1 .. b_20
-        rows = new(2 * it, n)                                              # d_i, a_i
+        acc = torch.zeros(it, m, device=dev, dtype=torch.float32) if use else None    # c_1 .. c_20: one fill
+        K, c = _sk_matrix(feats, vol_feat, SinkhornMatchFn.EPS, use, acc[0] if use else None)
+        As, Bs, Cs, Ds = [torch.full((n,), 1.0 / n, device=dev, dtype=K.dtype)], [], [], []
         for i in range(it):
-            c, b, d, a = acc[i], hist[i], rows[2 * i], rows[2 * i + 1]
-            c_next = acc[i + 1] if i + 1 < it else None
-            call("moda_sinkhorn_pass", ptr(K), n, m, None, ptr(d), ptr(a), ptr(c_next), 0, 1.0 / n, dl, None, None,
-                 1, ptr(c), None, None, 1.0 / m, ptr(b), stream())
+            last = i + 1 == it
+            b, d, a, c_next = _sk_pass(K, use, 0, 1.0 / n, dl, xmode=1, xc=c, xp=1.0 / m, want_w=not last,
+                                       w_out=acc[i + 1] if use and not last else None)
             As.append(a), Bs.append(b), Cs.append(c), Ds.append(d)
-        # pts = (K b) Q / rowsum: X = b (x) [Qx Qy Qz 1]; the fourth product is the row sum d_20 again
-        X = torch.cat([query, torch.ones_like(query[:, :1])], 1) * Bs[-1][:, None]
-        out4 = new(n, 4)
-        call("moda_sinkhorn_rows4", ptr(K), n, m, ptr(X), ptr(out4), stream())
+            c = c_next
+        # T = a K b^T row-normalised: with the final a this is K b^T / rowsum; the reference normalises a K b^T whose row
+        # sums are a_20 (K b_20): identical up to rounding.  X = b (x) [Qx Qy Qz 1]: the fourth product is the row sum again
         s = Ds[-1]
-        pts = out4[:, :3] / s[:, None]
-        ctx.fused = True
+        X = torch.cat([query, torch.ones_like(query[:, :1])], 1) * Bs[-1][:, None]
+        pts = _sk_rows4(K, X, use)[:, :3] / s[:, None]
+        ctx.use = use
         ctx.save_for_backward(feats, vol_feat, query, K, pts, s)
         ctx.hist = (As, Bs, Cs, Ds)
         return pts
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.fused:
-            return SinkhornMatchFn._backward_fused(ctx, g)
         feats, vol_feat, query, K, pts, s = ctx.saved_tensors
         As, Bs, Cs, Ds = ctx.hist
-        dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
-        b20 = Bs[-1]
-        U = (g.matmul(query.t()) - (g * pts).sum(-1, keepdim=True)) / s[:, None]   # dL / d(K_nj b_j)
-        gb = (U * K).sum(0)
-        gK = U * b20[None]
-        left, right = [], []            # gK += sum_k left_k (x) right_k
-        for i in range(it, 0, -1):
-            gc = -gb * Bs[i - 1] / (Cs[i - 1] + dl)
-            left.append(As[i - 1]), right.append(gc)
-            if i - 1 < 1:
-                break
-            ga = torch.mv(K, gc)
-            gd = -ga * As[i - 1] / (Ds[i - 2] + dl)
-            gb = torch.mv(K.t(), gd)
-            left.append(gd), right.append(Bs[i - 2])
-        gK.addmm_(torch.stack(left, 1), torch.stack(right, 0))
-        gcost = gK.mul_(K).mul_(1.0 / SinkhornMatchFn.EPS)
-        gq = None
-        if ctx.needs_input_grad[2]:
-            gq = (K * b20[None] / s[:, None]).t().matmul(g)
-        return gcost.matmul(vol_feat), gcost.t().matmul(feats), gq
-
-    @staticmethod
-    def _backward_fused(ctx, g):
-        """The reverse sweep with one pass over K per iteration, and dLoss/dK kept in factored form: the direct term
-        U (.) b_20 with U[r][j] = (g_r . Q_j - g_r . pts_r) / s_r has rank 4 and the sweep adds 39 outer products, so
-        gcost = K / eps * (L Rm) with L (n, 44), Rm (44, m) is consumed tile by tile (moda_sinkhorn_gcost) and never
-        written."""
-        feats, vol_feat, query, K, pts, s = ctx.saved_tensors
-        As, Bs, Cs, Ds = ctx.hist
+        use = ctx.use
         dl, it = SinkhornMatchFn.DELTA, SinkhornMatchFn.ITERS
         n, m, dev = K.shape[0], K.shape[1], K.device
-        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
-        g = g.contiguous().float()
+        g = g.contiguous().to(K.dtype)
         b20 = Bs[-1]
-        RANK = 44                       # 4 (direct term) + 20 (a_{i-1} (x) gc_i) + 19 (gd_{i-1} (x) b_{i-1}) + 1 zero
-        L, Rm = torch.zeros(n, RANK, device=dev, dtype=torch.float32), torch.zeros(RANK, m, device=dev, dtype=torch.float32)
-        # direct term: U = alpha . Q^T - beta with alpha = g / s, beta = (g . pts) / s
-        L[:, 0:3] = g / s[:, None]
-        L[:, 3] = -(g * pts).sum(-1) / s
-        Rm[0:3] = query.t() * b20[None]
-        Rm[3] = b20
+        # direct term: dL / d(K_rj b_j) = U[r][j] = alpha_r . Q_j - beta_r with alpha = g / s, beta = (g . pts) / s
+        Wt = torch.cat([g / s[:, None], (-(g * pts).sum(-1) / s)[:, None]], 1)          # (n, 4) = [alpha | -beta]
         # gb_20 = sum_r K[r][j] U[r][j] = Q_j . (K^T alpha)_j - (K^T beta)_j: one pass with four row-weight vectors
-        cols = torch.zeros(m, 4, device=dev, dtype=torch.float32)
-        call("moda_sinkhorn_cols4", ptr(K), n, m, ptr(L[:, 0:4].contiguous()), ptr(cols), stream())
+        cols = _sk_cols4(K, Wt, use)
         gb = ((cols[:, 0:3] * query).sum(-1) + cols[:, 3]).contiguous()
-        acc = torch.zeros(it, m, device=dev, dtype=torch.float32)       # gb_{i-1}: column sums of the passes
-        gds = new(it - 1, n)
-        # factor columns 4, 6, .. 42: a_{i-1} (x) gc_i for i = 20 .. 1; columns 5, 7, .. 41: gd_{i-1} (x) b_{i-1} for i = 20 .. 2
-        for q, i in enumerate(range(it, 1, -1)):
-            # gc_i = -gb_i b_i / (c_i + delta) formed while staged (and written to its row of Rm), ga = K gc_i,
-            # gd = -ga a_{i-1} / (d_{i-1} + delta), gb_{i-1} = K^T gd: one pass over K
-            gb_next = acc[i - 1]
-            call("moda_sinkhorn_pass", ptr(K), n, m, None, None, ptr(gds[q]), ptr(gb_next), 1, 0.0, dl, ptr(As[i - 1]),
-                 ptr(Ds[i - 2]), 2, ptr(Cs[i - 1]), ptr(gb), ptr(Bs[i - 1]), 0.0, ptr(Rm[4 + 2 * q]), stream())
-            gb = gb_next
-        Rm[4 + 2 * (it - 1)] = -gb * Bs[0] / (Cs[0] + dl)
-        L[:, 4:4 + 2 * it:2] = torch.stack([As[i - 1] for i in range(it, 0, -1)], 1)
-        L[:, 5:5 + 2 * (it - 1):2] = gds.t()
-        Rm[5:5 + 2 * (it - 1):2] = torch.stack([Bs[i - 2] for i in range(it, 1, -1)], 0)
-        gF = torch.zeros_like(feats)
-        gV = torch.zeros_like(vol_feat)
-        call("moda_sinkhorn_gcost", ptr(K), n, m, ptr(L), ptr(Rm), RANK, ptr(feats), ptr(vol_feat), feats.shape[1],
-             SinkhornMatchFn.EPS, ptr(gF), ptr(gV), stream())
+        acc = torch.zeros(it, m, device=dev, dtype=torch.float32) if use else None      # gb_{i-1}: column sums of the passes
+        left, right = [], []            # dLoss/dK = U (.) b_20 + sum_k left_k (x) right_k
+        for i in range(it, 1, -1):
+            # gc_i = -gb_i b_i / (c_i + delta) formed while staged, ga = K gc_i, gd = -ga a_{i-1} / (d_{i-1} + delta),
+            # gb_{i-1} = K^T gd: one pass over K
+            gc, _, gd, gb = _sk_pass(K, use, 1, 0.0, dl, u=As[i - 1], v=Ds[i - 2], xmode=2, xc=Cs[i - 1], xg=gb, xb=Bs[i - 1],
+                                     want_y=False, w_out=acc[i - 1] if use else None)
+            left += [As[i - 1], gd]
+            right += [gc, Bs[i - 2]]
+        left.append(As[0])
+        right.append(-gb * Bs[0] / (Cs[0] + dl))
+        rank = 4 + len(left)
+        pad = (-rank) % 4
+        L = torch.cat([Wt, torch.stack(left, 1), torch.zeros(n, pad, device=dev, dtype=K.dtype)], 1)
+        Rm = torch.cat([query.t() * b20[None], b20[None], torch.stack(right, 0), torch.zeros(pad, m, device=dev, dtype=K.dtype)], 0)
+        gF, gV = _sk_gcost(K, L, Rm, feats, vol_feat, SinkhornMatchFn.EPS, use)
         gq = None
         if ctx.needs_input_grad[2]:
             gq = (K * b20[None] / s[:, None]).t().matmul(g)

@@ -307,8 +307,9 @@ def test_sinkhorn_matrix_rows_cols_gcost_against_fp64():
 
 
 def test_sinkhorn_match_fused_against_torch_ops_and_fp64():
-    """SinkhornMatchFn on the one-pass kernels against the same algebra as torch ops (the path the CPU oracle test pins
-    against autograd through the reference's loop) in fp64: matched points and the gradients of both feature sets."""
+    """SinkhornMatchFn with its five primitives on the one-pass kernels against the same algebra with tensor-op primitives
+    (the form the CPU oracle test pins against autograd through the reference's loop) in fp64 and fp32: matched points and
+    the gradients of both feature sets."""
     from moda_b200 import loss_utils as LU
     import torch.nn.functional as F
     gen = torch.Generator().manual_seed(11)
@@ -321,13 +322,12 @@ def test_sinkhorn_match_fused_against_torch_ops_and_fp64():
     def run(dtype, fused):
         f = f0.to(DEV, dtype).requires_grad_(True)
         v = v0.to(DEV, dtype).requires_grad_(True)
-        ok = LU._fused_ok
-        LU._fused_ok = (lambda a, b: ok(a, b)) if fused else (lambda a, b: False)
+        LU._USE_KERNELS = fused
         try:
             pts = LU.SinkhornMatchFn.apply(F.normalize(f, 2, -1), F.normalize(v, 2, -1), q.to(dtype))
             (pts * gout.to(dtype)).sum().backward()
         finally:
-            LU._fused_ok = ok
+            LU._USE_KERNELS = True
         return pts.detach().double(), f.grad.double(), v.grad.double()
 
     ref = run(torch.float64, False)
